@@ -1,0 +1,227 @@
+"""CPU oracle for the NCA step hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in explicit tensor arithmetic, the algorithm of the reference's
+NCA step so the CUDA path can be checked against it.  It is NOT a product path:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import it.  The product (the package under
+``video-stylization-with-nca_b200/``) never imports anything from ``oracle/`` and
+fails loudly when its CUDA library is missing.
+
+Parity status: the reference ships no tests, golden vectors or fixtures for this path
+ so parity is pinned against the reference ITSELF: ``oracle/make_golden.py``
+imports the unmodified reference modules from /root/reference in the build container and
+commits their outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks this
+restatement against those vectors (and, when /root/reference is present, live).
+
+Reference lines followed (all fp32, NCHW):
+  * DyNCA filters / perception / multi-scale / step / rollout:
+      ExtraChannels/models/dynca.py:63-69, 71-96, 98-111, 113-128, 130-131, 158-167
+      ConditioneDyNCA/models/dynca.py:117-138 (cond_img path), 182-213 (EdgeExtractor)
+  * CPE2D positional encoding: ExtraChannels/models/dynca.py:180-207
+  * ConditionedNCA (encoder-conditioned): EncoderConditioning/nca.py:29-58, 99-110, 152-209
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+PAD_MODES = ("constant", "circular", "replicate", "reflect")
+
+
+# --------------------------------------------------------------------------------------
+# index maps for a 1-px border, per axis (F.pad semantics; dynca.py:81)
+# --------------------------------------------------------------------------------------
+def _shift(x: torch.Tensor, dy: int, dx: int, mode: str) -> torch.Tensor:
+    """Return s with s[..., i, j] = x_padded[..., i+dy, j+dx] for dy, dx in {-1,0,1}."""
+    H, W = x.shape[-2:]
+
+    def idx(n: int, d: int):
+        i = torch.arange(n) + d
+        if mode == "circular":
+            return i % n, None
+        if mode == "replicate":
+            return i.clamp(0, n - 1), None
+        if mode == "reflect":
+            i = torch.where(i < 0, -i, i)
+            i = torch.where(i > n - 1, 2 * (n - 1) - i, i)
+            return i, None
+        if mode == "constant":
+            valid = (i >= 0) & (i < n)
+            return i.clamp(0, n - 1), valid
+        raise ValueError(mode)
+
+    iy, vy = idx(H, dy)
+    ix, vx = idx(W, dx)
+    s = x.index_select(-2, iy).index_select(-1, ix)
+    if vy is not None:
+        s = s * vy.to(x.dtype)[:, None] * vx.to(x.dtype)[None, :]
+    return s
+
+
+# unnormalised filters, cross-correlation taps w[a][b] applied to x[i+a-1, j+b-1]
+SOBEL_X = ((-1.0, 0.0, 1.0), (-2.0, 0.0, 2.0), (-1.0, 0.0, 1.0))   # d/dW  (dynca.py:63)
+SOBEL_Y = ((-1.0, -2.0, -1.0), (0.0, 0.0, 0.0), (1.0, 2.0, 1.0))   # d/dH  (dynca.py:65)
+LAPLACE = ((1.0, 2.0, 1.0), (2.0, -12.0, 2.0), (1.0, 2.0, 1.0))    # dynca.py:68
+
+
+def _stencil(x: torch.Tensor, taps, mode: str) -> torch.Tensor:
+    out = torch.zeros_like(x)
+    for a in range(3):
+        for b in range(3):
+            w = taps[a][b]
+            if w != 0.0:
+                out = out + w * _shift(x, a - 1, b - 1, mode)
+    return out
+
+
+def down2(x: torch.Tensor) -> torch.Tensor:
+    """bilinear, align_corners=False, exact /2 on even dims == 2x2 mean (dynca.py:73-77)."""
+    H, W = x.shape[-2:]
+    assert H % 2 == 0 and W % 2 == 0
+    return 0.25 * (x[..., 0::2, 0::2] + x[..., 0::2, 1::2] + x[..., 1::2, 0::2] + x[..., 1::2, 1::2])
+
+
+def _up_axis(x: torch.Tensor, dim: int) -> torch.Tensor:
+    n = x.shape[dim]
+    i = torch.arange(n)
+    lo = x.index_select(dim, (i - 1).clamp(0, n - 1))
+    hi = x.index_select(dim, (i + 1).clamp(0, n - 1))
+    even = 0.25 * lo + 0.75 * x          # dst 2Q   <- src Q-0.25
+    odd = 0.75 * x + 0.25 * hi           # dst 2Q+1 <- src Q+0.25
+    st = torch.stack([even, odd], dim=dim + 1 if dim >= 0 else dim)
+    shp = list(x.shape)
+    shp[dim] = 2 * n
+    return st.reshape(shp)
+
+
+def up2(x: torch.Tensor) -> torch.Tensor:
+    """bilinear x2 upsample, align_corners=False, edge clamped (dynca.py:93-94)."""
+    x = _up_axis(x, x.dim() - 2)
+    x = _up_axis(x, x.dim() - 1)
+    return x
+
+
+def perceive(x: torch.Tensor, scale: int, mode: str) -> torch.Tensor:
+    """[B,C,H,W] -> [B,4C,H,W], channel blocks [id | sobel_x | sobel_y | lap] (dynca.py:71-96)."""
+    H, W = x.shape[-2:]
+    if scale == 1:
+        x = down2(x)
+    elif scale > 1:
+        x = F.interpolate(x, size=(H // 2 ** scale, W // 2 ** scale), mode="bilinear", align_corners=False)
+    y = torch.cat([x, _stencil(x, SOBEL_X, mode), _stencil(x, SOBEL_Y, mode), _stencil(x, LAPLACE, mode)], dim=1)
+    if scale == 1:
+        y = up2(y)
+    elif scale > 1:
+        y = F.interpolate(y, size=(H, W), mode="bilinear", align_corners=False)
+    return y
+
+
+def cpe2d(B: int, H: int, W: int) -> torch.Tensor:
+    """Cartesian positional encoding [B,2,H,W] (dynca.py:180-207)."""
+    xs = torch.arange(H) / H
+    ys = torch.arange(W) / W
+    xs = 2.0 * (xs - 0.5 + 0.5 / H)
+    ys = 2.0 * (ys - 0.5 + 0.5 / W)
+    emb = torch.zeros(2, H, W)
+    emb[0] = xs[:, None]
+    emb[1] = ys[None, :]
+    return emb[None].repeat(B, 1, 1, 1)
+
+
+def edge_extract(img: torch.Tensor, transform: str = "tanh") -> torch.Tensor:
+    """CD EdgeExtractor: zero-padded sobel_x, sobel_y, laplacian of a 1-ch image
+    (ConditioneDyNCA/models/dynca.py:182-213)."""
+    e = torch.cat([_stencil(img, SOBEL_X, "constant"), _stencil(img, SOBEL_Y, "constant"),
+                   _stencil(img, LAPLACE, "constant")], dim=1)
+    return torch.tanh(e) if transform == "tanh" else e
+
+
+def perceive_multiscale(x, scales: Sequence[int], mode: str, cond: Optional[torch.Tensor]):
+    y = sum(perceive(x, s, mode) for s in scales) / len(scales)          # dynca.py:98-106
+    if cond is not None:
+        y = torch.cat([y, cond], dim=1)                                  # dynca.py:108-109
+    return y
+
+
+def dynca_mask_from_uniform(u: torch.Tensor, rate: float) -> torch.Tensor:
+    """floor(u + rate), u in [0,1) (dynca.py:121)."""
+    return (u + rate).floor()
+
+
+def dynca_step(x, w1, b1, w2, b2, mask, scales=(0,), mode="circular", cond=None):
+    """One DyNCA step with a SUPPLIED fire mask [B,1,H,W] (dynca.py:113-123).
+
+    w1: [fc, 4C+cc], b1: [fc], w2: [C, fc], b2: [C]."""
+    z = perceive_multiscale(x, scales, mode, cond)
+    h = torch.relu(torch.einsum("jk,bkhw->bjhw", w1, z) + b1[None, :, None, None])
+    y = torch.einsum("cj,bjhw->bchw", w2, h) + b2[None, :, None, None]
+    return x + y * mask
+
+
+def dynca_rollout(x, w1, b1, w2, b2, masks, scales=(0,), mode="circular", cond=None, keep=False):
+    """T steps (dynca.py:158-167). masks: [T,B,1,H,W]. Returns final state (and all states if keep)."""
+    hist = [x]
+    for t in range(masks.shape[0]):
+        x = dynca_step(x, w1, b1, w2, b2, masks[t], scales, mode, cond)
+        if keep:
+            hist.append(x)
+    return (x, hist) if keep else x
+
+
+# --------------------------------------------------------------------------------------
+# EncoderConditioning/nca.py
+# --------------------------------------------------------------------------------------
+def enc_alive(x, living_dim: int, thr: float = 0.1):
+    """nca.py:152-163 : 3x3 max-pool (-inf padded) of the living channel > thr."""
+    a = x[:, living_dim:living_dim + 1]
+    B, _, H, W = a.shape
+    p = torch.full((B, 1, H + 2, W + 2), -math.inf, dtype=a.dtype)
+    p[:, :, 1:-1, 1:-1] = a
+    m = p[:, :, 1:-1, 1:-1]
+    for dy in range(3):
+        for dx in range(3):
+            m = torch.maximum(m, p[:, :, dy:dy + H, dx:dx + W])
+    return m > thr
+
+
+def enc_perception(x, wp):
+    """Learned depthwise 3x3, zero pad, out channel j reads in channel j//3 (nca.py:99-107).
+    wp: [3C,1,3,3] (cross-correlation)."""
+    B, C, H, W = x.shape
+    outs = []
+    for j in range(3 * C):
+        c = j // 3
+        taps = [[float(wp[j, 0, a, b]) for b in range(3)] for a in range(3)]
+        outs.append(_stencil(x[:, c:c + 1], taps, "constant"))
+    return torch.cat(outs, dim=1)
+
+
+def enc_perception_fast(x, wp):
+    C = x.shape[1]
+    return F.conv2d(x, wp, padding=1, groups=C)
+
+
+def enc_step(x, goal, wp, wa, ba, wb, bb, wc, fire, living_dim=3, thr=0.1, fast=True):
+    """nca.py:176-195 with a SUPPLIED fire mask (float [B,1,H,W], = (u < rate))."""
+    pre = enc_alive(x, living_dim, thr)
+    xin = x + goal * pre
+    p = enc_perception_fast(xin, wp) if fast else enc_perception(xin, wp)
+    h1 = torch.relu(torch.einsum("jk,bkhw->bjhw", wa, p) + ba[None, :, None, None])
+    h2 = torch.relu(torch.einsum("jk,bkhw->bjhw", wb, h1) + bb[None, :, None, None])
+    out = torch.einsum("cj,bjhw->bchw", wc, h2)
+    x = x + fire * out
+    post = enc_alive(x, living_dim, thr)
+    x = x * (pre & post).to(x.dtype)
+    return torch.clamp(x, -10.0, 10.0)
+
+
+def enc_rollout(x, goal, wp, wa, ba, wb, bb, wc, fires, living_dim=3, thr=0.1, keep=False):
+    hist = [x]
+    for t in range(fires.shape[0]):
+        x = enc_step(x, goal, wp, wa, ba, wb, bb, wc, fires[t], living_dim, thr)
+        if keep:
+            hist.append(x)
+    return (x, hist) if keep else x
