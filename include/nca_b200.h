@@ -1,0 +1,158 @@
+/*
+ * nca_b200.h — C ABI of the B200-native NCA step (libnca_b200.so).
+ *
+ * The reference (smehra34/Video-Stylization-with-NCA) has no FFI layer: its boundary for this
+ * path is the Python nn.Module API of DyNCA / ConditionedNCA.  These entry points
+ * are what a torch-side binding of that API calls; each one names the reference code it replaces.
+ * Plain C types only: device pointers, sizes, a cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - all tensors fp32, contiguous, NCHW, resident on the current CUDA device;
+ *   - the callee never allocates, frees or retains device memory: state history, gradients and
+ *     workspace are caller-owned (query sizes with the *_workspace_bytes functions);
+ *   - every launch goes to `stream`; no internal synchronisation; graph-capturable;
+ *   - return value 0 = ok, negative = error (message: nca_last_error(), thread local);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns NCA_ERR_CUDA.
+ */
+#ifndef NCA_B200_H_
+#define NCA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCA_B200_ABI_VERSION 1
+
+enum { NCA_OK = 0, NCA_ERR_ARG = -1, NCA_ERR_UNSUPPORTED = -2, NCA_ERR_CUDA = -3, NCA_ERR_WORKSPACE = -4 };
+
+/* padding_mode of DyNCA.perceive_torch (ExtraChannels/models/dynca.py:81) */
+enum { NCA_PAD_CONSTANT = 0, NCA_PAD_CIRCULAR = 1, NCA_PAD_REPLICATE = 2, NCA_PAD_REFLECT = 3 };
+/* conditioning inputs appended to the perception vector (dynca.py:108-109) */
+enum { NCA_COND_NONE = 0,   /* pos_emb=None / conditioning=None                                   */
+       NCA_COND_CPE = 1,    /* CPE2D computed in-kernel from coordinates (dynca.py:180-207), cc=2 */
+       NCA_COND_TENSOR = 2  /* caller-supplied [B,cc,H,W] (CD: EdgeExtractor output, cc=3)        */ };
+/* arithmetic of the update MLP */
+enum { NCA_PREC_FP32 = 0,   /* CUDA-core FFMA, parity 1e-5 per step                      */
+       NCA_PREC_BF16 = 1    /* tcgen05 BF16 operands, fp32 accumulate in TMEM, parity 1e-2 */ };
+/* fire mask source */
+enum { NCA_MASK_SUPPLIED = 0, /* float [T,B,1,H,W], 1 = fire (parity runs)                 */
+       NCA_MASK_PHILOX = 1    /* in-kernel Philox4x32-10 keyed on (seed, t0+t, b, y, x)    */ };
+
+/* Describes one DyNCA model + batch geometry.  Replaces the ctor arguments of
+ * ExtraChannels/models/dynca.py:30-69 and ConditioneDyNCA/models/dynca.py:30-73. */
+typedef struct NcaDyncaDesc {
+    int32_t B, C, H, W;      /* state [B,C,H,W]                                                 */
+    int32_t fc;              /* hidden width of the update MLP (fc_dim)                          */
+    int32_t cond_kind;       /* NCA_COND_*                                                       */
+    int32_t cc;              /* number of cond channels (0, 2 for CPE, any for TENSOR)           */
+    int32_t pad_mode;        /* NCA_PAD_*                                                        */
+    int32_t n_scales;        /* 1: perception_scales=[0]; 2: [0,1]  (H and W even)               */
+    int32_t precision;       /* NCA_PREC_*                                                       */
+    int32_t mask_mode;       /* NCA_MASK_*                                                       */
+    float   update_rate;     /* fire probability (dynca.py:113,121)                              */
+} NcaDyncaDesc;
+
+/* Weights in the reference state_dict layout:
+ *   w1 [fc, 4C+cc] (= w1.weight[:, :, 0, 0]),  b1 [fc],  w2 [C, fc],  b2 [C].                   */
+typedef struct NcaDyncaWeights {
+    const float* w1; const float* b1; const float* w2; const float* b2;
+} NcaDyncaWeights;
+typedef struct NcaDyncaWeightGrads {
+    float* w1; float* b1; float* w2; float* b2;   /* overwritten, not accumulated */
+} NcaDyncaWeightGrads;
+
+const char* nca_last_error(void);
+int nca_abi_version(void);
+/* number of kernels launched by this library on the calling thread since the last reset */
+long long nca_launch_count(void);
+void nca_launch_count_reset(void);
+
+/* ---- DyNCA ------------------------------------------------------------------------------- */
+
+/* DyNCA.perceive_multiscale (dynca.py:98-111): z [B, 4C+cc, H, W]. */
+int nca_dynca_perceive(const NcaDyncaDesc* d, const float* x, const float* cond, float* z, void* stream);
+
+/* EdgeExtractor.forward (ConditioneDyNCA/models/dynca.py:204-213): img [B,1,H,W] -> out [B,3,H,W];
+ * tanh_transform != 0 applies tanh. */
+int nca_edge_extract(int B, int H, int W, const float* img, int tanh_transform, float* out, void* stream);
+
+/* DyNCA.forward_nsteps (dynca.py:158-167): T steps of DyNCA.forward (dynca.py:113-128).
+ *   states : keep_history != 0 -> [T+1,B,C,H,W], caller has written states[0]; step t writes states[t+1]
+ *            keep_history == 0 -> [2,B,C,H,W] ping-pong, input in slot 0, result in slot (T & 1)
+ *   cond   : [B,cc,H,W] when cond_kind == NCA_COND_TENSOR else NULL
+ *   masks  : [T,B,1,H,W] when mask_mode == NCA_MASK_SUPPLIED else NULL
+ *   seed,t0: Philox key / first step counter when mask_mode == NCA_MASK_PHILOX
+ *   workspace: nca_dynca_workspace_bytes(d, 0) bytes                                              */
+int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
+                      uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* BPTT through the T steps recorded in `states` ([T+1,B,C,H,W] from nca_dynca_forward with keep_history).
+ * Replaces autograd's replay of dynca.py:113-128 x T.
+ *   g_final  : dL/d states[T]                       [B,C,H,W] or NULL (zeros)
+ *   g_taps   : host array of n_taps device pointers, g_taps[i] = dL/d (tap_scale * states[tap_steps[i]][:, :tap_c]),
+ *              each [B,tap_c,H,W]: the gradients of the rgb list of forward_nsteps(return_middle_feature=True)
+ *              (dynca.py:130-131,163-165; fit_video_motion.py:230-235 uses steps 1, 65, 129)
+ *   tap_steps: host array [n_taps], strictly increasing, each in 1..T
+ *   gx0      : dL/d states[0]  [B,C,H,W] (written)
+ *   gw       : weight gradients, reference layout (written)
+ *   workspace: nca_dynca_workspace_bytes(d, 1) bytes
+ * State gradients are accumulated with red.add (fp32 summation order is not deterministic).          */
+int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
+                       uint64_t seed, int32_t t0, int32_t T, const float* states,
+                       const float* g_final, const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps,
+                       int32_t tap_c, float tap_scale, float* gx0, const NcaDyncaWeightGrads* gw,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward);
+
+/* The Philox fire mask the kernels generate, materialised as float [T,B,1,H,W] (tests / debugging).
+ * enc != 0 uses the ConditionedNCA rule (u < rate, EncoderConditioning/nca.py:165-174). */
+int nca_philox_mask(int32_t B, int32_t H, int32_t W, float rate, int32_t enc, uint64_t seed, int32_t t0,
+                    int32_t T, float* out, void* stream);
+
+/* ---- ConditionedNCA (EncoderConditioning/nca.py) --------------------------------------- */
+
+typedef struct NcaEncDesc {
+    int32_t B, C, H, W;       /* state [B,C,H,W], C = num_channels (nca.py:79)               */
+    int32_t hid;              /* UpdateNet hidden width (64, nca.py:40-46)                    */
+    int32_t living_dim;       /* living_channel_dim (nca.py:66)                               */
+    int32_t mask_mode;        /* NCA_MASK_*                                                   */
+    float   alive_thr;        /* 0.1 (nca.py:163)                                             */
+    float   fire_rate;        /* cell_fire_rate (nca.py:67)                                   */
+    float   clamp;            /* 10.0 (nca.py:194)                                            */
+} NcaEncDesc;
+
+/* wp [3C,1,3,3] perception_net.weight; wa [hid,3C], ba [hid]; wb [hid,hid], bb [hid]; wc [C,hid]. */
+typedef struct NcaEncWeights {
+    const float* wp; const float* wa; const float* ba; const float* wb; const float* bb; const float* wc;
+} NcaEncWeights;
+typedef struct NcaEncWeightGrads {
+    float* wp; float* wa; float* ba; float* wb; float* bb; float* wc;
+} NcaEncWeightGrads;
+
+/* ConditionedNCA.grow's T-loop of ConditionedNCA.forward/update (nca.py:176-209), goal [B,C,H,W]
+ * already encoded and zero-padded (nca.py:198-203).  states/masks/workspace as for DyNCA;
+ * supplied masks are (u < rate) as float.
+ *   life_hist: uint8 [T,B,H,W] (keep_history != 0) written by forward: life_hist[t] = pre & post life mask of
+ *              step t (nca.py:181,191-193); backward reads it (the post-update alive mask depends on the
+ *              updated state of the 3x3 neighbourhood and is not recoverable from states[t+1]). May be NULL
+ *              when keep_history == 0. */
+int nca_enc_forward(const NcaEncDesc* d, const NcaEncWeights* w, const float* goal, const float* masks,
+                    uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, uint8_t* life_hist,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* BPTT through nca_enc_forward's T steps. g_goal [B,C,H,W] = dL/d goal (consumed by the ImageEncoder,
+ * EncoderConditioning/encoder.py, which stays in PyTorch); gx0, g_goal and gw are written. */
+int nca_enc_backward(const NcaEncDesc* d, const NcaEncWeights* w, const float* goal, const float* masks,
+                     uint64_t seed, int32_t t0, int32_t T, const float* states, const uint8_t* life_hist,
+                     const float* g_final, float* gx0, float* g_goal, const NcaEncWeightGrads* gw,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t nca_enc_workspace_bytes(const NcaEncDesc* d, int32_t backward);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCA_B200_H_ */

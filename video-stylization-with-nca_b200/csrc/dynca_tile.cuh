@@ -1,0 +1,187 @@
+// Tile geometry + the perception stage shared by the DyNCA kernels (fp32 CUDA-core path, perceive-only
+// kernel, and the BPTT kernel).  One CTA owns a TH x TW = 4 x 32 block of cells of one sample: a warp is one
+// image row of 32 consecutive cells, so global rows are 128-byte coalesced and every shared-memory stencil
+// read is conflict free.
+#pragma once
+#include "dynca_common.cuh"
+
+#define DT_TH 4
+#define DT_TW 32
+#define DT_TM 128            // cells per tile
+#define DT_TMS 132           // smem row stride of [k][cell] matrices (== 4 mod 32: conflict-free float4 rows)
+#define DT_XS (DT_TW + 2)    // fine state tile width incl. 1-cell ring
+#define DT_XR (DT_TH + 2)
+#define DT_PCH (DT_TH / 2 + 2)   // coarse perception rows feeding the bilinear x2 of one tile
+#define DT_PCW (DT_TW / 2 + 2)
+#define DT_CXH (DT_PCH + 2)      // coarse state rows (perception rows + ring)
+#define DT_CXW (DT_PCW + 2)
+#define DT_THREADS 256
+
+// smem (floats) the perception stage needs besides sZ
+__host__ __device__ static inline int dynca_stage_floats(const DyncaGeom& g) {
+    int n = g.C * DT_XR * DT_XS;
+    if (g.ns == 2) n += g.C * DT_CXH * DT_CXW + 4 * g.C * DT_PCH * DT_PCW;
+    return (n + 3) / 4 * 4;
+}
+
+struct DyncaTile {
+    int b, y0, x0;
+};
+__device__ __forceinline__ DyncaTile dynca_tile_of(int t, int tiles_x, int tiles_y) {
+    DyncaTile r;
+    r.x0 = (t % tiles_x) * DT_TW;
+    t /= tiles_x;
+    r.y0 = (t % tiles_y) * DT_TH;
+    r.b = t / tiles_y;
+    return r;
+}
+
+// 3x3 cross-correlation filters of ExtraChannels/models/dynca.py:63-69 applied to a 3x3 neighbourhood v
+__device__ __forceinline__ void dynca_filters(const float v[3][3], float& sx, float& sy, float& lap) {
+    sx = (v[0][2] - v[0][0]) + 2.0f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0]);
+    sy = (v[2][0] - v[0][0]) + 2.0f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2]);
+    lap = (v[0][0] + v[0][2] + v[2][0] + v[2][2]) + 2.0f * (v[0][1] + v[1][0] + v[1][2] + v[2][1]) - 12.0f * v[1][1];
+}
+// tap weights as tables (used by the transposed stencil)
+__device__ __forceinline__ float dynca_tap_sx(int a, int b) { return (b == 1) ? 0.0f : ((b == 2 ? 1.0f : -1.0f) * (a == 1 ? 2.0f : 1.0f)); }
+__device__ __forceinline__ float dynca_tap_sy(int a, int b) { return (a == 1) ? 0.0f : ((a == 2 ? 1.0f : -1.0f) * (b == 1 ? 2.0f : 1.0f)); }
+__device__ __forceinline__ float dynca_tap_lap(int a, int b) { return (a == 1 && b == 1) ? -12.0f : ((a == 1 || b == 1) ? 2.0f : 1.0f); }
+
+// Stage x (state of sample b around the tile) and build the perception matrix
+//   sZ[k][m], k < Ppad, m = py*32+px:  rows [id C | sobel_x C | sobel_y C | lap C | cond cc | 1 | 0..]
+// (DyNCA.perceive_multiscale, dynca.py:98-111).  Cells outside the image get z = 0.
+// sStage: dynca_stage_floats(g) floats of scratch.  Ends with __syncthreads().
+template <int NS>
+__device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const float* __restrict__ x,
+                                                    const float* __restrict__ cond, const DyncaTile& t,
+                                                    float* __restrict__ sStage, float* __restrict__ sZ) {
+    const int tid = threadIdx.x;
+    const int C = g.C, H = g.H, W = g.W;
+    const size_t plane = (size_t)H * W;
+    const float* xb = x + (size_t)t.b * C * plane;
+    float* sX = sStage;
+    float* sXc = sX + C * DT_XR * DT_XS;
+    float* sCP = sXc + C * DT_CXH * DT_CXW;
+
+    for (int i = tid; i < C * DT_XR * DT_XS; i += DT_THREADS) {
+        int q = i % DT_XS, r = (i / DT_XS) % DT_XR, c = i / (DT_XS * DT_XR);
+        int iy = nca_padmap(t.y0 - 1 + r, H, g.pad), ix = nca_padmap(t.x0 - 1 + q, W, g.pad);
+        sX[i] = (iy >= 0 && ix >= 0) ? __ldg(xb + c * plane + (size_t)iy * W + ix) : 0.0f;
+    }
+    if (NS == 2) {
+        const int Hc = H >> 1, Wc = W >> 1;
+        const int cyp = (t.y0 >> 1) - 2, cxp = (t.x0 >> 1) - 2;   // coarse padded coordinate of sXc[.][0][0]
+        for (int i = tid; i < C * DT_CXH * DT_CXW; i += DT_THREADS) {
+            int q = i % DT_CXW, r = (i / DT_CXW) % DT_CXH, c = i / (DT_CXW * DT_CXH);
+            int qy = nca_padmap(cyp + r, Hc, g.pad), qx = nca_padmap(cxp + q, Wc, g.pad);
+            float v = 0.0f;
+            if (qy >= 0 && qx >= 0) {
+                const float* p = xb + c * plane + (size_t)(2 * qy) * W + 2 * qx;
+                v = 0.25f * (((__ldg(p) + __ldg(p + 1)) + __ldg(p + W)) + __ldg(p + W + 1));   // dynca.py:73-77
+            }
+            sXc[i] = v;
+        }
+    }
+    __syncthreads();
+    if (NS == 2) {
+        // coarse perception at the DT_PCH x DT_PCW coarse cells whose bilinear footprint touches the tile
+        for (int i = tid; i < C * DT_PCH * DT_PCW; i += DT_THREADS) {
+            int q = i % DT_PCW, r = (i / DT_PCW) % DT_PCH, c = i / (DT_PCW * DT_PCH);
+            float v[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) v[a][bb] = sXc[(c * DT_CXH + r + a) * DT_CXW + q + bb];
+            float sx, sy, lap;
+            dynca_filters(v, sx, sy, lap);
+            const int o = r * DT_PCW + q, ps = DT_PCH * DT_PCW;
+            sCP[(0 * C + c) * ps + o] = v[1][1];
+            sCP[(1 * C + c) * ps + o] = sx;
+            sCP[(2 * C + c) * ps + o] = sy;
+            sCP[(3 * C + c) * ps + o] = lap;
+        }
+        __syncthreads();
+    }
+    {
+        const int m = tid & (DT_TM - 1), half = tid >> 7;
+        const int py = m >> 5, px = m & 31;
+        const int gy = t.y0 + py, gx = t.x0 + px;
+        const bool inimg = gy < H && gx < W;
+        int by = 0, bx = 0;
+        float wy0 = 0, wy1 = 0, wx0 = 0, wx1 = 0;
+        if (NS == 2 && inimg) {
+            dynca_up_taps(gy, H >> 1, by, wy0, wy1);
+            dynca_up_taps(gx, W >> 1, bx, wx0, wx1);
+            by -= (t.y0 >> 1) - 1;   // to sCP-local rows / cols
+            bx -= (t.x0 >> 1) - 1;
+        }
+        for (int c = half; c < C; c += 2) {
+            float f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+            if (inimg) {
+                float v[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) v[a][bb] = sX[(c * DT_XR + py + a) * DT_XS + px + bb];
+                f0 = v[1][1];
+                dynca_filters(v, f1, f2, f3);
+                if (NS == 2) {
+                    const int ps = DT_PCH * DT_PCW;
+                    const float* cp = sCP + c * ps + by * DT_PCW + bx;
+                    float u[4];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const float* q = cp + f * C * ps;
+                        u[f] = wy0 * (wx0 * q[0] + wx1 * q[1]) + wy1 * (wx0 * q[DT_PCW] + wx1 * q[DT_PCW + 1]);
+                    }
+                    f0 = (f0 + u[0]) * g.s0; f1 = (f1 + u[1]) * g.s0; f2 = (f2 + u[2]) * g.s0; f3 = (f3 + u[3]) * g.s0;
+                }
+            }
+            sZ[(0 * C + c) * DT_TMS + m] = f0;
+            sZ[(1 * C + c) * DT_TMS + m] = f1;
+            sZ[(2 * C + c) * DT_TMS + m] = f2;
+            sZ[(3 * C + c) * DT_TMS + m] = f3;
+        }
+        // cond rows, the constant-1 row and the zero padding rows
+        for (int k = 4 * C + half; k < g.Ppad; k += 2) {
+            float v = 0.0f;
+            if (inimg) {
+                int i = k - 4 * C;
+                if (i < g.cc) {
+                    if (g.cond_kind == NCA_COND_CPE) v = (i == 0) ? dynca_cpe(gy, H, g.cpe_oh) : dynca_cpe(gx, W, g.cpe_ow);
+                    else v = __ldg(cond + ((size_t)(t.b * g.cc + i) * H + gy) * W + gx);
+                } else if (i == g.cc) v = 1.0f;
+            }
+            sZ[k * DT_TMS + m] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// GEMM1: acc[i][jj] = sum_k sZ[k][pix(i)] * sW1[k][ty*8+jj], k <= P (bias row included).
+// pix(i) = tx*4+i (i<4) | 64+tx*4+(i-4);  tx = tid & 15, ty = tid >> 4.  Threads with ty*8 >= FCpad idle.
+__device__ __forceinline__ void dynca_gemm1(const DyncaGeom& g, const float* __restrict__ sZ,
+                                            const float* __restrict__ sW1, float acc[8][8]) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    if (ty * 8 >= g.FCpad) return;
+    const float* zp = sZ + tx * 4;
+    const float* wp = sW1 + ty * 8;
+    const int kEnd = g.P + 1;
+#pragma unroll 2
+    for (int k = 0; k < kEnd; ++k) {
+        float4 za = *reinterpret_cast<const float4*>(zp + k * DT_TMS);
+        float4 zb = *reinterpret_cast<const float4*>(zp + k * DT_TMS + 64);
+        float4 wa = *reinterpret_cast<const float4*>(wp + k * g.FCpad);
+        float4 wb = *reinterpret_cast<const float4*>(wp + k * g.FCpad + 4);
+        const float z[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(z[i], w[j], acc[i][j]);
+    }
+}

@@ -1,0 +1,17 @@
+// Internal launcher prototypes shared between the translation units of libnca_b200.so (not part of the ABI).
+#pragma once
+#include "dynca_common.cuh"
+
+// dynca_f32.cu
+size_t dynca_f32_weight_floats(const DyncaGeom& g);
+size_t dynca_f32_grad_floats(const DyncaGeom& g);
+int dynca_f32_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, float* ws, cudaStream_t s);
+int dynca_f32_forward_step(const DyncaGeom& g, const float* wsW, const float* x_in, float* x_out, const float* cond,
+                           const FireMask& fm, cudaStream_t s);
+int dynca_f32_perceive(const DyncaGeom& g, const float* x, const float* cond, float* z, cudaStream_t s);
+int dynca_f32_backward_step(const DyncaGeom& g, const float* wsW, float* wsG, const float* x_in, const float* g_next,
+                            const float* g_tap, int tap_c, float tap_scale, float* g_out, const float* cond,
+                            const FireMask& fm, cudaStream_t s);
+int dynca_f32_unpack_grads(const DyncaGeom& g, const float* wsG, const NcaDyncaWeightGrads* gw, cudaStream_t s);
+int nca_edge_extract_launch(int B, int H, int W, const float* img, int tanh_transform, float* out, cudaStream_t s);
+int nca_philox_mask_launch(int B, int H, int W, float rate, int enc, uint64_t seed, int t0, int T, float* out, cudaStream_t s);

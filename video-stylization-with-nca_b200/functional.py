@@ -1,0 +1,233 @@
+"""Functional layer over the C ABI: rollouts as autograd Functions, perception, edge maps, Philox masks.
+
+Everything here runs on CUDA through libnca_b200.so; tensors are fp32, contiguous, NCHW.  torch is used only
+for device memory, streams and autograd bookkeeping.
+"""
+import collections.abc
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import NcaError, check, load_library
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NcaError("the NCA step runs on CUDA only (got a CPU tensor); there is no CPU fallback")
+        if t.dtype != torch.float32:
+            raise NcaError(f"expected float32, got {t.dtype}")
+
+
+def _c(t):
+    return None if t is None else t.detach().contiguous()
+
+
+def new_seed():
+    """Philox key drawn from torch's default generator, so torch.manual_seed controls the fire masks."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+# ------------------------------------------------------------------------------------------------
+# DyNCA
+# ------------------------------------------------------------------------------------------------
+class DyncaConfig:
+    """Static description of a DyNCA model (ctor arguments of the reference's DyNCA, dynca.py:30-69)."""
+
+    def __init__(self, C_, fc, pad, scales, cond_kind, cc, precision="fp32"):
+        scales = list(scales)
+        if scales not in ([0], [0, 1]):
+            raise NcaError(f"perception_scales {scales} not supported (only [0] and [0, 1])")
+        if pad not in _lib.NCA_PAD:
+            raise NcaError(f"padding_mode {pad!r} not supported")
+        self.C, self.fc, self.pad, self.ns = C_, fc, _lib.NCA_PAD[pad], len(scales)
+        self.cond_kind, self.cc, self.precision = cond_kind, cc, _lib.NCA_PREC[precision]
+
+    def desc(self, B, H, W, rate, supplied):
+        return _lib.DyncaDesc(B, self.C, H, W, self.fc, self.cond_kind, self.cc, self.pad, self.ns, self.precision,
+                              _lib.NCA_MASK_SUPPLIED if supplied else _lib.NCA_MASK_PHILOX, float(rate))
+
+
+def _weights_struct(w1, b1, w2, b2):
+    return _lib.DyncaWeights(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr())
+
+
+def dynca_perceive(cfg, x, cond=None):
+    """DyNCA.perceive_multiscale (dynca.py:98-111) -> [B, 4C+cc, H, W]."""
+    _need_cuda(x, cond)
+    lib = load_library()
+    x, cond = _c(x), _c(cond)
+    B, Cc, H, W = x.shape
+    z = torch.empty(B, 4 * Cc + cfg.cc, H, W, device=x.device, dtype=torch.float32)
+    d = cfg.desc(B, H, W, 0.5, False)
+    with torch.cuda.device(x.device):
+        check(lib.nca_dynca_perceive(C.byref(d), _ptr(x), _ptr(cond), _ptr(z), _stream()))
+    return z
+
+
+def edge_extract(img, tanh):
+    """EdgeExtractor.forward (ConditioneDyNCA/models/dynca.py:204-213): [B,1,H,W] -> [B,3,H,W]."""
+    _need_cuda(img)
+    lib = load_library()
+    img = _c(img)
+    B, one, H, W = img.shape
+    if one != 1:
+        raise NcaError("edge_extract expects a one-channel image")
+    out = torch.empty(B, 3, H, W, device=img.device, dtype=torch.float32)
+    with torch.cuda.device(img.device):
+        check(lib.nca_edge_extract(B, H, W, _ptr(img), int(bool(tanh)), _ptr(out), _stream()))
+    return out
+
+
+def philox_mask(B, H, W, rate, seed, T, t0=0, enc=False, device="cuda"):
+    """The fire masks the kernels generate for (seed, t0..t0+T), as float [T,B,1,H,W]."""
+    lib = load_library()
+    out = torch.empty(T, B, 1, H, W, device=device, dtype=torch.float32)
+    with torch.cuda.device(out.device):
+        check(lib.nca_philox_mask(B, H, W, float(rate), int(enc), C.c_uint64(seed), t0, T, _ptr(out), _stream()))
+    return out
+
+
+def _dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, masks, seed, T, rate, keep_history):
+    lib = load_library()
+    B, Cc, H, W = x0.shape
+    d = cfg.desc(B, H, W, rate, masks is not None)
+    n_slots = T + 1 if keep_history else 2
+    states = torch.empty(n_slots, B, Cc, H, W, device=x0.device, dtype=torch.float32)
+    states[0].copy_(x0)
+    with torch.cuda.device(x0.device):
+        nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
+        ws = torch.empty(max(nbytes, 16), device=x0.device, dtype=torch.uint8)
+        wst = _weights_struct(w1, b1, w2, b2)
+        check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(seed), 0, T,
+                                    int(keep_history), _ptr(states), _ptr(ws), nbytes, _stream()))
+    return states
+
+
+class _RolloutHandle:
+    """Shared between the rollout Function and the lazy rgb taps: gradients of taps land here."""
+
+    def __init__(self):
+        self.tap_grads = {}
+        self.hist = None
+        self.c_out = 0
+
+
+class _DyncaRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, w1, b1, w2, b2, cond, masks, cfg, T, rate, seed, handle):
+        x0c, w1c, b1c, w2c, b2c = _c(x0), _c(w1), _c(b1), _c(w2), _c(b2)
+        cond, masks = _c(cond), _c(masks)
+        hist = _dynca_forward_raw(cfg, x0c, w1c, b1c, w2c, b2c, cond, masks, seed, T, rate, True)
+        ctx.cfg, ctx.T, ctx.rate, ctx.seed, ctx.handle = cfg, T, rate, seed, handle
+        ctx.w_shapes = (w1.shape, b1.shape, w2.shape, b2.shape)
+        ctx.save_for_backward(w1c, b1c, w2c, b2c, cond, masks)
+        ctx.hist = hist
+        handle.hist = hist
+        ctx.set_materialize_grads(False)
+        token = x0.new_zeros(())
+        return hist[T], token
+
+    @staticmethod
+    def backward(ctx, g_final, _g_token):
+        lib = load_library()
+        w1, b1, w2, b2, cond, masks = ctx.saved_tensors
+        hist, cfg, T = ctx.hist, ctx.cfg, ctx.T
+        _, B, Cc, H, W = hist.shape
+        d = cfg.desc(B, H, W, ctx.rate, masks is not None)
+        g_final = _c(g_final)
+        taps = sorted(ctx.handle.tap_grads.items())
+        n_taps = len(taps)
+        tap_c = ctx.handle.c_out
+        tap_ptrs = (C.c_void_p * max(n_taps, 1))(*[t.data_ptr() for _, t in taps])
+        tap_steps = (C.c_int32 * max(n_taps, 1))(*[s for s, _ in taps])
+        gx0 = torch.empty(B, Cc, H, W, device=hist.device, dtype=torch.float32)
+        gw1, gb1, gw2, gb2 = (torch.empty_like(t) for t in (w1, b1, w2, b2))
+        with torch.cuda.device(hist.device):
+            nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 1)
+            ws = torch.empty(nbytes, device=hist.device, dtype=torch.uint8)
+            wst = _weights_struct(w1, b1, w2, b2)
+            gst = _weights_struct(gw1, gb1, gw2, gb2)
+            check(lib.nca_dynca_backward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(ctx.seed), 0, T,
+                                         _ptr(hist), _ptr(g_final), tap_ptrs, tap_steps, n_taps, max(tap_c, 1), 2.0,
+                                         _ptr(gx0), C.byref(gst), _ptr(ws), nbytes, _stream()))
+        ctx.handle.tap_grads = {}
+        s1, sb1, s2, sb2 = ctx.w_shapes
+        return (gx0, gw1.view(s1), gb1.view(sb1), gw2.view(s2), gb2.view(sb2), None, None, None, None, None, None, None)
+
+
+class _RgbTap(torch.autograd.Function):
+    """rgb_t = 2 * states[t][:, :c_out] (DyNCA.to_rgb, dynca.py:130-131) whose gradient is routed into the
+    rollout's BPTT as a tap instead of through a dense gradient of the whole history."""
+
+    @staticmethod
+    def forward(ctx, token, handle, t):
+        ctx.handle, ctx.t = handle, t
+        return handle.hist[t][:, :handle.c_out] * 2.0
+
+    @staticmethod
+    def backward(ctx, g):
+        h = ctx.handle
+        g = g.contiguous()
+        h.tap_grads[ctx.t] = g if ctx.t not in h.tap_grads else h.tap_grads[ctx.t] + g
+        return torch.zeros((), device=g.device, dtype=g.dtype), None, None
+
+
+class RgbTaps(collections.abc.Sequence):
+    """List-like view of the per-step rgb outputs of forward_nsteps(return_middle_feature=True): entry i is the
+    rgb after step i+1 (dynca.py:161-165).  Entries are materialised on access."""
+
+    def __init__(self, handle, token, T):
+        self._h, self._token, self._T = handle, token, T
+
+    def __len__(self):
+        return self._T
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._T))]
+        if i < 0:
+            i += self._T
+        if not 0 <= i < self._T:
+            raise IndexError(i)
+        if self._token is None:
+            return self._h.hist[i + 1][:, :self._h.c_out] * 2.0
+        return _RgbTap.apply(self._token, self._h, i + 1)
+
+
+def dynca_rollout(cfg, x0, w1, b1, w2, b2, T, rate=0.5, cond=None, masks=None, seed=None, c_out=3,
+                  return_taps=False):
+    """T DyNCA steps (DyNCA.forward_nsteps, dynca.py:158-167).
+
+    masks: optional supplied fire masks [T,B,1,H,W] (1 = fire); otherwise in-kernel Philox keyed on `seed`.
+    Returns (final_state, taps) with taps an RgbTaps sequence when return_taps else None."""
+    _need_cuda(x0, w1, b1, w2, b2, cond, masks)
+    if seed is None:
+        seed = new_seed() if masks is None else 0
+    if masks is not None and tuple(masks.shape) != (T, x0.shape[0], 1, x0.shape[2], x0.shape[3]):
+        raise NcaError(f"masks must be [T,B,1,H,W] = {(T, x0.shape[0], 1, x0.shape[2], x0.shape[3])}, got {tuple(masks.shape)}")
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (x0, w1, b1, w2, b2))
+    handle = _RolloutHandle()
+    handle.c_out = c_out
+    if T == 0:
+        return x0, (RgbTaps(handle, None, 0) if return_taps else None)
+    if needs_grad:
+        final, token = _DyncaRollout.apply(x0, w1, b1, w2, b2, cond, masks, cfg, T, rate, seed, handle)
+        return final, (RgbTaps(handle, token, T) if return_taps else None)
+    states = _dynca_forward_raw(cfg, _c(x0), _c(w1), _c(b1), _c(w2), _c(b2), _c(cond), _c(masks), seed, T, rate,
+                                return_taps)
+    if return_taps:
+        handle.hist = states
+        return states[T], RgbTaps(handle, None, T)
+    return states[T & 1], None
