@@ -66,7 +66,7 @@ typedef struct NcaDyncaWeightGrads {
 
 const char* nca_last_error(void);
 int nca_abi_version(void);
-/* number of kernels launched by this library on the calling thread since the last reset */
+/* number of kernels launched by this library (all threads of the process) since the last reset */
 long long nca_launch_count(void);
 void nca_launch_count_reset(void);
 

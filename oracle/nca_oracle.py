@@ -172,6 +172,43 @@ def dynca_rollout(x, w1, b1, w2, b2, masks, scales=(0,), mode="circular", cond=N
 
 
 # --------------------------------------------------------------------------------------
+# The same DyNCA step phrased with the ATen ops the reference dispatches on CPU (F.pad + depthwise
+# F.conv2d + F.interpolate + 1x1 conv2d, dynca.py:71-123).  Used ONLY as the CPU baseline that bench.py
+# times on the host cores (cpu_baseline / --impl reference); checked against the golden vectors too.
+# --------------------------------------------------------------------------------------
+def _filters(C, dtype):
+    f = torch.tensor([SOBEL_X, SOBEL_Y, LAPLACE], dtype=dtype)          # [3,3,3]
+    return [f[i][None, None].repeat(C, 1, 1, 1) for i in range(3)]
+
+
+def perceive_aten(x, scale, mode):
+    H, W = x.shape[-2:]
+    C = x.shape[1]
+    if scale != 0:
+        x = F.interpolate(x, size=(H // 2 ** scale, W // 2 ** scale), mode="bilinear", align_corners=False)
+    xp = F.pad(x, [1, 1, 1, 1], mode)
+    ys = [x] + [F.conv2d(xp, w, groups=C) for w in _filters(C, x.dtype)]
+    y = torch.cat(ys, dim=1)
+    if scale != 0:
+        y = F.interpolate(y, size=(H, W), mode="bilinear", align_corners=False)
+    return y
+
+
+def dynca_step_aten(x, w1, b1, w2, b2, mask, scales=(0,), mode="circular", cond=None):
+    z = sum(perceive_aten(x, s, mode) for s in scales) / len(scales)
+    if cond is not None:
+        z = torch.cat([z, cond], dim=1)
+    y = F.conv2d(torch.relu(F.conv2d(z, w1[:, :, None, None], b1)), w2[:, :, None, None], b2)
+    return x + y * mask
+
+
+def dynca_rollout_aten(x, w1, b1, w2, b2, masks, scales=(0,), mode="circular", cond=None):
+    for t in range(masks.shape[0]):
+        x = dynca_step_aten(x, w1, b1, w2, b2, masks[t], scales, mode, cond)
+    return x
+
+
+# --------------------------------------------------------------------------------------
 # EncoderConditioning/nca.py
 # --------------------------------------------------------------------------------------
 def enc_alive(x, living_dim: int, thr: float = 0.1):

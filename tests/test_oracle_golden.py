@@ -35,6 +35,15 @@ def test_dynca_oracle_matches_reference(name):
         assert rel_err(p.grad.detach(), t[k]) < gtol, k
 
 
+@pytest.mark.parametrize("name", DYNCA_CASES)
+def test_dynca_aten_baseline_matches_reference(name):
+    """the CPU-baseline phrasing (ATen ops) that bench.py times is the same function"""
+    t, m = load_case(name)
+    final = O.dynca_rollout_aten(t["x0"], t["w1"], t["b1"], t["w2"], t["b2"], t["masks"], m["scales"], m["pad"],
+                                 cond_for(t, m))
+    assert rel_err(final, t["final"]) < 2e-6
+
+
 @pytest.mark.parametrize("name", ENC_CASES)
 def test_enc_oracle_matches_reference(name):
     t, m = load_case(name)

@@ -1,10 +1,11 @@
 // C ABI of libnca_b200.so (include/nca_b200.h): argument checking, workspace carving, step loops.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "nca_internal.h"
 
 static thread_local char t_err[512] = "";
-static thread_local long long t_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide: autograd runs backward on its own thread
 
 void nca_set_error(const char* fmt, ...) {
     va_list ap;
@@ -12,14 +13,14 @@ void nca_set_error(const char* fmt, ...) {
     vsnprintf(t_err, sizeof(t_err), fmt, ap);
     va_end(ap);
 }
-void nca_count_launch(int n) { t_launches += n; }
+void nca_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" {
 
 const char* nca_last_error(void) { return t_err; }
 int nca_abi_version(void) { return NCA_B200_ABI_VERSION; }
-long long nca_launch_count(void) { return t_launches; }
-void nca_launch_count_reset(void) { t_launches = 0; }
+long long nca_launch_count(void) { return g_launches.load(); }
+void nca_launch_count_reset(void) { g_launches.store(0); }
 
 static int check_device() {
     int n = 0;
