@@ -1,0 +1,78 @@
+"""Parity of the tcgen05 (BF16 operands, fp32 accumulate) DyNCA forward path.  Tolerance (BASELINE.json north_star):
+per-step state within 1e-2 relative when the MLP runs in BF16; rollouts over T <= 6 steps within 3e-2."""
+import pytest
+import torch
+
+import nca_b200
+from nca_b200 import functional as Fn, _lib
+from oracle import nca_oracle as O
+from helpers import DYNCA_CASES, load_case, rel_err, cond_for
+from test_dynca_gpu import build_model, ORACLE_CASES
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+STEP_TOL, ROLLOUT_TOL = 1e-2, 3e-2
+
+
+@pytest.mark.parametrize("name", DYNCA_CASES)
+def test_golden_case_bf16(name):
+    t, m = load_case(name)
+    model = build_model(m, t, precision="bf16")
+    ref = build_model(m, t, precision="fp32")
+    x0, masks = t["x0"].to(DEV), t["masks"].to(DEV)
+    kwargs = dict(cond_img=t["cond_img"].to(DEV) if "cond_img" in t else None) if m["flavour"] == "cd" else {}
+    with torch.no_grad():
+        one, _ = model.forward_nsteps(x0, 1, masks=masks[:1], **kwargs)
+        one_ref, _ = ref.forward_nsteps(x0, 1, masks=masks[:1], **kwargs)
+        # the update (x' - x) is what the MLP produces: check it, not just the state it is added to
+        assert rel_err((one - x0).cpu(), (one_ref - x0).cpu()) < STEP_TOL
+        T = min(m["T"], 6)
+        fin, _ = model.forward_nsteps(x0, T, masks=masks[:T], **kwargs)
+        fin_ref, _ = ref.forward_nsteps(x0, T, masks=masks[:T], **kwargs)
+    assert rel_err(fin.cpu(), fin_ref.cpu()) < ROLLOUT_TOL
+    if T == m["T"]:
+        assert rel_err(fin.cpu(), t["final"]) < ROLLOUT_TOL
+
+
+@pytest.mark.parametrize("case", ORACLE_CASES, ids=lambda c: "B%d_C%d_fc%d_%dx%d_%s_s%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[6], len(c[7]), c[8]))
+def test_against_oracle_seeded_bf16(case):
+    B, C, fc, H, W, T, pad, scales, cond = case
+    g = torch.Generator().manual_seed(11)
+    cc = {"cpe": 2, None: 0, "tensor": 3}[cond]
+    w1 = torch.randn(fc, 4 * C + cc, generator=g) * 0.15
+    b1 = torch.randn(fc, generator=g) * 0.1
+    w2 = torch.randn(C, fc, generator=g) * 0.1
+    b2 = torch.randn(C, generator=g) * 0.02
+    x0 = torch.rand(B, C, H, W, generator=g) - 0.5
+    masks = (torch.rand(T, B, 1, H, W, generator=g) + 0.5).floor()
+    cond_t = O.cpe2d(B, H, W) if cond == "cpe" else (torch.randn(B, 3, H, W, generator=g) if cond == "tensor" else None)
+    want = O.dynca_rollout(x0, w1, b1, w2, b2, masks, scales, pad, cond_t)
+    kind = {"cpe": _lib.NCA_COND_CPE, None: _lib.NCA_COND_NONE, "tensor": _lib.NCA_COND_TENSOR}[cond]
+    cfg = Fn.DyncaConfig(C, fc, pad, scales, kind, cc, precision="bf16")
+    with torch.no_grad():
+        got, _ = Fn.dynca_rollout(cfg, x0.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), T, 0.5,
+                                  cond=cond_t.to(DEV) if cond == "tensor" else None, masks=masks.to(DEV))
+        one, _ = Fn.dynca_rollout(cfg, x0.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), 1, 0.5,
+                                  cond=cond_t.to(DEV) if cond == "tensor" else None, masks=masks[:1].to(DEV))
+    want1 = O.dynca_step(x0, w1, b1, w2, b2, masks[0], scales, pad, cond_t)
+    assert rel_err((one.cpu() - x0), (want1 - x0)) < STEP_TOL
+    assert rel_err(got.cpu(), want) < ROLLOUT_TOL
+
+
+def test_bf16_full_size_properties():
+    """config-2 size: never-firing cells keep their value bit-exactly; Philox == supplied mask; bf16 close to fp32."""
+    torch.manual_seed(3)
+    B, C, fc, H, W, T = 2, 16, 128, 256, 256, 4
+    kw = dict(fc_dim=fc, padding_mode="replicate", pos_emb="CPE", perception_scales=[0, 1], device=torch.device(DEV))
+    mb = nca_b200.DyNCA_EC(C, 3, precision="bf16", **kw)
+    mf = nca_b200.DyNCA_EC(C, 3, precision="fp32", **kw)
+    mf.load_state_dict(mb.state_dict())
+    x0 = torch.rand(B, C, H, W, device=DEV) - 0.5
+    with torch.no_grad():
+        s, _ = mb.forward_nsteps(x0, T, masks=torch.zeros(T, B, 1, H, W, device=DEV))
+        assert torch.equal(s, x0)
+        a, _ = mb.forward_nsteps(x0, T, seed=5)
+        b, _ = mb.forward_nsteps(x0, T, masks=Fn.philox_mask(B, H, W, 0.5, 5, T))
+        assert torch.equal(a, b)
+        f, _ = mf.forward_nsteps(x0, T, seed=5)
+    assert rel_err((a - x0).cpu(), (f - x0).cpu()) < ROLLOUT_TOL

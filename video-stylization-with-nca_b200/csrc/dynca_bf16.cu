@@ -1,0 +1,385 @@
+// DyNCA forward step with the update MLP on the 5th-gen tensor cores (NCA_PREC_BF16).
+// Reference semantics: ExtraChannels/models/dynca.py:113-123 (same step as dynca_f32.cu).
+//
+// One CTA = 128 threads = one 4x32 tile of cells; thread r owns cell r (TMEM lane r, row r of both A operands).
+//   perception (CUDA cores, fp32)  ->  A1 [128 x K1] bf16 in shared memory, UMMA canonical K-major layout
+//   GEMM1  D1[128 x fc]  = A1 . W1^T      tcgen05.mma kind::f16, M=128, N=fc, K1/16 instructions, fp32 accum in TMEM
+//   epilogue 1: tcgen05.ld D1 -> relu -> bf16 -> A2 [128 x fc] in shared memory
+//   GEMM2  D2[128 x 16]  = A2 . W2^T      M=128, N=16, fc/16 instructions
+//   epilogue 2: tcgen05.ld D2 -> + b2 -> * fire mask -> + x -> coalesced NCHW store
+// K order of A1 / W1 is permuted so that one thread produces whole 16-byte rows of core matrices:
+//   k' = 8*cp + 4*h + f  <->  channel c = 2*cp + h, filter f (id, sobel_x, sobel_y, lap);
+//   chunk cp = ceil(C/2): [cond_0 .. cond_{cc-1}, 1, 1, 0 ..]  (the two constant-1 columns carry b1 split into
+//   bf16 hi + lo parts, so the bias keeps ~16 bits of mantissa).
+// Operand smem layout (no swizzle): element (row, k) at  (k/8)*LBO + (row/8)*128 + (row%8)*16 + (k%8)*2  bytes,
+// i.e. 8x8 core matrices of 128 contiguous bytes, SBO = 128 (next 8 rows), LBO = rows*16 (next 8 k).
+#include <cuda_bf16.h>
+#include "dynca_tile.cuh"
+#include "nca_internal.h"
+
+#define BT_THREADS 128
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T ; one elected thread issues
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor: start [0,14), LBO [16,30),
+// SBO [32,46), version=1 at bit 46, layout_type [61,64) = 0)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- geometry of the bf16 operands ---------------------------------------------------------------
+struct Bf16Geom {
+    int npairs;      // ceil(C/2) perception chunks
+    int K1;          // padded K of GEMM1 (multiple of 16)
+    int N1;          // fc (multiple of 16)
+    int tmem_cols;   // power of two >= N1 + 16
+    uint32_t a1_bytes, b1_bytes, a2_bytes, b2_bytes;
+};
+static inline int dynca_bf16_geom(const DyncaGeom& g, Bf16Geom* b) {
+    if (g.fc % 16 != 0 || g.fc < 16 || g.fc > 240) { nca_set_error("bf16 path needs fc %% 16 == 0 and 16 <= fc <= 240 (got %d)", g.fc); return NCA_ERR_UNSUPPORTED; }
+    if (g.cc + 2 > 8) { nca_set_error("bf16 path supports at most 6 cond channels (got %d)", g.cc); return NCA_ERR_UNSUPPORTED; }
+    b->npairs = (g.C + 1) / 2;
+    b->K1 = ((b->npairs + 1) * 8 + 15) / 16 * 16;
+    b->N1 = g.fc;
+    int need = g.fc + 16, cols = 32;
+    while (cols < need) cols *= 2;
+    b->tmem_cols = cols;
+    b->a1_bytes = (uint32_t)(b->K1 / 8) * 2048u;
+    b->b1_bytes = (uint32_t)(b->K1 / 8) * (uint32_t)(g.fc / 8) * 128u;
+    b->a2_bytes = (uint32_t)(g.fc / 8) * 2048u;
+    b->b2_bytes = (uint32_t)(g.fc / 8) * 256u;
+    return NCA_OK;
+}
+
+// ---- weight packing: fp32 reference layout -> bf16 UMMA operand images -------------------------------
+__global__ void dynca_bf16_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __restrict__ w1, const float* __restrict__ b1,
+                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                       __nv_bfloat16* __restrict__ B1, __nv_bfloat16* __restrict__ B2, float* __restrict__ b2p) {
+    const int n1 = bg.K1 * g.fc, n2 = g.fc * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + 16; i += gridDim.x * blockDim.x) {
+        if (i < n1) {
+            const int kp = i / g.fc, j = i % g.fc;            // (k', hidden unit)
+            const int kc = kp >> 3, s = kp & 7;
+            float v = 0.0f;
+            if (kc < bg.npairs) {
+                const int c = 2 * kc + (s >> 2), f = s & 3;
+                if (c < g.C) v = w1[j * g.P + f * g.C + c];
+            } else if (kc == bg.npairs) {
+                if (s < g.cc) v = w1[j * g.P + 4 * g.C + s];
+                else if (s == g.cc) v = __bfloat162float(__float2bfloat16_rn(b1[j]));
+                else if (s == g.cc + 1) v = b1[j] - __bfloat162float(__float2bfloat16_rn(b1[j]));
+            }
+            const size_t off = (size_t)kc * (g.fc / 8) * 64 + (size_t)(j >> 3) * 64 + (j & 7) * 8 + s;   // in elements
+            B1[off] = __float2bfloat16_rn(v);
+        } else if (i < n1 + n2) {
+            const int e = i - n1, j = e / 16, c = e % 16;     // (hidden unit = k, channel = n)
+            const float v = c < g.C ? w2[c * g.fc + j] : 0.0f;
+            const size_t off = (size_t)(j >> 3) * 128 + (size_t)(c >> 3) * 64 + (c & 7) * 8 + (j & 7);
+            B2[off] = __float2bfloat16_rn(v);
+        } else {
+            const int c = i - n1 - n2;
+            b2p[c] = c < g.C ? b2[c] : 0.0f;
+        }
+    }
+}
+
+// ---- forward step ------------------------------------------------------------------------------------
+struct DyncaBf16Args {
+    DyncaGeom g;
+    Bf16Geom bg;
+    const float* x_in; float* x_out; const float* cond;
+    const __nv_bfloat16* B1; const __nv_bfloat16* B2; const float* b2p;
+    FireMask fm;
+    int tiles_x, tiles_y, n_tiles;
+};
+
+static inline size_t dynca_bf16_smem_bytes(const DyncaGeom& g, const Bf16Geom& bg) {
+    size_t stage = (size_t)dynca_stage_floats(g) * 4;
+    size_t u = stage > bg.a2_bytes ? stage : bg.a2_bytes;
+    return 1024 /*alignment slack*/ + 128 /*barrier, tmem ptr, b2*/ + bg.a1_bytes + bg.b1_bytes + bg.b2_bytes + u;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaBf16Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    const DyncaGeom& g = a.g;
+    const Bf16Geom& bg = a.bg;
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 8);
+    float* sB2 = reinterpret_cast<float*>(base + 64);          // 16 floats
+    uint8_t* sA1 = base + 128;
+    uint8_t* sB1 = sA1 + bg.a1_bytes;
+    uint8_t* sB2w = sB1 + bg.b1_bytes;
+    uint8_t* sU = sB2w + bg.b2_bytes;                          // stage (fp32) | A2 (bf16)
+    float* sStage = reinterpret_cast<float*>(sU);
+    uint8_t* sA2 = sU;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int C = g.C, H = g.H, W = g.W;
+    const size_t plane = (size_t)H * W;
+
+    // ---- one-time setup: weights -> smem, barrier, TMEM ----
+    for (uint32_t i = tid; i < bg.b1_bytes / 16; i += BT_THREADS)
+        reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
+    for (uint32_t i = tid; i < bg.b2_bytes / 16; i += BT_THREADS)
+        reinterpret_cast<uint4*>(sB2w)[i] = __ldg(reinterpret_cast<const uint4*>(a.B2) + i);
+    if (tid < 16) sB2[tid] = a.b2p[tid];
+    // chunks of A1 beyond the cond chunk are constant zero
+    for (uint32_t i = tid + (uint32_t)(bg.npairs + 1) * 128; i < bg.a1_bytes / 16; i += BT_THREADS)
+        reinterpret_cast<uint4*>(sA1)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)bg.tmem_cols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_d2_col = (uint32_t)bg.N1;
+    const uint32_t idesc1 = umma_idesc_bf16(128, bg.N1), idesc2 = umma_idesc_bf16(128, 16);
+    const uint32_t lbo_b1 = (uint32_t)(g.fc / 8) * 128u;
+    uint32_t phase = 0;
+    const int py = tid >> 5, px = tid & 31;
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;   // this thread's row inside a K-chunk
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const DyncaTile t = dynca_tile_of(tile, a.tiles_x, a.tiles_y);
+        const int gy = t.y0 + py, gx = t.x0 + px;
+        const bool inimg = gy < H && gx < W;
+        dynca_stage_tile<NS, BT_THREADS>(g, a.x_in, t, sStage);
+        // ---- perception -> A1 (this thread's row) ----
+        {
+            DyncaUp u = {};
+            if (NS == 2 && inimg) u = dynca_up_of(g, t, gy, gx);
+            for (int cp = 0; cp < bg.npairs; ++cp) {
+                float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+                if (inimg) {
+                    dynca_cell_percept<NS>(g, sStage, u, 2 * cp, py, px, f0);
+                    if (2 * cp + 1 < C) dynca_cell_percept<NS>(g, sStage, u, 2 * cp + 1, py, px, f1);
+                }
+                uint4 v;
+                v.x = pack_bf16(f0[0], f0[1]); v.y = pack_bf16(f0[2], f0[3]);
+                v.z = pack_bf16(f1[0], f1[1]); v.w = pack_bf16(f1[2], f1[3]);
+                *reinterpret_cast<uint4*>(sA1 + (uint32_t)cp * 2048u + row_off) = v;
+            }
+            float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (inimg) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < g.cc) {
+                        if (g.cond_kind == NCA_COND_CPE) cv[i] = (i == 0) ? dynca_cpe(gy, H, g.cpe_oh) : dynca_cpe(gx, W, g.cpe_ow);
+                        else cv[i] = __ldg(a.cond + ((size_t)(t.b * g.cc + i) * H + gy) * W + gx);
+                    } else if (i == g.cc || i == g.cc + 1) cv[i] = 1.0f;
+                }
+            }
+            uint4 v;
+            v.x = pack_bf16(cv[0], cv[1]); v.y = pack_bf16(cv[2], cv[3]); v.z = pack_bf16(cv[4], cv[5]); v.w = pack_bf16(cv[6], cv[7]);
+            *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = v;
+        }
+        fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        tc_fence_before();
+        __syncthreads();
+        // ---- GEMM1 ----
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA1), b_addr = smem_u32(sB1);
+            for (int ks = 0; ks < bg.K1 / 16; ++ks) {
+                const uint64_t da = umma_desc(a_addr + (uint32_t)ks * 2u * 2048u, 2048u, 128u);
+                const uint64_t db = umma_desc(b_addr + (uint32_t)ks * 2u * lbo_b1, lbo_b1, 128u);
+                umma_f16_ss(tmem_base, da, db, idesc1, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        __syncwarp();            // tcgen05.ld is .sync.aligned: reconverge after the single-thread issue branch
+        tc_fence_after();
+        // ---- epilogue 1: D1 -> relu -> bf16 -> A2 (overlays the stage area: all perception reads are done) ----
+        for (int j0 = 0; j0 < bg.N1; j0 += 32) {
+            uint32_t v[32];
+            if (bg.N1 - j0 >= 32) {
+                tmem_ld32(tmem_lane + (uint32_t)j0, v);
+            } else {   // fc % 32 == 16: last 16 columns
+                tmem_ld16(tmem_lane + (uint32_t)j0, v);
+#pragma unroll
+                for (int i = 16; i < 32; ++i) v[i] = 0u;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (j0 + q * 8 < bg.N1) {
+                    uint4 o;
+                    o.x = pack_bf16(fmaxf(__uint_as_float(v[q * 8 + 0]), 0.f), fmaxf(__uint_as_float(v[q * 8 + 1]), 0.f));
+                    o.y = pack_bf16(fmaxf(__uint_as_float(v[q * 8 + 2]), 0.f), fmaxf(__uint_as_float(v[q * 8 + 3]), 0.f));
+                    o.z = pack_bf16(fmaxf(__uint_as_float(v[q * 8 + 4]), 0.f), fmaxf(__uint_as_float(v[q * 8 + 5]), 0.f));
+                    o.w = pack_bf16(fmaxf(__uint_as_float(v[q * 8 + 6]), 0.f), fmaxf(__uint_as_float(v[q * 8 + 7]), 0.f));
+                    *reinterpret_cast<uint4*>(sA2 + (uint32_t)(j0 / 8 + q) * 2048u + row_off) = o;
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- GEMM2 ----
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA2), b_addr = smem_u32(sB2w);
+            for (int ks = 0; ks < bg.N1 / 16; ++ks) {
+                const uint64_t da = umma_desc(a_addr + (uint32_t)ks * 2u * 2048u, 2048u, 128u);
+                const uint64_t db = umma_desc(b_addr + (uint32_t)ks * 2u * 256u, 256u, 128u);
+                umma_f16_ss(tmem_base + tmem_d2_col, da, db, idesc2, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        __syncwarp();            // tcgen05.ld is .sync.aligned: reconverge after the single-thread issue branch
+        tc_fence_after();
+        // ---- epilogue 2: y = D2 + b2 ; x' = x + y * fire ----
+        {
+            uint32_t v[16];
+            tmem_ld16(tmem_lane + tmem_d2_col, v);
+            tmem_ld_wait();
+            if (inimg) {
+                const float fire = dynca_fire(a.fm, t.b, gy, gx, H, W);
+                const size_t off = (size_t)t.b * C * plane + (size_t)gy * W + gx;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c < C) a.x_out[off + c * plane] = __ldg(a.x_in + off + c * plane) + (__uint_as_float(v[c]) + sB2[c]) * fire;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // stage area / A1 are rewritten by the next tile; TMEM reads are complete
+    }
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)bg.tmem_cols);
+}
+
+// ---- host launchers -----------------------------------------------------------------------------------
+static int bf16_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+size_t dynca_bf16_weight_bytes(const DyncaGeom& g) {
+    Bf16Geom bg;
+    if (dynca_bf16_geom(g, &bg)) return 0;
+    return nca_align_up((size_t)bg.b1_bytes + bg.b2_bytes + 64, 256);
+}
+
+int dynca_bf16_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s) {
+    Bf16Geom bg;
+    int rc = dynca_bf16_geom(g, &bg);
+    if (rc) return rc;
+    __nv_bfloat16* B1 = (__nv_bfloat16*)ws;
+    __nv_bfloat16* B2 = (__nv_bfloat16*)((uint8_t*)ws + bg.b1_bytes);
+    float* b2p = (float*)((uint8_t*)ws + bg.b1_bytes + bg.b2_bytes);
+    dynca_bf16_prep_kernel<<<32, 256, 0, s>>>(g, bg, w->w1, w->b1, w->w2, w->b2, B1, B2, b2p);
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+int dynca_bf16_forward_step(const DyncaGeom& g, const void* ws, const float* x_in, float* x_out, const float* cond,
+                            const FireMask& fm, cudaStream_t s) {
+    DyncaBf16Args a;
+    int rc = dynca_bf16_geom(g, &a.bg);
+    if (rc) return rc;
+    a.g = g; a.x_in = x_in; a.x_out = x_out; a.cond = cond;
+    a.B1 = (const __nv_bfloat16*)ws;
+    a.B2 = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes);
+    a.b2p = (const float*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes);
+    a.fm = fm;
+    a.tiles_x = (g.W + DT_TW - 1) / DT_TW; a.tiles_y = (g.H + DT_TH - 1) / DT_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
+    const size_t smem = dynca_bf16_smem_bytes(g, a.bg);
+    if (smem > 227 * 1024) { nca_set_error("shared memory need %zu B exceeds 227 KB", smem); return NCA_ERR_UNSUPPORTED; }
+    // resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM)
+    int occ = (int)((227 * 1024) / (smem + 1024));
+    if (occ > 512 / a.bg.tmem_cols) occ = 512 / a.bg.tmem_cols;
+    if (occ > 4) occ = 4;
+    if (occ < 1) occ = 1;
+    int grid = bf16_num_sms() * occ;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    if (g.ns == 2) {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_fwd_bf16_kernel<2><<<grid, BT_THREADS, smem, s>>>(a);
+    } else {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_fwd_bf16_kernel<1><<<grid, BT_THREADS, smem, s>>>(a);
+    }
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}

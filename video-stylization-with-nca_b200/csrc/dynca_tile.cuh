@@ -47,14 +47,14 @@ __device__ __forceinline__ float dynca_tap_sx(int a, int b) { return (b == 1) ? 
 __device__ __forceinline__ float dynca_tap_sy(int a, int b) { return (a == 1) ? 0.0f : ((a == 2 ? 1.0f : -1.0f) * (b == 1 ? 2.0f : 1.0f)); }
 __device__ __forceinline__ float dynca_tap_lap(int a, int b) { return (a == 1 && b == 1) ? -12.0f : ((a == 1 || b == 1) ? 2.0f : 1.0f); }
 
-// Stage x (state of sample b around the tile) and build the perception matrix
-//   sZ[k][m], k < Ppad, m = py*32+px:  rows [id C | sobel_x C | sobel_y C | lap C | cond cc | 1 | 0..]
-// (DyNCA.perceive_multiscale, dynca.py:98-111).  Cells outside the image get z = 0.
-// sStage: dynca_stage_floats(g) floats of scratch.  Ends with __syncthreads().
-template <int NS>
-__device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const float* __restrict__ x,
-                                                    const float* __restrict__ cond, const DyncaTile& t,
-                                                    float* __restrict__ sStage, float* __restrict__ sZ) {
+// Stage the state of sample t.b around the tile into shared memory:
+//   sX  [C][DT_XR][DT_XS]    fine cells incl. the 1-cell ring, padding mode applied
+//   sXc [C][DT_CXH][DT_CXW]  (NS == 2) 2x2-mean coarse cells incl. ring, padding applied on the coarse grid
+//   sCP [4C][DT_PCH][DT_PCW] (NS == 2) coarse perception [id|sx|sy|lap] feeding the bilinear x2 of the tile
+// Ends with __syncthreads().
+template <int NS, int NT>
+__device__ __forceinline__ void dynca_stage_tile(const DyncaGeom& g, const float* __restrict__ x, const DyncaTile& t,
+                                                 float* __restrict__ sStage) {
     const int tid = threadIdx.x;
     const int C = g.C, H = g.H, W = g.W;
     const size_t plane = (size_t)H * W;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const fl
     float* sXc = sX + C * DT_XR * DT_XS;
     float* sCP = sXc + C * DT_CXH * DT_CXW;
 
-    for (int i = tid; i < C * DT_XR * DT_XS; i += DT_THREADS) {
+    for (int i = tid; i < C * DT_XR * DT_XS; i += NT) {
         int q = i % DT_XS, r = (i / DT_XS) % DT_XR, c = i / (DT_XS * DT_XR);
         int iy = nca_padmap(t.y0 - 1 + r, H, g.pad), ix = nca_padmap(t.x0 - 1 + q, W, g.pad);
         sX[i] = (iy >= 0 && ix >= 0) ? __ldg(xb + c * plane + (size_t)iy * W + ix) : 0.0f;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const fl
     if (NS == 2) {
         const int Hc = H >> 1, Wc = W >> 1;
         const int cyp = (t.y0 >> 1) - 2, cxp = (t.x0 >> 1) - 2;   // coarse padded coordinate of sXc[.][0][0]
-        for (int i = tid; i < C * DT_CXH * DT_CXW; i += DT_THREADS) {
+        for (int i = tid; i < C * DT_CXH * DT_CXW; i += NT) {
             int q = i % DT_CXW, r = (i / DT_CXW) % DT_CXH, c = i / (DT_CXW * DT_CXH);
             int qy = nca_padmap(cyp + r, Hc, g.pad), qx = nca_padmap(cxp + q, Wc, g.pad);
             float v = 0.0f;
@@ -84,8 +84,7 @@ __device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const fl
     }
     __syncthreads();
     if (NS == 2) {
-        // coarse perception at the DT_PCH x DT_PCW coarse cells whose bilinear footprint touches the tile
-        for (int i = tid; i < C * DT_PCH * DT_PCW; i += DT_THREADS) {
+        for (int i = tid; i < C * DT_PCH * DT_PCW; i += NT) {
             int q = i % DT_PCW, r = (i / DT_PCW) % DT_PCH, c = i / (DT_PCW * DT_PCH);
             float v[3][3];
 #pragma unroll
@@ -102,41 +101,69 @@ __device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const fl
         }
         __syncthreads();
     }
+}
+
+// bilinear x2 taps of the in-image cell (gy, gx) in sCP-local coordinates
+struct DyncaUp {
+    int by, bx;
+    float wy0, wy1, wx0, wx1;
+};
+__device__ __forceinline__ DyncaUp dynca_up_of(const DyncaGeom& g, const DyncaTile& t, int gy, int gx) {
+    DyncaUp u;
+    dynca_up_taps(gy, g.H >> 1, u.by, u.wy0, u.wy1);
+    dynca_up_taps(gx, g.W >> 1, u.bx, u.wx0, u.wx1);
+    u.by -= (t.y0 >> 1) - 1;
+    u.bx -= (t.x0 >> 1) - 1;
+    return u;
+}
+// the 4 perception values [id, sx, sy, lap] of channel c at tile cell (py, px) (in-image), averaged over scales
+template <int NS>
+__device__ __forceinline__ void dynca_cell_percept(const DyncaGeom& g, const float* __restrict__ sStage, const DyncaUp& u,
+                                                   int c, int py, int px, float f[4]) {
+    const int C = g.C;
+    const float* sX = sStage;
+    const float* sCP = sStage + C * DT_XR * DT_XS + C * DT_CXH * DT_CXW;
+    float v[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) v[a][bb] = sX[(c * DT_XR + py + a) * DT_XS + px + bb];
+    f[0] = v[1][1];
+    dynca_filters(v, f[1], f[2], f[3]);
+    if (NS == 2) {
+        const int ps = DT_PCH * DT_PCW;
+        const float* cp = sCP + c * ps + u.by * DT_PCW + u.bx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float* q = cp + k * C * ps;
+            float up = u.wy0 * (u.wx0 * q[0] + u.wx1 * q[1]) + u.wy1 * (u.wx0 * q[DT_PCW] + u.wx1 * q[DT_PCW + 1]);
+            f[k] = (f[k] + up) * g.s0;
+        }
+    }
+}
+
+// Stage x and build the perception matrix
+//   sZ[k][m], k < Ppad, m = py*32+px:  rows [id C | sobel_x C | sobel_y C | lap C | cond cc | 1 | 0..]
+// (DyNCA.perceive_multiscale, dynca.py:98-111).  Cells outside the image get z = 0.
+// sStage: dynca_stage_floats(g) floats of scratch.  Ends with __syncthreads().
+template <int NS>
+__device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const float* __restrict__ x,
+                                                    const float* __restrict__ cond, const DyncaTile& t,
+                                                    float* __restrict__ sStage, float* __restrict__ sZ) {
+    const int tid = threadIdx.x;
+    const int C = g.C, H = g.H, W = g.W;
+    dynca_stage_tile<NS, DT_THREADS>(g, x, t, sStage);
     {
         const int m = tid & (DT_TM - 1), half = tid >> 7;
         const int py = m >> 5, px = m & 31;
         const int gy = t.y0 + py, gx = t.x0 + px;
         const bool inimg = gy < H && gx < W;
-        int by = 0, bx = 0;
-        float wy0 = 0, wy1 = 0, wx0 = 0, wx1 = 0;
-        if (NS == 2 && inimg) {
-            dynca_up_taps(gy, H >> 1, by, wy0, wy1);
-            dynca_up_taps(gx, W >> 1, bx, wx0, wx1);
-            by -= (t.y0 >> 1) - 1;   // to sCP-local rows / cols
-            bx -= (t.x0 >> 1) - 1;
-        }
+        DyncaUp u = {};
+        if (NS == 2 && inimg) u = dynca_up_of(g, t, gy, gx);
         for (int c = half; c < C; c += 2) {
-            float f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-            if (inimg) {
-                float v[3][3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int bb = 0; bb < 3; ++bb) v[a][bb] = sX[(c * DT_XR + py + a) * DT_XS + px + bb];
-                f0 = v[1][1];
-                dynca_filters(v, f1, f2, f3);
-                if (NS == 2) {
-                    const int ps = DT_PCH * DT_PCW;
-                    const float* cp = sCP + c * ps + by * DT_PCW + bx;
-                    float u[4];
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        const float* q = cp + f * C * ps;
-                        u[f] = wy0 * (wx0 * q[0] + wx1 * q[1]) + wy1 * (wx0 * q[DT_PCW] + wx1 * q[DT_PCW + 1]);
-                    }
-                    f0 = (f0 + u[0]) * g.s0; f1 = (f1 + u[1]) * g.s0; f2 = (f2 + u[2]) * g.s0; f3 = (f3 + u[3]) * g.s0;
-                }
-            }
+            float f[4] = {0.f, 0.f, 0.f, 0.f};
+            if (inimg) dynca_cell_percept<NS>(g, sStage, u, c, py, px, f);
+            const float f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3];
             sZ[(0 * C + c) * DT_TMS + m] = f0;
             sZ[(1 * C + c) * DT_TMS + m] = f1;
             sZ[(2 * C + c) * DT_TMS + m] = f2;

@@ -56,9 +56,16 @@ static int check_common(const NcaDyncaDesc* d, DyncaGeom* g, const float* cond, 
 size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward) {
     DyncaGeom g;
     if (dynca_make_geom(d, &g)) return 0;
+    // layout: [fp32 padded weights | (backward) grad accumulators, 2 state-gradient buffers | (bf16) operand images]
     size_t n = dynca_f32_weight_floats(g);
     if (backward) n += dynca_f32_grad_floats(g) + 2 * nca_align_up((size_t)g.B * g.C * g.H * g.W, 64);
-    return n * sizeof(float);
+    size_t bytes = n * sizeof(float);
+    if (d->precision == NCA_PREC_BF16 && !backward) {
+        size_t b = dynca_bf16_weight_bytes(g);
+        if (b == 0) return 0;
+        bytes += b;
+    }
+    return bytes;
 }
 
 int nca_dynca_perceive(const NcaDyncaDesc* d, const float* x, const float* cond, float* z, void* stream) {
@@ -100,10 +107,11 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
         nca_set_error("workspace too small: %zu < %zu", workspace_bytes, nca_dynca_workspace_bytes(d, 0));
         return NCA_ERR_WORKSPACE;
     }
-    if (d->precision != NCA_PREC_FP32) { nca_set_error("precision %d not available in this build", d->precision); return NCA_ERR_UNSUPPORTED; }
     cudaStream_t s = (cudaStream_t)stream;
     float* wsW = (float*)workspace;
-    rc = dynca_f32_prep_weights(g, w, wsW, s);
+    void* wsB = (uint8_t*)workspace + dynca_f32_weight_floats(g) * sizeof(float);
+    const bool bf16 = d->precision == NCA_PREC_BF16;
+    rc = bf16 ? dynca_bf16_prep_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s);
     if (rc) return rc;
     const size_t n = (size_t)g.B * g.C * g.H * g.W;
     for (int t = 0; t < T; ++t) {
@@ -111,7 +119,7 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
         fm.t = (uint32_t)(t0 + t);
         const float* xin = keep_history ? states + (size_t)t * n : states + (size_t)(t & 1) * n;
         float* xout = keep_history ? states + (size_t)(t + 1) * n : states + (size_t)((t + 1) & 1) * n;
-        rc = dynca_f32_forward_step(g, wsW, xin, xout, cond, fm, s);
+        rc = bf16 ? dynca_bf16_forward_step(g, wsB, xin, xout, cond, fm, s) : dynca_f32_forward_step(g, wsW, xin, xout, cond, fm, s);
         if (rc) return rc;
     }
     return NCA_OK;
@@ -137,7 +145,7 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         nca_set_error("workspace too small: %zu < %zu", workspace_bytes, nca_dynca_workspace_bytes(d, 1));
         return NCA_ERR_WORKSPACE;
     }
-    if (d->precision != NCA_PREC_FP32) { nca_set_error("precision %d not available in this build", d->precision); return NCA_ERR_UNSUPPORTED; }
+    // NCA_PREC_BF16: the BPTT step still runs the fp32 CUDA-core kernel (recompute in fp32)
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)g.B * g.C * g.H * g.W, nb = n * sizeof(float);
     float* wsW = (float*)workspace;
