@@ -76,3 +76,52 @@ def test_bf16_full_size_properties():
         assert torch.equal(a, b)
         f, _ = mf.forward_nsteps(x0, T, seed=5)
     assert rel_err((a - x0).cpu(), (f - x0).cpu()) < ROLLOUT_TOL
+
+
+GRAD_TOL = 2e-2   # bf16 operands in every GEMM of the BPTT step (fp32 accumulation): gradients within 2e-2 relative
+
+
+def _grads(model, x0, T, masks, taps, coefs, **kwargs):
+    x = x0.clone().requires_grad_(True)
+    state, _, mids = model.forward_nsteps(x, T, return_middle_feature=True, masks=masks, **kwargs)
+    loss = (state * coefs[0]).sum()
+    for i, tp in enumerate(taps):
+        loss = loss + (mids[tp - 1] * coefs[1 + i]).sum()
+    gs = torch.autograd.grad(loss, [x, model.w1.weight, model.w1.bias, model.w2.weight, model.w2.bias])
+    return [g.detach().cpu() for g in gs]
+
+
+@pytest.mark.parametrize("name", DYNCA_CASES)
+def test_golden_case_bf16_gradients(name):
+    t, m = load_case(name)
+    mb, mf = build_model(m, t, precision="bf16"), build_model(m, t, precision="fp32")
+    x0, masks = t["x0"].to(DEV), t["masks"].to(DEV)
+    kwargs = dict(cond_img=t["cond_img"].to(DEV) if "cond_img" in t else None) if m["flavour"] == "cd" else {}
+    T = min(m["T"], 6)
+    taps = [tp for tp in m["taps"] if tp <= T]
+    coefs = [t["coef_final"].to(DEV)] + [t[f"coef_tap{tp}"].to(DEV) for tp in taps]
+    gb = _grads(mb, x0, T, masks[:T], taps, coefs, **kwargs)
+    gf = _grads(mf, x0, T, masks[:T], taps, coefs, **kwargs)
+    for a, b, n in zip(gb, gf, ("x0", "w1", "b1", "w2", "b2")):
+        assert rel_err(a, b) < GRAD_TOL, (n, rel_err(a, b))
+
+
+def test_bf16_backward_full_size_linearity():
+    torch.manual_seed(1)
+    B, C, fc, H, W, T = 2, 16, 128, 256, 256, 3
+    model = nca_b200.DyNCA_EC(C, 3, fc_dim=fc, padding_mode="replicate", pos_emb="CPE", perception_scales=[0, 1],
+                              device=torch.device(DEV), precision="bf16")
+    ref = nca_b200.DyNCA_EC(C, 3, fc_dim=fc, padding_mode="replicate", pos_emb="CPE", perception_scales=[0, 1],
+                            device=torch.device(DEV), precision="fp32")
+    ref.load_state_dict(model.state_dict())
+    x0 = (torch.rand(B, C, H, W, device=DEV) - 0.5).requires_grad_(True)
+    g1 = torch.randn(B, C, H, W, device=DEV)
+
+    def grads(mdl, g):
+        s, _ = mdl.forward_nsteps(x0, T, seed=99)
+        return torch.autograd.grad((s * g).sum(), [x0, mdl.w1.weight, mdl.w1.bias, mdl.w2.weight, mdl.w2.bias])
+
+    a, z, f = grads(model, g1), grads(model, torch.zeros_like(g1)), grads(ref, g1)
+    for i in range(5):
+        assert float(z[i].abs().max()) == 0.0
+        assert rel_err(a[i].cpu(), f[i].cpu()) < GRAD_TOL, (i, rel_err(a[i].cpu(), f[i].cpu()))

@@ -151,6 +151,26 @@ __global__ void dynca_bf16_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __
     }
 }
 
+
+__global__ void dynca_bf16_prep_b1_kernel(DyncaGeom g, Bf16Geom bg, const float* __restrict__ w1, const float* __restrict__ b1,
+                                          __nv_bfloat16* __restrict__ B1) {
+    const int n1 = bg.K1 * g.fc;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
+        const int kp = i / g.fc, j = i % g.fc;
+        const int kc = kp >> 3, s = kp & 7;
+        float v = 0.0f;
+        if (kc < bg.npairs) {
+            const int c = 2 * kc + (s >> 2), f = s & 3;
+            if (c < g.C) v = w1[j * g.P + f * g.C + c];
+        } else if (kc == bg.npairs) {
+            if (s < g.cc) v = w1[j * g.P + 4 * g.C + s];
+            else if (s == g.cc) v = __bfloat162float(__float2bfloat16_rn(b1[j]));
+            else if (s == g.cc + 1) v = b1[j] - __bfloat162float(__float2bfloat16_rn(b1[j]));
+        }
+        B1[(size_t)kc * (g.fc / 8) * 64 + (size_t)(j >> 3) * 64 + (j & 7) * 8 + s] = __float2bfloat16_rn(v);
+    }
+}
+
 // ---- forward step ------------------------------------------------------------------------------------
 struct DyncaBf16Args {
     DyncaGeom g;
@@ -325,6 +345,311 @@ __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaB
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)bg.tmem_cols);
 }
 
+// =====================================================================================================
+// BPTT step on the tensor cores.  256 threads: thread (m = tid & 127, half = tid >> 7) works on cell m.
+//   S1: D1 = A1 . W1^T (recompute a)          D3 = Gy . W2   (g_h)                       [128 cells x fc]
+//   E1: h = relu(D1), g_a = D3 * [D1 > 0]  ->  bf16 operands sH, sGa
+//   S2: D4 += H^T . Gy   (gW2, [fc x 16])     D5 += G_a^T . Z  (gW1 | gb1, [fc x K1])    accumulated in TMEM over
+//       D6  = G_a . W1   (g_z, [128 cells x K1])                                          all tiles of the CTA
+//   E2: D6 -> s0 * g_z as fp32 [k'][cell] -> transposed perception -> red.add into g_t
+// The weight-gradient operands are the SAME shared-memory tiles viewed MN-major (cells become K):
+//   tile (cell m, col j) at (j/8)*2048 + (m/8)*128 + (m%8)*16 + (j%8)*2  ==  K-major  [m][j]  (LBO 2048, SBO 128)
+//                                                                      ==  MN-major [j][m]  (SBO 2048, LBO 128)
+// =====================================================================================================
+#define BB_THREADS 256
+#define BB_TMEM_D1 0u
+#define BB_TMEM_D3 128u
+#define BB_TMEM_D4 256u
+#define BB_TMEM_D5 272u
+#define BB_TMEM_D6 352u
+
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {   // both operands MN-major
+    return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
+
+// B1t [N=K1][K=fc] (dgrad1) and B2d [N=fc][K=16] (dgrad2) operand images
+__global__ void dynca_bf16_prep_bwd_kernel(DyncaGeom g, Bf16Geom bg, const float* __restrict__ w1, const float* __restrict__ b1,
+                                           const float* __restrict__ w2, __nv_bfloat16* __restrict__ B1t,
+                                           __nv_bfloat16* __restrict__ B2d) {
+    const int n1 = bg.K1 * g.fc, n2 = g.fc * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+        if (i < n1) {
+            const int kp = i / g.fc, j = i % g.fc;
+            const int kc = kp >> 3, s = kp & 7;
+            float v = 0.0f;
+            if (kc < bg.npairs) {
+                const int c = 2 * kc + (s >> 2), f = s & 3;
+                if (c < g.C) v = w1[j * g.P + f * g.C + c];
+            }   // cond / bias columns of g_z are never used: leave zero
+            const size_t off = (size_t)(j >> 3) * (bg.K1 / 8) * 64 + (size_t)kc * 64 + s * 8 + (j & 7);
+            B1t[off] = __float2bfloat16_rn(v);
+        } else {
+            const int e = i - n1, j = e / 16, c = e % 16;
+            const float v = c < g.C ? w2[c * g.fc + j] : 0.0f;
+            const size_t off = (size_t)(c >> 3) * (g.fc / 8) * 64 + (size_t)(j >> 3) * 64 + (j & 7) * 8 + (c & 7);
+            B2d[off] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+struct DyncaBf16BwdArgs {
+    DyncaGeom g;
+    Bf16Geom bg;
+    const float* x_in; const float* g_next; const float* g_tap; int tap_c; float tap_scale;
+    float* g_out; const float* cond;
+    const __nv_bfloat16* B1; const __nv_bfloat16* B1t; const __nv_bfloat16* B2d;
+    float* gW1p; float* gW2p; float* gb2p;      // fp32 accumulators, padded fp32-path layout (red.add)
+    FireMask fm;
+    int tiles_x, tiles_y, n_tiles;
+};
+
+static inline size_t dynca_bf16_bwd_smem_bytes(const DyncaGeom& g, const Bf16Geom& bg) {
+    return 1024 + 128 + bg.a1_bytes + 4096 /*Gy*/ + 2 * 32768 /*H, Ga*/ + 2 * bg.b1_bytes + (size_t)2 * (g.fc / 8) * 128 +
+           (size_t)dynca_stage_floats(g) * 4;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const DyncaBf16BwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const DyncaGeom& g = a.g;
+    const Bf16Geom& bg = a.bg;
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 8);
+    uint8_t* sA1 = base + 128;
+    uint8_t* sGy = sA1 + bg.a1_bytes;
+    uint8_t* sH = sGy + 4096;
+    uint8_t* sGa = sH + 32768;
+    uint8_t* sB1 = sGa + 32768;
+    uint8_t* sB1t = sB1 + bg.b1_bytes;
+    uint8_t* sB2d = sB1t + bg.b1_bytes;
+    float* sStage = reinterpret_cast<float*>(sB2d + (size_t)2 * (g.fc / 8) * 128);
+    float* sGz = reinterpret_cast<float*>(sH);       // fp32 [8*npairs][DT_TMS], overlays H | Ga after S2 completes
+    float* sScr = reinterpret_cast<float*>(sA1);     // scatter scratch (NS == 2), overlays A1 after S2 completes
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = tid & 127, half = tid >> 7;
+    const int C = g.C, H = g.H, W = g.W, fc = g.fc;
+    const size_t plane = (size_t)H * W;
+
+    for (uint32_t i = tid; i < bg.b1_bytes / 16; i += BB_THREADS) {
+        reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
+        reinterpret_cast<uint4*>(sB1t)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1t) + i);
+    }
+    for (uint32_t i = tid; i < (uint32_t)(2 * (fc / 8) * 128) / 16; i += BB_THREADS)
+        reinterpret_cast<uint4*>(sB2d)[i] = __ldg(reinterpret_cast<const uint4*>(a.B2d) + i);
+    // zero everything the MMAs read but the tile loop never writes: A1 chunks past the cond chunk, H / Ga chunks
+    // past fc/8 (rows fc..127 of the M=128 weight-gradient operands)
+    for (uint32_t i = tid; i < bg.a1_bytes / 16; i += BB_THREADS) reinterpret_cast<uint4*>(sA1)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < (2u * 32768u) / 16; i += BB_THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t idesc_fc = umma_idesc_bf16(128, fc), idesc_k1 = umma_idesc_bf16(128, bg.K1);
+    const uint32_t idesc_w2 = umma_idesc_bf16_mn(128, 16), idesc_w1 = umma_idesc_bf16_mn(128, bg.K1);
+    const uint32_t lbo_fc = (uint32_t)(fc / 8) * 128u, lbo_k1 = (uint32_t)(bg.K1 / 8) * 128u;
+    uint32_t phase = 0;
+    const int py = m >> 5, px = m & 31;
+    const uint32_t row_off = (uint32_t)(m >> 3) * 128u + (uint32_t)(m & 7) * 16u;
+    float b2acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b2acc[i] = 0.0f;
+    bool first = true;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const DyncaTile t = dynca_tile_of(tile, a.tiles_x, a.tiles_y);
+        const int gy = t.y0 + py, gx = t.x0 + px;
+        const bool inimg = gy < H && gx < W;
+        dynca_stage_tile<NS, BB_THREADS>(g, a.x_in, t, sStage);
+        // ---- recompute perception -> A1 ----
+        {
+            DyncaUp u = {};
+            if (NS == 2 && inimg) u = dynca_up_of(g, t, gy, gx);
+            for (int cp = half; cp < bg.npairs; cp += 2) {
+                float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+                if (inimg) {
+                    dynca_cell_percept<NS>(g, sStage, u, 2 * cp, py, px, f0);
+                    if (2 * cp + 1 < C) dynca_cell_percept<NS>(g, sStage, u, 2 * cp + 1, py, px, f1);
+                }
+                uint4 v;
+                v.x = pack_bf16(f0[0], f0[1]); v.y = pack_bf16(f0[2], f0[3]);
+                v.z = pack_bf16(f1[0], f1[1]); v.w = pack_bf16(f1[2], f1[3]);
+                *reinterpret_cast<uint4*>(sA1 + (uint32_t)cp * 2048u + row_off) = v;
+            }
+            if (half == 0) {
+                float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (inimg) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < g.cc) {
+                            if (g.cond_kind == NCA_COND_CPE) cv[i] = (i == 0) ? dynca_cpe(gy, H, g.cpe_oh) : dynca_cpe(gx, W, g.cpe_ow);
+                            else cv[i] = __ldg(a.cond + ((size_t)(t.b * g.cc + i) * H + gy) * W + gx);
+                        } else if (i == g.cc || i == g.cc + 1) cv[i] = 1.0f;
+                    }
+                }
+                uint4 v;
+                v.x = pack_bf16(cv[0], cv[1]); v.y = pack_bf16(cv[2], cv[3]); v.z = pack_bf16(cv[4], cv[5]); v.w = pack_bf16(cv[6], cv[7]);
+                *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = v;
+            }
+            // chunks past the cond chunk were overwritten by the scatter scratch of the previous tile: re-zero
+            for (uint32_t i = tid + (uint32_t)(bg.npairs + 1) * 128; i < bg.a1_bytes / 16; i += BB_THREADS)
+                reinterpret_cast<uint4*>(sA1)[i] = make_uint4(0, 0, 0, 0);
+        }
+        // ---- g_y = fire * g_{t+1}: this thread's 8 channels of its cell ----
+        {
+            float gyv[8];
+            const float fire = inimg ? dynca_fire(a.fm, t.b, gy, gx, H, W) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = 8 * half + i;
+                gyv[i] = (inimg && c < C) ? fire * dynca_gnext(a.g_next, a.g_tap, a.tap_c, a.tap_scale, C, t.b, c, (size_t)gy * W + gx, plane) : 0.0f;
+                b2acc[i] += gyv[i];
+            }
+            uint4 v;
+            v.x = pack_bf16(gyv[0], gyv[1]); v.y = pack_bf16(gyv[2], gyv[3]); v.z = pack_bf16(gyv[4], gyv[5]); v.w = pack_bf16(gyv[6], gyv[7]);
+            *reinterpret_cast<uint4*>(sGy + (uint32_t)half * 2048u + row_off) = v;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- S1: D1 = A1 . W1^T ; D3 = Gy . W2 ----
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA1), b_addr = smem_u32(sB1);
+            for (int ks = 0; ks < bg.K1 / 16; ++ks)
+                umma_f16_ss(tmem_base + BB_TMEM_D1, umma_desc(a_addr + (uint32_t)ks * 4096u, 2048u, 128u),
+                            umma_desc(b_addr + (uint32_t)ks * 2u * lbo_fc, lbo_fc, 128u), idesc_fc, ks > 0 ? 1u : 0u);
+            umma_f16_ss(tmem_base + BB_TMEM_D3, umma_desc(smem_u32(sGy), 2048u, 128u), umma_desc(smem_u32(sB2d), lbo_fc, 128u),
+                        idesc_fc, 0u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+        // ---- E1: h, g_a -> bf16 operands; half -> columns [64*half, 64*half + 64) ----
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+            const int j0 = 64 * half + 32 * blk;
+            if (j0 < fc) {     // warp-uniform
+                uint32_t av[32], gv[32];
+                tmem_ld32(tmem_lane + BB_TMEM_D1 + (uint32_t)j0, av);
+                tmem_ld32(tmem_lane + BB_TMEM_D3 + (uint32_t)j0, gv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float hh[8], ga[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float av_ = __uint_as_float(av[q * 8 + i]);
+                        hh[i] = fmaxf(av_, 0.0f);
+                        ga[i] = av_ > 0.0f ? __uint_as_float(gv[q * 8 + i]) : 0.0f;
+                    }
+                    uint4 o;
+                    o.x = pack_bf16(hh[0], hh[1]); o.y = pack_bf16(hh[2], hh[3]); o.z = pack_bf16(hh[4], hh[5]); o.w = pack_bf16(hh[6], hh[7]);
+                    *reinterpret_cast<uint4*>(sH + (uint32_t)(j0 / 8 + q) * 2048u + row_off) = o;
+                    o.x = pack_bf16(ga[0], ga[1]); o.y = pack_bf16(ga[2], ga[3]); o.z = pack_bf16(ga[4], ga[5]); o.w = pack_bf16(ga[6], ga[7]);
+                    *reinterpret_cast<uint4*>(sGa + (uint32_t)(j0 / 8 + q) * 2048u + row_off) = o;
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- S2: weight gradients (accumulated in TMEM across tiles) and g_z ----
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t h_addr = smem_u32(sH), ga_addr = smem_u32(sGa), gy_addr = smem_u32(sGy), z_addr = smem_u32(sA1);
+            for (int ks = 0; ks < 8; ++ks) {   // 16 cells per instruction
+                const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                umma_f16_ss(tmem_base + BB_TMEM_D4, umma_desc(h_addr + (uint32_t)ks * 256u, 128u, 2048u),
+                            umma_desc(gy_addr + (uint32_t)ks * 256u, 128u, 2048u), idesc_w2, acc);
+                umma_f16_ss(tmem_base + BB_TMEM_D5, umma_desc(ga_addr + (uint32_t)ks * 256u, 128u, 2048u),
+                            umma_desc(z_addr + (uint32_t)ks * 256u, 128u, 2048u), idesc_w1, acc);
+            }
+            const uint32_t bt_addr = smem_u32(sB1t);
+            for (int ks = 0; ks < fc / 16; ++ks)
+                umma_f16_ss(tmem_base + BB_TMEM_D6, umma_desc(ga_addr + (uint32_t)ks * 4096u, 2048u, 128u),
+                            umma_desc(bt_addr + (uint32_t)ks * 2u * lbo_k1, lbo_k1, 128u), idesc_k1, ks > 0 ? 1u : 0u);
+            umma_commit(bar);
+        }
+        first = false;
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+        // ---- E2: g_z -> fp32 [k'][cell] (overlays H | Ga: every MMA that read them has completed) ----
+        {
+            const int k0 = 32 * half;
+            if (k0 < 8 * bg.npairs) {
+                uint32_t v[32];
+                tmem_ld32(tmem_lane + BB_TMEM_D6 + (uint32_t)k0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (k0 + i < 8 * bg.npairs) sGz[(k0 + i) * DT_TMS + m] = __uint_as_float(v[i]) * g.s0;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        dynca_scatter_tile<NS, BB_THREADS, true>(g, t, sGz, sScr, a.g_out, a.g_next, a.g_tap, a.tap_c, a.tap_scale);
+        __syncthreads();
+        // H / Ga rows past fc and the zero tail were clobbered by sGz: restore the zeros the next S2 relies on
+        if (fc < 128)
+            for (uint32_t i = tid; i < (uint32_t)(16 - fc / 8) * 128u; i += BB_THREADS) {
+                reinterpret_cast<uint4*>(sH + (uint32_t)(fc / 8) * 2048u)[i] = make_uint4(0, 0, 0, 0);
+                reinterpret_cast<uint4*>(sGa + (uint32_t)(fc / 8) * 2048u)[i] = make_uint4(0, 0, 0, 0);
+            }
+    }
+    // ---- flush: D4 [fc x 16] -> gW2p[j][c];  D5 [fc x K1] -> gW1p[k][j] (k' -> reference k);  gb2 ----
+    {
+        const int j = (warp & 3) * 32 + lane;
+        uint32_t v[32];
+        if (half == 0) {
+            tmem_ld16(tmem_lane + BB_TMEM_D4, v);
+            tmem_ld_wait();
+            if (j < fc)
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c < C) atomicAdd(a.gW2p + j * g.CP + c, __uint_as_float(v[c]));
+        }
+        for (int k0 = 32 * half; k0 < bg.K1; k0 += 64) {
+            if (bg.K1 - k0 >= 32) tmem_ld32(tmem_lane + BB_TMEM_D5 + (uint32_t)k0, v);
+            else tmem_ld16(tmem_lane + BB_TMEM_D5 + (uint32_t)k0, v);
+            tmem_ld_wait();
+            if (j < fc) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int kp = k0 + i;
+                    if (kp >= bg.K1 || (i >= 16 && bg.K1 - k0 < 32)) continue;
+                    const int kc = kp >> 3, s = kp & 7;
+                    int k = -1;
+                    if (kc < bg.npairs) { const int c = 2 * kc + (s >> 2); if (c < C) k = (s & 3) * C + c; }
+                    else if (kc == bg.npairs) { if (s < g.cc) k = 4 * C + s; else if (s == g.cc) k = g.P; }
+                    if (k >= 0) atomicAdd(a.gW1p + k * g.FCpad + j, __uint_as_float(v[i]));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float s = b2acc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && 8 * half + i < C) atomicAdd(a.gb2p + 8 * half + i, s);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
 // ---- host launchers -----------------------------------------------------------------------------------
 static int bf16_num_sms() {
     static int n = 0;
@@ -379,6 +704,61 @@ int dynca_bf16_forward_step(const DyncaGeom& g, const void* ws, const float* x_i
     } else {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dynca_fwd_bf16_kernel<1><<<grid, BT_THREADS, smem, s>>>(a);
+    }
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+size_t dynca_bf16_bwd_weight_bytes(const DyncaGeom& g) {
+    Bf16Geom bg;
+    if (dynca_bf16_geom(g, &bg)) return 0;
+    return nca_align_up((size_t)2 * bg.b1_bytes + (size_t)2 * (g.fc / 8) * 128 + 64, 256);
+}
+bool dynca_bf16_bwd_supported(const DyncaGeom& g) {
+    Bf16Geom bg;
+    if (g.fc % 32 != 0 || g.fc > 128 || g.cc + 2 > 8) return false;
+    if (dynca_bf16_geom(g, &bg)) return false;
+    return bg.K1 <= 80 && dynca_bf16_bwd_smem_bytes(g, bg) <= 227 * 1024;
+}
+
+int dynca_bf16_prep_bwd_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s) {
+    Bf16Geom bg;
+    int rc = dynca_bf16_geom(g, &bg);
+    if (rc) return rc;
+    __nv_bfloat16* B1 = (__nv_bfloat16*)ws;
+    __nv_bfloat16* B1t = (__nv_bfloat16*)((uint8_t*)ws + bg.b1_bytes);
+    __nv_bfloat16* B2d = (__nv_bfloat16*)((uint8_t*)ws + 2 * bg.b1_bytes);
+    // B1 via the forward packer (its B2 / b2 outputs go to a scratch tail that is not used here)
+    dynca_bf16_prep_bwd_kernel<<<32, 256, 0, s>>>(g, bg, w->w1, w->b1, w->w2, B1t, B2d);
+    NCA_LAUNCH_OK();
+    dynca_bf16_prep_b1_kernel<<<32, 256, 0, s>>>(g, bg, w->w1, w->b1, B1);
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const float* x_in, const float* g_next,
+                             const float* g_tap, int tap_c, float tap_scale, float* g_out, const float* cond,
+                             const FireMask& fm, cudaStream_t s) {
+    DyncaBf16BwdArgs a;
+    int rc = dynca_bf16_geom(g, &a.bg);
+    if (rc) return rc;
+    a.g = g; a.x_in = x_in; a.g_next = g_next; a.g_tap = g_tap; a.tap_c = tap_c; a.tap_scale = tap_scale;
+    a.g_out = g_out; a.cond = cond;
+    a.B1 = (const __nv_bfloat16*)ws;
+    a.B1t = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes);
+    a.B2d = (const __nv_bfloat16*)((const uint8_t*)ws + 2 * a.bg.b1_bytes);
+    a.gW1p = wsG; a.gW2p = a.gW1p + (size_t)g.Ppad * g.FCpad; a.gb2p = a.gW2p + (size_t)g.FCpad * g.CP;
+    a.fm = fm;
+    a.tiles_x = (g.W + DT_TW - 1) / DT_TW; a.tiles_y = (g.H + DT_TH - 1) / DT_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
+    const size_t smem = dynca_bf16_bwd_smem_bytes(g, a.bg);
+    int grid = bf16_num_sms();
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    if (g.ns == 2) {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_bwd_bf16_kernel<2><<<grid, BB_THREADS, smem, s>>>(a);
+    } else {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_bwd_bf16_kernel<1><<<grid, BB_THREADS, smem, s>>>(a);
     }
     NCA_LAUNCH_OK();
     return NCA_OK;

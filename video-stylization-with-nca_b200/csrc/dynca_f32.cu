@@ -209,12 +209,6 @@ static inline size_t dynca_bwd_smem_floats(const DyncaGeom& g) {
     return (size_t)g.Ppad * g.FCpad + (size_t)g.CP * g.FCpad + DT_TM + (size_t)g.CP * DT_TMS + (size_t)g.Ppad * DT_TMS + u;
 }
 
-__device__ __forceinline__ float dynca_gnext(const DyncaBwdArgs& a, int b, int c, size_t pix, size_t plane) {
-    float v = a.g_next ? __ldg(a.g_next + ((size_t)b * a.g.C + c) * plane + pix) : 0.0f;
-    if (a.g_tap && c < a.tap_c) v = fmaf(a.tap_scale, __ldg(a.g_tap + ((size_t)b * a.tap_c + c) * plane + pix), v);
-    return v;
-}
-
 template <int NS>
 __global__ void __launch_bounds__(DT_THREADS, 1) dynca_bwd_f32_kernel(const DyncaBwdArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -261,7 +255,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dynca_bwd_f32_kernel(const Dync
             int c = i >> 7, m = i & 127;
             int gy = t.y0 + (m >> 5), gx = t.x0 + (m & 31);
             float v = 0.0f;
-            if (c < C && gy < H && gx < W) v = sMask[m] * dynca_gnext(a, t.b, c, (size_t)gy * W + gx, plane);
+            if (c < C && gy < H && gx < W) v = sMask[m] * dynca_gnext(a.g_next, a.g_tap, a.tap_c, a.tap_scale, C, t.b, c, (size_t)gy * W + gx, plane);
             sGy[c * DT_TMS + m] = v;
         }
         float acc[8][8];
@@ -399,90 +393,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dynca_bwd_f32_kernel(const Dync
             }
         }
         __syncthreads();   // sZ now holds s0 * g_z (rows < 4C)
-        float* gob = a.g_out + (size_t)t.b * C * plane;
-        // ---- scale 0: transposed 3x3 stencils over the tile + ring, residual pass-through, red.add ----
-        for (int i = tid; i < C * DT_XR * DT_XS; i += DT_THREADS) {
-            const int rx = i % DT_XS, ry = (i / DT_XS) % DT_XR, c = i / (DT_XS * DT_XR);
-            const int yy = t.y0 - 1 + ry, xx = t.x0 - 1 + rx;     // padded coordinate of this position
-            if (yy > H || xx > W) continue;
-            float v = 0.0f;
-#pragma unroll
-            for (int aa = 0; aa < 3; ++aa) {
-                const int py = ry - aa;
-                if (py < 0 || py >= DT_TH) continue;
-#pragma unroll
-                for (int bb = 0; bb < 3; ++bb) {
-                    const int px = rx - bb;
-                    if (px < 0 || px >= DT_TW) continue;
-                    const int m = py * DT_TW + px;
-                    v = fmaf(dynca_tap_sx(aa, bb), sZ[(C + c) * DT_TMS + m], v);
-                    v = fmaf(dynca_tap_sy(aa, bb), sZ[(2 * C + c) * DT_TMS + m], v);
-                    v = fmaf(dynca_tap_lap(aa, bb), sZ[(3 * C + c) * DT_TMS + m], v);
-                }
-            }
-            // in-tile AND in-image cells also get the identity tap and the residual pass-through; in-tile cells
-            // beyond the image edge are ordinary pad positions of the last image row / column
-            const bool interior = ry >= 1 && ry <= DT_TH && rx >= 1 && rx <= DT_TW && yy < H && xx < W;
-            if (interior) {
-                v += sZ[c * DT_TMS + (ry - 1) * DT_TW + (rx - 1)];
-                v += dynca_gnext(a, t.b, c, (size_t)yy * W + xx, plane);
-            }
-            const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
-            if (iy < 0 || ix < 0) continue;
-            atomicAdd(gob + c * plane + (size_t)iy * W + ix, v);
-        }
-        if (NS == 2) {
-            // ---- scale 1: Up^T (bilinear x2) -> coarse g_percept, stencil^T on the coarse grid, Down^T ----
-            const int Hc = H >> 1, Wc = W >> 1;
-            const int cy0 = (t.y0 >> 1) - 1, cx0 = (t.x0 >> 1) - 1;
-            const int ps = DT_PCH * DT_PCW;
-            float* sG = sU;   // [4C][PCH*PCW]
-            for (int i = tid; i < 4 * C * ps; i += DT_THREADS) {
-                const int pq = i % DT_PCW, pr = (i / DT_PCW) % DT_PCH, k = i / ps;
-                const int qy = cy0 + pr, qx = cx0 + pq;
-                float v = 0.0f;
-                if (qy >= 0 && qy < Hc && qx >= 0 && qx < Wc) {
-                    for (int fy = 2 * qy - 1; fy <= 2 * qy + 2; ++fy) {
-                        const int py = fy - t.y0;
-                        if (py < 0 || py >= DT_TH || fy >= H) continue;
-                        const float wy = dynca_up_weight(fy, qy, Hc);
-                        for (int fx = 2 * qx - 1; fx <= 2 * qx + 2; ++fx) {
-                            const int px = fx - t.x0;
-                            if (px < 0 || px >= DT_TW || fx >= W) continue;
-                            v = fmaf(wy * dynca_up_weight(fx, qx, Wc), sZ[k * DT_TMS + py * DT_TW + px], v);
-                        }
-                    }
-                }
-                sG[i] = v;
-            }
-            __syncthreads();
-            for (int i = tid; i < C * DT_CXH * DT_CXW; i += DT_THREADS) {
-                const int rx = i % DT_CXW, ry = (i / DT_CXW) % DT_CXH, c = i / (DT_CXW * DT_CXH);
-                const int yy = cy0 - 1 + ry, xx = cx0 - 1 + rx;   // coarse padded coordinate
-                if (yy < -1 || xx < -1 || yy > Hc || xx > Wc) continue;
-                float v = 0.0f;
-#pragma unroll
-                for (int aa = 0; aa < 3; ++aa) {
-                    const int pr = ry - aa;
-                    if (pr < 0 || pr >= DT_PCH) continue;
-#pragma unroll
-                    for (int bb = 0; bb < 3; ++bb) {
-                        const int pq = rx - bb;
-                        if (pq < 0 || pq >= DT_PCW) continue;
-                        const int o = pr * DT_PCW + pq;
-                        v = fmaf(dynca_tap_sx(aa, bb), sG[(C + c) * ps + o], v);
-                        v = fmaf(dynca_tap_sy(aa, bb), sG[(2 * C + c) * ps + o], v);
-                        v = fmaf(dynca_tap_lap(aa, bb), sG[(3 * C + c) * ps + o], v);
-                    }
-                }
-                if (ry >= 1 && ry <= DT_PCH && rx >= 1 && rx <= DT_PCW) v += sG[c * ps + (ry - 1) * DT_PCW + (rx - 1)];
-                const int qy = nca_padmap(yy, Hc, g.pad), qx = nca_padmap(xx, Wc, g.pad);
-                if (qy < 0 || qx < 0 || v == 0.0f) continue;
-                float* p = gob + c * plane + (size_t)(2 * qy) * W + 2 * qx;
-                v *= 0.25f;
-                atomicAdd(p, v); atomicAdd(p + 1, v); atomicAdd(p + W, v); atomicAdd(p + W + 1, v);
-            }
-        }
+        // transposed perception of s0*g_z (+ residual pass-through of g_{t+1}) -> red.add into g_out
+        dynca_scatter_tile<NS, DT_THREADS, false>(g, t, sZ, sU, a.g_out, a.g_next, a.g_tap, a.tap_c, a.tap_scale);
         __syncthreads();   // smem reused by the next tile
     }
     // ---- flush weight-gradient partial sums ----

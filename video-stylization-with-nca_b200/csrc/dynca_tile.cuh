@@ -185,6 +185,123 @@ __device__ __forceinline__ void dynca_perceive_tile(const DyncaGeom& g, const fl
     __syncthreads();
 }
 
+// gradient arriving at states[t+1]: what later steps propagated plus an optional rgb tap (tap_scale * g_tap on the
+// first tap_c channels)
+__device__ __forceinline__ float dynca_gnext(const float* __restrict__ g_next, const float* __restrict__ g_tap, int tap_c,
+                                             float tap_scale, int C, int b, int c, size_t pix, size_t plane) {
+    float v = g_next ? __ldg(g_next + ((size_t)b * C + c) * plane + pix) : 0.0f;
+    if (g_tap && c < tap_c) v = fmaf(tap_scale, __ldg(g_tap + ((size_t)b * tap_c + c) * plane + pix), v);
+    return v;
+}
+
+// row of the [k][cell] perception-gradient matrix that holds (channel c, filter f):
+//   KPERM == false: reference order  f*C + c            (fp32 path)
+//   KPERM == true : tensor-core order 8*(c/2) + 4*(c%2) + f   (bf16 path, see dynca_bf16.cu)
+template <bool KPERM>
+__device__ __forceinline__ int dynca_krow(int C, int c, int f) {
+    return KPERM ? (8 * (c >> 1) + 4 * (c & 1) + f) : (f * C + c);
+}
+
+// Transposed perception of one tile.  sZ holds s0 * g_z as [k][cell] (row stride DT_TMS); the result
+//   g_t = g_{t+1} (+tap) + Perceive^T(g_z)
+// is accumulated with red.add into g_out (zeroed by the caller): contributions to the tile's ring land in the
+// neighbouring tiles' cells (or wrap / fold back according to the padding mode).  sG: 4C*DT_PCH*DT_PCW floats of
+// scratch (NS == 2).  Caller must __syncthreads() before (sZ complete) and after (smem reuse).
+template <int NS, int NT, bool KPERM>
+__device__ __forceinline__ void dynca_scatter_tile(const DyncaGeom& g, const DyncaTile& t, const float* __restrict__ sZ,
+                                                   float* __restrict__ sU, float* __restrict__ g_out,
+                                                   const float* __restrict__ g_next, const float* __restrict__ g_tap,
+                                                   int tap_c, float tap_scale) {
+    const int tid = threadIdx.x;
+    const int C = g.C, H = g.H, W = g.W;
+    const size_t plane = (size_t)H * W;
+    float* gob = g_out + (size_t)t.b * C * plane;
+    // ---- scale 0: transposed 3x3 stencils over the tile + ring, residual pass-through, red.add ----
+    for (int i = tid; i < C * DT_XR * DT_XS; i += NT) {
+        const int rx = i % DT_XS, ry = (i / DT_XS) % DT_XR, c = i / (DT_XS * DT_XR);
+        const int yy = t.y0 - 1 + ry, xx = t.x0 - 1 + rx;     // padded coordinate of this position
+        if (yy > H || xx > W) continue;
+        float v = 0.0f;
+#pragma unroll
+        for (int aa = 0; aa < 3; ++aa) {
+            const int py = ry - aa;
+            if (py < 0 || py >= DT_TH) continue;
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) {
+                const int px = rx - bb;
+                if (px < 0 || px >= DT_TW) continue;
+                const int m = py * DT_TW + px;
+                v = fmaf(dynca_tap_sx(aa, bb), sZ[dynca_krow<KPERM>(C, c, 1) * DT_TMS + m], v);
+                v = fmaf(dynca_tap_sy(aa, bb), sZ[dynca_krow<KPERM>(C, c, 2) * DT_TMS + m], v);
+                v = fmaf(dynca_tap_lap(aa, bb), sZ[dynca_krow<KPERM>(C, c, 3) * DT_TMS + m], v);
+            }
+        }
+        // in-tile AND in-image cells also get the identity tap and the residual pass-through; in-tile cells
+        // beyond the image edge are ordinary pad positions of the last image row / column
+        const bool interior = ry >= 1 && ry <= DT_TH && rx >= 1 && rx <= DT_TW && yy < H && xx < W;
+        if (interior) {
+            v += sZ[dynca_krow<KPERM>(C, c, 0) * DT_TMS + (ry - 1) * DT_TW + (rx - 1)];
+            v += dynca_gnext(g_next, g_tap, tap_c, tap_scale, C, t.b, c, (size_t)yy * W + xx, plane);
+        }
+        const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
+        if (iy < 0 || ix < 0) continue;
+        atomicAdd(gob + c * plane + (size_t)iy * W + ix, v);
+    }
+    if (NS == 2) {
+        // ---- scale 1: Up^T (bilinear x2) -> coarse g_percept, stencil^T on the coarse grid, Down^T ----
+        const int Hc = H >> 1, Wc = W >> 1;
+        const int cy0 = (t.y0 >> 1) - 1, cx0 = (t.x0 >> 1) - 1;
+        const int ps = DT_PCH * DT_PCW;
+        float* sG = sU;   // [4C][PCH*PCW]
+        for (int i = tid; i < 4 * C * ps; i += NT) {
+            const int pq = i % DT_PCW, pr = (i / DT_PCW) % DT_PCH, k = i / ps;
+            const int krow = dynca_krow<KPERM>(C, k % C, k / C);
+            const int qy = cy0 + pr, qx = cx0 + pq;
+            float v = 0.0f;
+            if (qy >= 0 && qy < Hc && qx >= 0 && qx < Wc) {
+                for (int fy = 2 * qy - 1; fy <= 2 * qy + 2; ++fy) {
+                    const int py = fy - t.y0;
+                    if (py < 0 || py >= DT_TH || fy >= H) continue;
+                    const float wy = dynca_up_weight(fy, qy, Hc);
+                    for (int fx = 2 * qx - 1; fx <= 2 * qx + 2; ++fx) {
+                        const int px = fx - t.x0;
+                        if (px < 0 || px >= DT_TW || fx >= W) continue;
+                        v = fmaf(wy * dynca_up_weight(fx, qx, Wc), sZ[krow * DT_TMS + py * DT_TW + px], v);
+                    }
+                }
+            }
+            sG[i] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < C * DT_CXH * DT_CXW; i += NT) {
+            const int rx = i % DT_CXW, ry = (i / DT_CXW) % DT_CXH, c = i / (DT_CXW * DT_CXH);
+            const int yy = cy0 - 1 + ry, xx = cx0 - 1 + rx;   // coarse padded coordinate
+            if (yy < -1 || xx < -1 || yy > Hc || xx > Wc) continue;
+            float v = 0.0f;
+#pragma unroll
+            for (int aa = 0; aa < 3; ++aa) {
+                const int pr = ry - aa;
+                if (pr < 0 || pr >= DT_PCH) continue;
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) {
+                    const int pq = rx - bb;
+                    if (pq < 0 || pq >= DT_PCW) continue;
+                    const int o = pr * DT_PCW + pq;
+                    v = fmaf(dynca_tap_sx(aa, bb), sG[(C + c) * ps + o], v);
+                    v = fmaf(dynca_tap_sy(aa, bb), sG[(2 * C + c) * ps + o], v);
+                    v = fmaf(dynca_tap_lap(aa, bb), sG[(3 * C + c) * ps + o], v);
+                }
+            }
+            if (ry >= 1 && ry <= DT_PCH && rx >= 1 && rx <= DT_PCW) v += sG[c * ps + (ry - 1) * DT_PCW + (rx - 1)];
+            const int qy = nca_padmap(yy, Hc, g.pad), qx = nca_padmap(xx, Wc, g.pad);
+            if (qy < 0 || qx < 0 || v == 0.0f) continue;
+            float* p = gob + c * plane + (size_t)(2 * qy) * W + 2 * qx;
+            v *= 0.25f;
+            atomicAdd(p, v); atomicAdd(p + 1, v); atomicAdd(p + W, v); atomicAdd(p + W + 1, v);
+        }
+    }
+}
+
 // GEMM1: acc[i][jj] = sum_k sZ[k][pix(i)] * sW1[k][ty*8+jj], k <= P (bias row included).
 // pix(i) = tx*4+i (i<4) | 64+tx*4+(i-4);  tx = tid & 15, ty = tid >> 4.  Threads with ty*8 >= FCpad idle.
 __device__ __forceinline__ void dynca_gemm1(const DyncaGeom& g, const float* __restrict__ sZ,

@@ -60,8 +60,8 @@ size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward) {
     size_t n = dynca_f32_weight_floats(g);
     if (backward) n += dynca_f32_grad_floats(g) + 2 * nca_align_up((size_t)g.B * g.C * g.H * g.W, 64);
     size_t bytes = n * sizeof(float);
-    if (d->precision == NCA_PREC_BF16 && !backward) {
-        size_t b = dynca_bf16_weight_bytes(g);
+    if (d->precision == NCA_PREC_BF16) {
+        size_t b = backward ? dynca_bf16_bwd_weight_bytes(g) : dynca_bf16_weight_bytes(g);
         if (b == 0) return 0;
         bytes += b;
     }
@@ -145,13 +145,15 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         nca_set_error("workspace too small: %zu < %zu", workspace_bytes, nca_dynca_workspace_bytes(d, 1));
         return NCA_ERR_WORKSPACE;
     }
-    // NCA_PREC_BF16: the BPTT step still runs the fp32 CUDA-core kernel (recompute in fp32)
+    // NCA_PREC_BF16: tcgen05 BPTT kernel when the shape is supported (fc % 32 == 0, fc <= 128), else the fp32 kernel
+    const bool bf16 = d->precision == NCA_PREC_BF16 && dynca_bf16_bwd_supported(g);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)g.B * g.C * g.H * g.W, nb = n * sizeof(float);
     float* wsW = (float*)workspace;
     float* wsG = wsW + dynca_f32_weight_floats(g);
     float* gbuf[2] = {wsG + dynca_f32_grad_floats(g), wsG + dynca_f32_grad_floats(g) + nca_align_up(n, 64)};
-    rc = dynca_f32_prep_weights(g, w, wsW, s);
+    void* wsB = (void*)(gbuf[1] + nca_align_up(n, 64));
+    rc = bf16 ? dynca_bf16_prep_bwd_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s);
     if (rc) return rc;
     NCA_CUDA_OK(cudaMemsetAsync(wsG, 0, dynca_f32_grad_floats(g) * sizeof(float), s));
     int ti = n_taps - 1;   // taps are consumed from the last step backwards
@@ -168,7 +170,8 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         NCA_CUDA_OK(cudaMemsetAsync(gout, 0, nb, s));
         const float* tap = nullptr;   // gradient injected at states[t+1]
         if (ti >= 0 && tap_steps[ti] == t + 1) tap = g_taps[ti--];
-        rc = dynca_f32_backward_step(g, wsW, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s);
+        rc = bf16 ? dynca_bf16_backward_step(g, wsB, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s)
+                  : dynca_f32_backward_step(g, wsW, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s);
         if (rc) return rc;
         gnext = gout;
     }
