@@ -209,6 +209,69 @@ def dynca_rollout_aten(x, w1, b1, w2, b2, masks, scales=(0,), mode="circular", c
 
 
 # --------------------------------------------------------------------------------------
+# BF16-operand emulation of the DyNCA step and its BPTT (checker for the tcgen05 path).
+# The tensor-core kernels round the GEMM operands to bfloat16 (round-to-nearest-even) and accumulate in
+# fp32; everything else (perception, bias b2, fire mask, residual, transposed perception) stays fp32.
+# This restatement rounds at exactly those points so the CUDA path can be checked to accumulation-order
+# accuracy instead of to bf16 accuracy.  Rounding points (csrc/dynca_bf16.cu):
+#   forward : z -> bf16 (cond inputs and b1 as bf16 hi + lo pairs, i.e. ~fp32), W1 -> bf16, h = relu(a) -> bf16,
+#             W2 -> bf16
+#   backward: g_y = mask * g_next -> bf16, g_a = g_h * [a > 0] -> bf16; gb2 sums the unrounded g_y
+# --------------------------------------------------------------------------------------
+def bf16r(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _hilo(t):
+    hi = bf16r(t)
+    return hi + bf16r(t - hi)
+
+
+def dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, mode, cond, g_final, taps=None):
+    """T steps forward with bf16-rounded GEMM operands, then manual BPTT with the kernel's rounding points.
+    taps: {step t in 1..T: dL/d(2 * states[t][:, :3])}.  Returns (final, dict of gradients)."""
+    taps = taps or {}
+    T = masks.shape[0]
+    C = x0.shape[1]
+    w1q = bf16r(w1)                             # cond columns: the bf16 weight multiplies the hi and the lo input slot
+    w2q, b1q = bf16r(w2), _hilo(b1)
+    xs, saved = [x0], []
+    x = x0
+    for t in range(T):
+        xr = x.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            zp = perceive_multiscale(xr, scales, mode, None)
+        zq = bf16r(zp.detach())
+        if cond is not None:
+            zq = torch.cat([zq, _hilo(cond)], dim=1)
+        a = torch.einsum("jk,bkhw->bjhw", w1q, zq) + b1q[None, :, None, None]
+        hq = bf16r(torch.relu(a))
+        y = torch.einsum("cj,bjhw->bchw", w2q, hq) + b2[None, :, None, None]
+        x = x.detach() + y * masks[t]
+        saved.append((xr, zp, zq, a, hq))
+        xs.append(x)
+    g = g_final.clone() if g_final is not None else torch.zeros_like(x0)
+    gw1 = torch.zeros_like(w1); gb1 = torch.zeros_like(b1); gw2 = torch.zeros_like(w2); gb2 = torch.zeros_like(b2)
+    for t in range(T - 1, -1, -1):
+        if (t + 1) in taps:
+            g = g.clone()
+            g[:, :3] += 2.0 * taps[t + 1]
+        xr, zp, zq, a, hq = saved[t]
+        gy32 = masks[t] * g
+        gy = bf16r(gy32)
+        gb2 += gy32.sum(dim=(0, 2, 3))
+        gw2 += torch.einsum("bchw,bjhw->cj", gy, hq)
+        gh = torch.einsum("bchw,cj->bjhw", gy, w2q)
+        ga = bf16r(gh * (a > 0).to(gh.dtype))
+        gw1 += torch.einsum("bjhw,bkhw->jk", ga, zq)
+        gb1 += ga.sum(dim=(0, 2, 3))
+        gz = torch.einsum("bjhw,jk->bkhw", ga, w1q[:, :4 * C])
+        (gx,) = torch.autograd.grad(zp, xr, gz)
+        g = g + gx
+    return xs[-1], dict(x0=g, w1=gw1, b1=gb1, w2=gw2, b2=gb2), xs
+
+
+# --------------------------------------------------------------------------------------
 # EncoderConditioning/nca.py
 # --------------------------------------------------------------------------------------
 def enc_alive(x, living_dim: int, thr: float = 0.1):

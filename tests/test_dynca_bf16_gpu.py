@@ -78,21 +78,25 @@ def test_bf16_full_size_properties():
     assert rel_err((a - x0).cpu(), (f - x0).cpu()) < ROLLOUT_TOL
 
 
-GRAD_TOL = 2e-2   # bf16 operands in every GEMM of the BPTT step (fp32 accumulation): gradients within 2e-2 relative
+EMU_STATE_TOL, EMU_GRAD_TOL = 2e-4, 5e-3   # vs the bf16-emulating oracle: only accumulation order (and the rare
+#                                            relu flip of a pre-activation within 1e-6 of zero) differ
+FP32_GRAD_RMS_TOL = 8e-2                    # vs the fp32 path: bf16 recompute flips near-zero relu units, so only a
+#                                            loose relative-L2 bound is meaningful
 
 
-def _grads(model, x0, T, masks, taps, coefs, **kwargs):
+def _cuda_grads(model, x0, T, masks, taps, coefs, **kwargs):
     x = x0.clone().requires_grad_(True)
     state, _, mids = model.forward_nsteps(x, T, return_middle_feature=True, masks=masks, **kwargs)
     loss = (state * coefs[0]).sum()
     for i, tp in enumerate(taps):
         loss = loss + (mids[tp - 1] * coefs[1 + i]).sum()
     gs = torch.autograd.grad(loss, [x, model.w1.weight, model.w1.bias, model.w2.weight, model.w2.bias])
-    return [g.detach().cpu() for g in gs]
+    return state.detach().cpu(), [g.detach().cpu() for g in gs]
 
 
 @pytest.mark.parametrize("name", DYNCA_CASES)
-def test_golden_case_bf16_gradients(name):
+def test_golden_case_bf16_vs_emulated_oracle(name):
+    """forward + BPTT of the tcgen05 path against the oracle that rounds the GEMM operands to bf16 at the same points"""
     t, m = load_case(name)
     mb, mf = build_model(m, t, precision="bf16"), build_model(m, t, precision="fp32")
     x0, masks = t["x0"].to(DEV), t["masks"].to(DEV)
@@ -100,19 +104,25 @@ def test_golden_case_bf16_gradients(name):
     T = min(m["T"], 6)
     taps = [tp for tp in m["taps"] if tp <= T]
     coefs = [t["coef_final"].to(DEV)] + [t[f"coef_tap{tp}"].to(DEV) for tp in taps]
-    gb = _grads(mb, x0, T, masks[:T], taps, coefs, **kwargs)
-    gf = _grads(mf, x0, T, masks[:T], taps, coefs, **kwargs)
+    fb, gb = _cuda_grads(mb, x0, T, masks[:T], taps, coefs, **kwargs)
+    fe, ge, _ = O.dynca_bf16emu_rollout_grads(t["x0"], t["w1"], t["b1"], t["w2"], t["b2"], t["masks"][:T], m["scales"], m["pad"],
+                                              cond_for(t, m), t["coef_final"], {tp: t[f"coef_tap{tp}"] for tp in taps})
+    assert rel_err(fb, fe) < EMU_STATE_TOL
+    shapes = dict(x0=x0.shape, w1=(m["fc"], -1), b1=(-1,), w2=(m["C"], m["fc"]), b2=(-1,))
+    for a, n in zip(gb, ("x0", "w1", "b1", "w2", "b2")):
+        assert rel_err(a.reshape(shapes[n]), ge[n]) < EMU_GRAD_TOL, (n, rel_err(a.reshape(shapes[n]), ge[n]))
+    # and loosely against the fp32 path
+    _, gf = _cuda_grads(mf, x0, T, masks[:T], taps, coefs, **kwargs)
     for a, b, n in zip(gb, gf, ("x0", "w1", "b1", "w2", "b2")):
-        assert rel_err(a, b) < GRAD_TOL, (n, rel_err(a, b))
+        assert float((a - b).norm() / b.norm()) < FP32_GRAD_RMS_TOL, n
 
 
-def test_bf16_backward_full_size_linearity():
+def test_bf16_backward_full_size_properties():
     torch.manual_seed(1)
     B, C, fc, H, W, T = 2, 16, 128, 256, 256, 3
-    model = nca_b200.DyNCA_EC(C, 3, fc_dim=fc, padding_mode="replicate", pos_emb="CPE", perception_scales=[0, 1],
-                              device=torch.device(DEV), precision="bf16")
-    ref = nca_b200.DyNCA_EC(C, 3, fc_dim=fc, padding_mode="replicate", pos_emb="CPE", perception_scales=[0, 1],
-                            device=torch.device(DEV), precision="fp32")
+    kw = dict(fc_dim=fc, padding_mode="replicate", pos_emb="CPE", perception_scales=[0, 1], device=torch.device(DEV))
+    model = nca_b200.DyNCA_EC(C, 3, precision="bf16", **kw)
+    ref = nca_b200.DyNCA_EC(C, 3, precision="fp32", **kw)
     ref.load_state_dict(model.state_dict())
     x0 = (torch.rand(B, C, H, W, device=DEV) - 0.5).requires_grad_(True)
     g1 = torch.randn(B, C, H, W, device=DEV)
@@ -123,5 +133,5 @@ def test_bf16_backward_full_size_linearity():
 
     a, z, f = grads(model, g1), grads(model, torch.zeros_like(g1)), grads(ref, g1)
     for i in range(5):
-        assert float(z[i].abs().max()) == 0.0
-        assert rel_err(a[i].cpu(), f[i].cpu()) < GRAD_TOL, (i, rel_err(a[i].cpu(), f[i].cpu()))
+        assert float(z[i].abs().max()) == 0.0                       # zero in -> exactly zero out
+        assert float((a[i] - f[i]).norm() / f[i].norm()) < FP32_GRAD_RMS_TOL, i

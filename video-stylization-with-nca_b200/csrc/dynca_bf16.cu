@@ -95,6 +95,40 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+
+// the cond chunk of A1 for one cell: [cond_0..cond_{cc-1} (bf16 hi), 1, 1, cond_0..cond_{cc-1} (lo residuals), 0..];
+// the lo slots exist when 2*cc + 2 <= 8 and make the cond inputs ~fp32-accurate (the matching W1 columns are
+// simply repeated); the two constant-1 slots carry b1 as bf16 hi + lo
+__device__ __forceinline__ bool dynca_cond_split(int cc) { return 2 * cc + 2 <= 8; }
+__device__ __forceinline__ uint4 dynca_cond_chunk(const DyncaGeom& g, const float* __restrict__ cond, int b, int gy, int gx, bool inimg) {
+    float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (inimg) {
+        const bool split = dynca_cond_split(g.cc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int src = i < g.cc ? i : ((split && i >= g.cc + 2 && i < 2 * g.cc + 2) ? i - g.cc - 2 : -1);
+            if (src >= 0) {
+                float raw;
+                if (g.cond_kind == NCA_COND_CPE) raw = (src == 0) ? dynca_cpe(gy, g.H, g.cpe_oh) : dynca_cpe(gx, g.W, g.cpe_ow);
+                else raw = __ldg(cond + ((size_t)(b * g.cc + src) * g.H + gy) * g.W + gx);
+                const float hi = __bfloat162float(__float2bfloat16_rn(raw));
+                cv[i] = i < g.cc ? hi : raw - hi;
+            } else if (i == g.cc || i == g.cc + 1) cv[i] = 1.0f;
+        }
+    }
+    uint4 v;
+    v.x = pack_bf16(cv[0], cv[1]); v.y = pack_bf16(cv[2], cv[3]); v.z = pack_bf16(cv[4], cv[5]); v.w = pack_bf16(cv[6], cv[7]);
+    return v;
+}
+// reference W1 column (or -1 = none, -2 = b1 hi, -3 = b1 lo) feeding slot s of the cond chunk
+__host__ __device__ __forceinline__ int dynca_cond_slot_src(int cc, int s) {
+    if (s < cc) return s;
+    if (s == cc) return -2;
+    if (s == cc + 1) return -3;
+    if (2 * cc + 2 <= 8 && s < 2 * cc + 2) return s - cc - 2;
+    return -1;
+}
+
 // ---- geometry of the bf16 operands ---------------------------------------------------------------
 struct Bf16Geom {
     int npairs;      // ceil(C/2) perception chunks
@@ -133,9 +167,10 @@ __global__ void dynca_bf16_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __
                 const int c = 2 * kc + (s >> 2), f = s & 3;
                 if (c < g.C) v = w1[j * g.P + f * g.C + c];
             } else if (kc == bg.npairs) {
-                if (s < g.cc) v = w1[j * g.P + 4 * g.C + s];
-                else if (s == g.cc) v = __bfloat162float(__float2bfloat16_rn(b1[j]));
-                else if (s == g.cc + 1) v = b1[j] - __bfloat162float(__float2bfloat16_rn(b1[j]));
+                const int src = dynca_cond_slot_src(g.cc, s);
+                if (src >= 0) v = w1[j * g.P + 4 * g.C + src];
+                else if (src == -2) v = __bfloat162float(__float2bfloat16_rn(b1[j]));
+                else if (src == -3) v = b1[j] - __bfloat162float(__float2bfloat16_rn(b1[j]));
             }
             const size_t off = (size_t)kc * (g.fc / 8) * 64 + (size_t)(j >> 3) * 64 + (j & 7) * 8 + s;   // in elements
             B1[off] = __float2bfloat16_rn(v);
@@ -163,9 +198,10 @@ __global__ void dynca_bf16_prep_b1_kernel(DyncaGeom g, Bf16Geom bg, const float*
             const int c = 2 * kc + (s >> 2), f = s & 3;
             if (c < g.C) v = w1[j * g.P + f * g.C + c];
         } else if (kc == bg.npairs) {
-            if (s < g.cc) v = w1[j * g.P + 4 * g.C + s];
-            else if (s == g.cc) v = __bfloat162float(__float2bfloat16_rn(b1[j]));
-            else if (s == g.cc + 1) v = b1[j] - __bfloat162float(__float2bfloat16_rn(b1[j]));
+            const int src = dynca_cond_slot_src(g.cc, s);
+            if (src >= 0) v = w1[j * g.P + 4 * g.C + src];
+            else if (src == -2) v = __bfloat162float(__float2bfloat16_rn(b1[j]));
+            else if (src == -3) v = b1[j] - __bfloat162float(__float2bfloat16_rn(b1[j]));
         }
         B1[(size_t)kc * (g.fc / 8) * 64 + (size_t)(j >> 3) * 64 + (j & 7) * 8 + s] = __float2bfloat16_rn(v);
     }
@@ -253,19 +289,7 @@ __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaB
                 v.z = pack_bf16(f1[0], f1[1]); v.w = pack_bf16(f1[2], f1[3]);
                 *reinterpret_cast<uint4*>(sA1 + (uint32_t)cp * 2048u + row_off) = v;
             }
-            float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (inimg) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i < g.cc) {
-                        if (g.cond_kind == NCA_COND_CPE) cv[i] = (i == 0) ? dynca_cpe(gy, H, g.cpe_oh) : dynca_cpe(gx, W, g.cpe_ow);
-                        else cv[i] = __ldg(a.cond + ((size_t)(t.b * g.cc + i) * H + gy) * W + gx);
-                    } else if (i == g.cc || i == g.cc + 1) cv[i] = 1.0f;
-                }
-            }
-            uint4 v;
-            v.x = pack_bf16(cv[0], cv[1]); v.y = pack_bf16(cv[2], cv[3]); v.z = pack_bf16(cv[4], cv[5]); v.w = pack_bf16(cv[6], cv[7]);
-            *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = v;
+            *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = dynca_cond_chunk(g, a.cond, t.b, gy, gx, inimg);
         }
         fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         tc_fence_before();
@@ -483,21 +507,8 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
                 v.z = pack_bf16(f1[0], f1[1]); v.w = pack_bf16(f1[2], f1[3]);
                 *reinterpret_cast<uint4*>(sA1 + (uint32_t)cp * 2048u + row_off) = v;
             }
-            if (half == 0) {
-                float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (inimg) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (i < g.cc) {
-                            if (g.cond_kind == NCA_COND_CPE) cv[i] = (i == 0) ? dynca_cpe(gy, H, g.cpe_oh) : dynca_cpe(gx, W, g.cpe_ow);
-                            else cv[i] = __ldg(a.cond + ((size_t)(t.b * g.cc + i) * H + gy) * W + gx);
-                        } else if (i == g.cc || i == g.cc + 1) cv[i] = 1.0f;
-                    }
-                }
-                uint4 v;
-                v.x = pack_bf16(cv[0], cv[1]); v.y = pack_bf16(cv[2], cv[3]); v.z = pack_bf16(cv[4], cv[5]); v.w = pack_bf16(cv[6], cv[7]);
-                *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = v;
-            }
+            if (half == 0)
+                *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = dynca_cond_chunk(g, a.cond, t.b, gy, gx, inimg);
             // chunks past the cond chunk were overwritten by the scatter scratch of the previous tile: re-zero
             for (uint32_t i = tid + (uint32_t)(bg.npairs + 1) * 128; i < bg.a1_bytes / 16; i += BB_THREADS)
                 reinterpret_cast<uint4*>(sA1)[i] = make_uint4(0, 0, 0, 0);
@@ -632,7 +643,7 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
                     const int kc = kp >> 3, s = kp & 7;
                     int k = -1;
                     if (kc < bg.npairs) { const int c = 2 * kc + (s >> 2); if (c < C) k = (s & 3) * C + c; }
-                    else if (kc == bg.npairs) { if (s < g.cc) k = 4 * C + s; else if (s == g.cc) k = g.P; }
+                    else if (kc == bg.npairs) { const int src = dynca_cond_slot_src(g.cc, s); if (src >= 0) k = 4 * C + src; else if (src == -2) k = g.P; }
                     if (k >= 0) atomicAdd(a.gW1p + k * g.FCpad + j, __uint_as_float(v[i]));
                 }
             }
