@@ -78,10 +78,12 @@ def test_bf16_full_size_properties():
     assert rel_err((a - x0).cpu(), (f - x0).cpu()) < ROLLOUT_TOL
 
 
-EMU_STATE_TOL, EMU_GRAD_TOL = 2e-4, 5e-3   # vs the bf16-emulating oracle: only accumulation order (and the rare
-#                                            relu flip of a pre-activation within 1e-6 of zero) differ
-FP32_GRAD_RMS_TOL = 8e-2                    # vs the fp32 path: bf16 recompute flips near-zero relu units, so only a
-#                                            loose relative-L2 bound is meaningful
+# Against the bf16-emulating oracle the tcgen05 path agrees to fp32 accumulation order (1e-7) unless some fp32
+# intermediate lands within one fp32 ulp of a bf16 rounding boundary or of the relu threshold and rounds the other way
+# (GPU FMA contraction / tanhf vs the CPU); one such flip moves the state by ~1e-3 and a small-image gradient by
+# ~1e-2.  So: loose per-case bounds, and a census that most single-step cases are exact.
+EMU_STATE_TOL, EMU_GRAD_MAX_TOL, EMU_GRAD_RMS_TOL, EXACT_TOL = 3e-3, 3e-2, 1e-2, 1e-5
+FP32_GRAD_RMS_TOL = 8e-2   # vs the fp32 path: bf16 recompute flips near-zero relu units, only a loose L2 bound is meaningful
 
 
 def _cuda_grads(model, x0, T, masks, taps, coefs, **kwargs):
@@ -94,27 +96,42 @@ def _cuda_grads(model, x0, T, masks, taps, coefs, **kwargs):
     return state.detach().cpu(), [g.detach().cpu() for g in gs]
 
 
-@pytest.mark.parametrize("name", DYNCA_CASES)
-def test_golden_case_bf16_vs_emulated_oracle(name):
-    """forward + BPTT of the tcgen05 path against the oracle that rounds the GEMM operands to bf16 at the same points"""
+def _emu_errors(name, T):
     t, m = load_case(name)
-    mb, mf = build_model(m, t, precision="bf16"), build_model(m, t, precision="fp32")
+    mb = build_model(m, t, precision="bf16")
     x0, masks = t["x0"].to(DEV), t["masks"].to(DEV)
     kwargs = dict(cond_img=t["cond_img"].to(DEV) if "cond_img" in t else None) if m["flavour"] == "cd" else {}
-    T = min(m["T"], 6)
+    T = min(m["T"], T)
     taps = [tp for tp in m["taps"] if tp <= T]
     coefs = [t["coef_final"].to(DEV)] + [t[f"coef_tap{tp}"].to(DEV) for tp in taps]
     fb, gb = _cuda_grads(mb, x0, T, masks[:T], taps, coefs, **kwargs)
     fe, ge, _ = O.dynca_bf16emu_rollout_grads(t["x0"], t["w1"], t["b1"], t["w2"], t["b2"], t["masks"][:T], m["scales"], m["pad"],
                                               cond_for(t, m), t["coef_final"], {tp: t[f"coef_tap{tp}"] for tp in taps})
-    assert rel_err(fb, fe) < EMU_STATE_TOL
     shapes = dict(x0=x0.shape, w1=(m["fc"], -1), b1=(-1,), w2=(m["C"], m["fc"]), b2=(-1,))
-    for a, n in zip(gb, ("x0", "w1", "b1", "w2", "b2")):
-        assert rel_err(a.reshape(shapes[n]), ge[n]) < EMU_GRAD_TOL, (n, rel_err(a.reshape(shapes[n]), ge[n]))
+    gmax = {n: rel_err(a.reshape(shapes[n]), ge[n]) for a, n in zip(gb, shapes)}
+    grms = {n: float((a.reshape(shapes[n]) - ge[n]).norm() / (ge[n].norm() + 1e-30)) for a, n in zip(gb, shapes)}
+    return rel_err(fb, fe), gmax, grms, (gb, t, m, x0, masks, taps, coefs, kwargs, T)
+
+
+@pytest.mark.parametrize("name", DYNCA_CASES)
+def test_golden_case_bf16_vs_emulated_oracle(name):
+    """forward + BPTT of the tcgen05 path against the oracle that rounds the GEMM operands to bf16 at the same points"""
+    es, gmax, grms, (gb, t, m, x0, masks, taps, coefs, kwargs, T) = _emu_errors(name, 6)
+    assert es < EMU_STATE_TOL
+    assert max(gmax.values()) < EMU_GRAD_MAX_TOL, gmax
+    assert max(grms.values()) < EMU_GRAD_RMS_TOL, grms
     # and loosely against the fp32 path
-    _, gf = _cuda_grads(mf, x0, T, masks[:T], taps, coefs, **kwargs)
+    _, gf = _cuda_grads(build_model(m, t, precision="fp32"), x0, T, masks[:T], taps, coefs, **kwargs)
     for a, b, n in zip(gb, gf, ("x0", "w1", "b1", "w2", "b2")):
         assert float((a - b).norm() / b.norm()) < FP32_GRAD_RMS_TOL, n
+
+
+def test_bf16_single_step_mostly_exact_vs_emulated_oracle():
+    exact = 0
+    for name in DYNCA_CASES:
+        es, gmax, _, _ = _emu_errors(name, 1)
+        exact += int(es < EXACT_TOL and max(gmax.values()) < EXACT_TOL)
+    assert exact >= (3 * len(DYNCA_CASES)) // 4, f"only {exact}/{len(DYNCA_CASES)} single-step cases agree to {EXACT_TOL}"
 
 
 def test_bf16_backward_full_size_properties():
