@@ -207,6 +207,30 @@ __device__ __forceinline__ int dynca_krow(int C, int c, int f) {
 // is accumulated with red.add into g_out (zeroed by the caller): contributions to the tile's ring land in the
 // neighbouring tiles' cells (or wrap / fold back according to the padding mode).  sG: 4C*DT_PCH*DT_PCW floats of
 // scratch (NS == 2).  Caller must __syncthreads() before (sZ complete) and after (smem reuse).
+//
+// Work items are (output position, channel parity): the validity mask and source offset of the 9 taps depend on the
+// position only, so they are computed once and the channel loop is branch-free (3 LDS + 3 FFMA per non-zero tap).
+template <bool KPERM>
+__device__ __forceinline__ float dynca_stencil_t(const float* __restrict__ S, int C, int c, int plane_stride, bool kperm_rows,
+                                                 const int off[9], const float mk[9]) {
+    // rows of the three filter planes of channel c
+    const float* zx = S + (kperm_rows ? dynca_krow<KPERM>(C, c, 1) : (C + c)) * plane_stride;
+    const float* zy = S + (kperm_rows ? dynca_krow<KPERM>(C, c, 2) : (2 * C + c)) * plane_stride;
+    const float* zl = S + (kperm_rows ? dynca_krow<KPERM>(C, c, 3) : (3 * C + c)) * plane_stride;
+    float v = 0.0f;
+#pragma unroll
+    for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) {
+            const int k = aa * 3 + bb;
+            float tv = dynca_tap_lap(aa, bb) * zl[off[k]];
+            if (bb != 1) tv = fmaf(dynca_tap_sx(aa, bb), zx[off[k]], tv);
+            if (aa != 1) tv = fmaf(dynca_tap_sy(aa, bb), zy[off[k]], tv);
+            v = fmaf(mk[k], tv, v);
+        }
+    return v;
+}
+
 template <int NS, int NT, bool KPERM>
 __device__ __forceinline__ void dynca_scatter_tile(const DyncaGeom& g, const DyncaTile& t, const float* __restrict__ sZ,
                                                    float* __restrict__ sU, float* __restrict__ g_out,
@@ -217,87 +241,103 @@ __device__ __forceinline__ void dynca_scatter_tile(const DyncaGeom& g, const Dyn
     const size_t plane = (size_t)H * W;
     float* gob = g_out + (size_t)t.b * C * plane;
     // ---- scale 0: transposed 3x3 stencils over the tile + ring, residual pass-through, red.add ----
-    for (int i = tid; i < C * DT_XR * DT_XS; i += NT) {
-        const int rx = i % DT_XS, ry = (i / DT_XS) % DT_XR, c = i / (DT_XS * DT_XR);
+    for (int item = tid; item < 2 * DT_XR * DT_XS; item += NT) {
+        const int hh = item >= DT_XR * DT_XS ? 1 : 0;
+        const int pos = item - hh * DT_XR * DT_XS;
+        const int rx = pos % DT_XS, ry = pos / DT_XS;
         const int yy = t.y0 - 1 + ry, xx = t.x0 - 1 + rx;     // padded coordinate of this position
         if (yy > H || xx > W) continue;
-        float v = 0.0f;
+        const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
+        if (iy < 0 || ix < 0) continue;
+        int off[9];
+        float mk[9];
 #pragma unroll
-        for (int aa = 0; aa < 3; ++aa) {
-            const int py = ry - aa;
-            if (py < 0 || py >= DT_TH) continue;
+        for (int aa = 0; aa < 3; ++aa)
 #pragma unroll
             for (int bb = 0; bb < 3; ++bb) {
-                const int px = rx - bb;
-                if (px < 0 || px >= DT_TW) continue;
-                const int m = py * DT_TW + px;
-                v = fmaf(dynca_tap_sx(aa, bb), sZ[dynca_krow<KPERM>(C, c, 1) * DT_TMS + m], v);
-                v = fmaf(dynca_tap_sy(aa, bb), sZ[dynca_krow<KPERM>(C, c, 2) * DT_TMS + m], v);
-                v = fmaf(dynca_tap_lap(aa, bb), sZ[dynca_krow<KPERM>(C, c, 3) * DT_TMS + m], v);
+                const int py = ry - aa, px = rx - bb;
+                const bool ok = py >= 0 && py < DT_TH && px >= 0 && px < DT_TW;
+                off[aa * 3 + bb] = ok ? py * DT_TW + px : 0;
+                mk[aa * 3 + bb] = ok ? 1.0f : 0.0f;
             }
-        }
         // in-tile AND in-image cells also get the identity tap and the residual pass-through; in-tile cells
         // beyond the image edge are ordinary pad positions of the last image row / column
         const bool interior = ry >= 1 && ry <= DT_TH && rx >= 1 && rx <= DT_TW && yy < H && xx < W;
-        if (interior) {
-            v += sZ[dynca_krow<KPERM>(C, c, 0) * DT_TMS + (ry - 1) * DT_TW + (rx - 1)];
-            v += dynca_gnext(g_next, g_tap, tap_c, tap_scale, C, t.b, c, (size_t)yy * W + xx, plane);
+        const size_t pix = (size_t)iy * W + ix;
+        for (int c = hh; c < C; c += 2) {
+            float v = dynca_stencil_t<KPERM>(sZ, C, c, DT_TMS, true, off, mk);
+            if (interior) {
+                v += sZ[dynca_krow<KPERM>(C, c, 0) * DT_TMS + (ry - 1) * DT_TW + (rx - 1)];
+                v += dynca_gnext(g_next, g_tap, tap_c, tap_scale, C, t.b, c, pix, plane);
+            }
+            atomicAdd(gob + c * plane + pix, v);
         }
-        const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
-        if (iy < 0 || ix < 0) continue;
-        atomicAdd(gob + c * plane + (size_t)iy * W + ix, v);
     }
     if (NS == 2) {
         // ---- scale 1: Up^T (bilinear x2) -> coarse g_percept, stencil^T on the coarse grid, Down^T ----
         const int Hc = H >> 1, Wc = W >> 1;
         const int cy0 = (t.y0 >> 1) - 1, cx0 = (t.x0 >> 1) - 1;
-        const int ps = DT_PCH * DT_PCW;
-        float* sG = sU;   // [4C][PCH*PCW]
-        for (int i = tid; i < 4 * C * ps; i += NT) {
-            const int pq = i % DT_PCW, pr = (i / DT_PCW) % DT_PCH, k = i / ps;
-            const int krow = dynca_krow<KPERM>(C, k % C, k / C);
+        constexpr int ps = DT_PCH * DT_PCW;
+        constexpr int NG = NT / ps;          // plane groups working in parallel
+        float* sG = sU;                      // [4C][PCH*PCW], reference plane order f*C + c
+        if (tid < NG * ps) {
+            const int cell = tid % ps, grp = tid / ps;
+            const int pr = cell / DT_PCW, pq = cell % DT_PCW;
             const int qy = cy0 + pr, qx = cx0 + pq;
-            float v = 0.0f;
-            if (qy >= 0 && qy < Hc && qx >= 0 && qx < Wc) {
-                for (int fy = 2 * qy - 1; fy <= 2 * qy + 2; ++fy) {
-                    const int py = fy - t.y0;
-                    if (py < 0 || py >= DT_TH || fy >= H) continue;
-                    const float wy = dynca_up_weight(fy, qy, Hc);
-                    for (int fx = 2 * qx - 1; fx <= 2 * qx + 2; ++fx) {
-                        const int px = fx - t.x0;
-                        if (px < 0 || px >= DT_TW || fx >= W) continue;
-                        v = fmaf(wy * dynca_up_weight(fx, qx, Wc), sZ[krow * DT_TMS + py * DT_TW + px], v);
-                    }
-                }
+            const bool cell_ok = qy >= 0 && qy < Hc && qx >= 0 && qx < Wc;
+            float wy[4], wx[4];
+            int oy[4], ox[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int fy = 2 * qy - 1 + i, py = fy - t.y0;
+                const bool oky = cell_ok && py >= 0 && py < DT_TH && fy < H;
+                wy[i] = oky ? dynca_up_weight(fy, qy, Hc) : 0.0f;
+                oy[i] = oky ? py * DT_TW : 0;
+                const int fx = 2 * qx - 1 + i, px = fx - t.x0;
+                const bool okx = cell_ok && px >= 0 && px < DT_TW && fx < W;
+                wx[i] = okx ? dynca_up_weight(fx, qx, Wc) : 0.0f;
+                ox[i] = okx ? px : 0;
             }
-            sG[i] = v;
+            for (int k = grp; k < 4 * C; k += NG) {
+                const float* zr = sZ + dynca_krow<KPERM>(C, k % C, k / C) * DT_TMS;
+                float v = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* r = zr + oy[i];
+                    v = fmaf(wy[i], fmaf(wx[0], r[ox[0]], fmaf(wx[1], r[ox[1]], fmaf(wx[2], r[ox[2]], wx[3] * r[ox[3]]))), v);
+                }
+                sG[k * ps + cell] = v;
+            }
         }
         __syncthreads();
-        for (int i = tid; i < C * DT_CXH * DT_CXW; i += NT) {
-            const int rx = i % DT_CXW, ry = (i / DT_CXW) % DT_CXH, c = i / (DT_CXW * DT_CXH);
+        for (int item = tid; item < 2 * DT_CXH * DT_CXW; item += NT) {
+            const int hh = item >= DT_CXH * DT_CXW ? 1 : 0;
+            const int pos = item - hh * DT_CXH * DT_CXW;
+            const int rx = pos % DT_CXW, ry = pos / DT_CXW;
             const int yy = cy0 - 1 + ry, xx = cx0 - 1 + rx;   // coarse padded coordinate
             if (yy < -1 || xx < -1 || yy > Hc || xx > Wc) continue;
-            float v = 0.0f;
+            const int qy = nca_padmap(yy, Hc, g.pad), qx = nca_padmap(xx, Wc, g.pad);
+            if (qy < 0 || qx < 0) continue;
+            int off[9];
+            float mk[9];
 #pragma unroll
-            for (int aa = 0; aa < 3; ++aa) {
-                const int pr = ry - aa;
-                if (pr < 0 || pr >= DT_PCH) continue;
+            for (int aa = 0; aa < 3; ++aa)
 #pragma unroll
                 for (int bb = 0; bb < 3; ++bb) {
-                    const int pq = rx - bb;
-                    if (pq < 0 || pq >= DT_PCW) continue;
-                    const int o = pr * DT_PCW + pq;
-                    v = fmaf(dynca_tap_sx(aa, bb), sG[(C + c) * ps + o], v);
-                    v = fmaf(dynca_tap_sy(aa, bb), sG[(2 * C + c) * ps + o], v);
-                    v = fmaf(dynca_tap_lap(aa, bb), sG[(3 * C + c) * ps + o], v);
+                    const int pr = ry - aa, pq = rx - bb;
+                    const bool ok = pr >= 0 && pr < DT_PCH && pq >= 0 && pq < DT_PCW;
+                    off[aa * 3 + bb] = ok ? pr * DT_PCW + pq : 0;
+                    mk[aa * 3 + bb] = ok ? 1.0f : 0.0f;
                 }
+            const bool ident = ry >= 1 && ry <= DT_PCH && rx >= 1 && rx <= DT_PCW;
+            float* p0 = gob + (size_t)(2 * qy) * W + 2 * qx;
+            for (int c = hh; c < C; c += 2) {
+                float v = dynca_stencil_t<KPERM>(sG, C, c, ps, false, off, mk);
+                if (ident) v += sG[c * ps + (ry - 1) * DT_PCW + (rx - 1)];
+                v *= 0.25f;
+                float* p = p0 + c * plane;
+                atomicAdd(p, v); atomicAdd(p + 1, v); atomicAdd(p + W, v); atomicAdd(p + W + 1, v);
             }
-            if (ry >= 1 && ry <= DT_PCH && rx >= 1 && rx <= DT_PCW) v += sG[c * ps + (ry - 1) * DT_PCW + (rx - 1)];
-            const int qy = nca_padmap(yy, Hc, g.pad), qx = nca_padmap(xx, Wc, g.pad);
-            if (qy < 0 || qx < 0 || v == 0.0f) continue;
-            float* p = gob + c * plane + (size_t)(2 * qy) * W + 2 * qx;
-            v *= 0.25f;
-            atomicAdd(p, v); atomicAdd(p + 1, v); atomicAdd(p + W, v); atomicAdd(p + W + 1, v);
         }
     }
 }
