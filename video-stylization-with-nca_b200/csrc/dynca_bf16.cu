@@ -225,10 +225,10 @@ static inline size_t dynca_bf16_smem_bytes(const DyncaGeom& g, const Bf16Geom& b
 
 template <int NS>
 __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaBf16Args a) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t* base = smem_raw;   // 1024-byte aligned by declaration; no integer round-trip, so accesses stay LDS/STS
     uint64_t* bar = reinterpret_cast<uint64_t*>(base);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 8);
     float* sB2 = reinterpret_cast<float*>(base + 64);          // 16 floats
@@ -434,10 +434,10 @@ static inline size_t dynca_bf16_bwd_smem_bytes(const DyncaGeom& g, const Bf16Geo
 
 template <int NS>
 __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const DyncaBf16BwdArgs a) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t* base = smem_raw;   // 1024-byte aligned by declaration; no integer round-trip, so accesses stay LDS/STS
     uint64_t* bar = reinterpret_cast<uint64_t*>(base);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 8);
     uint8_t* sA1 = base + 128;
