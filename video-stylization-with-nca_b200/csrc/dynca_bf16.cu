@@ -14,7 +14,7 @@
 // Operand smem layout (no swizzle): element (row, k) at  (k/8)*LBO + (row/8)*128 + (row%8)*16 + (k%8)*2  bytes,
 // i.e. 8x8 core matrices of 128 contiguous bytes, SBO = 128 (next 8 rows), LBO = rows*16 (next 8 k).
 #include <cuda_bf16.h>
-#include "dynca_tile.cuh"
+#include "dynca_stage2.cuh"
 #include "nca_internal.h"
 
 #define BT_THREADS 128
@@ -211,14 +211,14 @@ __global__ void dynca_bf16_prep_b1_kernel(DyncaGeom g, Bf16Geom bg, const float*
 struct DyncaBf16Args {
     DyncaGeom g;
     Bf16Geom bg;
-    const float* x_in; float* x_out; const float* cond;
+    const float* x_in; const float* xc; float* x_out; const float* cond;
     const __nv_bfloat16* B1; const __nv_bfloat16* B2; const float* b2p;
     FireMask fm;
     int tiles_x, tiles_y, n_tiles;
 };
 
 static inline size_t dynca_bf16_smem_bytes(const DyncaGeom& g, const Bf16Geom& bg) {
-    size_t stage = (size_t)dynca_stage_floats(g) * 4;
+    size_t stage = (size_t)dynca_stage2_floats(g) * 4;
     size_t u = stage > bg.a2_bytes ? stage : bg.a2_bytes;
     return 1024 /*alignment slack*/ + 128 /*barrier, tmem ptr, b2*/ + bg.a1_bytes + bg.b1_bytes + bg.b2_bytes + u;
 }
@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaB
         const DyncaTile t = dynca_tile_of(tile, a.tiles_x, a.tiles_y);
         const int gy = t.y0 + py, gx = t.x0 + px;
         const bool inimg = gy < H && gx < W;
-        dynca_stage_tile<NS, BT_THREADS>(g, a.x_in, t, sStage);
+        dynca_stage2_issue<NS, BT_THREADS>(g, a.x_in, a.xc, t, sStage);
+        dynca_stage2_finish<NS, BT_THREADS>(g, sStage);
         // ---- perception -> A1 (this thread's row) ----
         {
             DyncaUp u = {};
@@ -281,8 +282,8 @@ __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaB
             for (int cp = 0; cp < bg.npairs; ++cp) {
                 float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
                 if (inimg) {
-                    dynca_cell_percept<NS>(g, sStage, u, 2 * cp, py, px, f0);
-                    if (2 * cp + 1 < C) dynca_cell_percept<NS>(g, sStage, u, 2 * cp + 1, py, px, f1);
+                    dynca_cell_percept2<NS>(g, sStage, u, 2 * cp, py, px, f0);
+                    if (2 * cp + 1 < C) dynca_cell_percept2<NS>(g, sStage, u, 2 * cp + 1, py, px, f1);
                 }
                 uint4 v;
                 v.x = pack_bf16(f0[0], f0[1]); v.y = pack_bf16(f0[2], f0[3]);
@@ -419,7 +420,7 @@ __global__ void dynca_bf16_prep_bwd_kernel(DyncaGeom g, Bf16Geom bg, const float
 struct DyncaBf16BwdArgs {
     DyncaGeom g;
     Bf16Geom bg;
-    const float* x_in; const float* g_next; const float* g_tap; int tap_c; float tap_scale;
+    const float* x_in; const float* xc; const float* g_next; const float* g_tap; int tap_c; float tap_scale;
     float* g_out; const float* cond;
     const __nv_bfloat16* B1; const __nv_bfloat16* B1t; const __nv_bfloat16* B2d;
     float* gW1p; float* gW2p; float* gb2p;      // fp32 accumulators, padded fp32-path layout (red.add)
@@ -429,7 +430,7 @@ struct DyncaBf16BwdArgs {
 
 static inline size_t dynca_bf16_bwd_smem_bytes(const DyncaGeom& g, const Bf16Geom& bg) {
     return 1024 + 128 + bg.a1_bytes + 4096 /*Gy*/ + 2 * 32768 /*H, Ga*/ + 2 * bg.b1_bytes + (size_t)2 * (g.fc / 8) * 128 +
-           (size_t)dynca_stage_floats(g) * 4;
+           (size_t)dynca_stage2_floats(g) * 4;
 }
 
 template <int NS>
@@ -487,11 +488,13 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
     for (int i = 0; i < 8; ++i) b2acc[i] = 0.0f;
     bool first = true;
 
+    if ((int)blockIdx.x < a.n_tiles)
+        dynca_stage2_issue<NS, BB_THREADS>(g, a.x_in, a.xc, dynca_tile_of(blockIdx.x, a.tiles_x, a.tiles_y), sStage);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const DyncaTile t = dynca_tile_of(tile, a.tiles_x, a.tiles_y);
         const int gy = t.y0 + py, gx = t.x0 + px;
         const bool inimg = gy < H && gx < W;
-        dynca_stage_tile<NS, BB_THREADS>(g, a.x_in, t, sStage);
+        dynca_stage2_finish<NS, BB_THREADS>(g, sStage);
         // ---- recompute perception -> A1 ----
         {
             DyncaUp u = {};
@@ -499,8 +502,8 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
             for (int cp = half; cp < bg.npairs; cp += 2) {
                 float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
                 if (inimg) {
-                    dynca_cell_percept<NS>(g, sStage, u, 2 * cp, py, px, f0);
-                    if (2 * cp + 1 < C) dynca_cell_percept<NS>(g, sStage, u, 2 * cp + 1, py, px, f1);
+                    dynca_cell_percept2<NS>(g, sStage, u, 2 * cp, py, px, f0);
+                    if (2 * cp + 1 < C) dynca_cell_percept2<NS>(g, sStage, u, 2 * cp + 1, py, px, f1);
                 }
                 uint4 v;
                 v.x = pack_bf16(f0[0], f0[1]); v.y = pack_bf16(f0[2], f0[3]);
@@ -530,6 +533,9 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        // every thread is done reading the stage area: start copying the next tile of this CTA behind the MMAs
+        if (tile + (int)gridDim.x < a.n_tiles)
+            dynca_stage2_issue<NS, BB_THREADS>(g, a.x_in, a.xc, dynca_tile_of(tile + gridDim.x, a.tiles_x, a.tiles_y), sStage);
         // ---- S1: D1 = A1 . W1^T ; D3 = Gy . W2 ----
         if (tid == 0) {
             tc_fence_after();
@@ -689,12 +695,23 @@ int dynca_bf16_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* 
     return NCA_OK;
 }
 
-int dynca_bf16_forward_step(const DyncaGeom& g, const void* ws, const float* x_in, float* x_out, const float* cond,
+int dynca_bf16_coarsen(const DyncaGeom& g, const float* x, float* xc, cudaStream_t s) {
+    if (g.ns != 2) return NCA_OK;
+    const size_t n = (size_t)g.B * g.C * (g.H / 2) * (g.W / 2);
+    int grid = (int)((n + 255) / 256 < (size_t)bf16_num_sms() * 8 ? (n + 255) / 256 : (size_t)bf16_num_sms() * 8);
+    dynca_coarsen_kernel<<<grid, 256, 0, s>>>(g.B * g.C, g.H, g.W, x, xc);
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+int dynca_bf16_forward_step(const DyncaGeom& g, const void* ws, float* xc, const float* x_in, float* x_out, const float* cond,
                             const FireMask& fm, cudaStream_t s) {
     DyncaBf16Args a;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
-    a.g = g; a.x_in = x_in; a.x_out = x_out; a.cond = cond;
+    rc = dynca_bf16_coarsen(g, x_in, xc, s);
+    if (rc) return rc;
+    a.g = g; a.x_in = x_in; a.xc = xc; a.x_out = x_out; a.cond = cond;
     a.B1 = (const __nv_bfloat16*)ws;
     a.B2 = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes);
     a.b2p = (const float*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes);
@@ -747,13 +764,15 @@ int dynca_bf16_prep_bwd_weights(const DyncaGeom& g, const NcaDyncaWeights* w, vo
     return NCA_OK;
 }
 
-int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const float* x_in, const float* g_next,
+int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* xc, float* wsG, const float* x_in, const float* g_next,
                              const float* g_tap, int tap_c, float tap_scale, float* g_out, const float* cond,
                              const FireMask& fm, cudaStream_t s) {
     DyncaBf16BwdArgs a;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
-    a.g = g; a.x_in = x_in; a.g_next = g_next; a.g_tap = g_tap; a.tap_c = tap_c; a.tap_scale = tap_scale;
+    rc = dynca_bf16_coarsen(g, x_in, xc, s);
+    if (rc) return rc;
+    a.g = g; a.x_in = x_in; a.xc = xc; a.g_next = g_next; a.g_tap = g_tap; a.tap_c = tap_c; a.tap_scale = tap_scale;
     a.g_out = g_out; a.cond = cond;
     a.B1 = (const __nv_bfloat16*)ws;
     a.B1t = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes);
@@ -773,4 +792,8 @@ int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* wsG, con
     }
     NCA_LAUNCH_OK();
     return NCA_OK;
+}
+
+size_t dynca_bf16_coarse_floats(const DyncaGeom& g) {
+    return g.ns == 2 ? nca_align_up((size_t)g.B * g.C * (g.H / 2) * (g.W / 2), 64) : 0;
 }

@@ -63,7 +63,7 @@ size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward) {
     if (d->precision == NCA_PREC_BF16) {
         size_t b = backward ? dynca_bf16_bwd_weight_bytes(g) : dynca_bf16_weight_bytes(g);
         if (b == 0) return 0;
-        bytes += b;
+        bytes += b + dynca_bf16_coarse_floats(g) * sizeof(float);   // + coarse (2x2-mean) state of the current step
     }
     return bytes;
 }
@@ -111,6 +111,7 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
     float* wsW = (float*)workspace;
     void* wsB = (uint8_t*)workspace + dynca_f32_weight_floats(g) * sizeof(float);
     const bool bf16 = d->precision == NCA_PREC_BF16;
+    float* wsXc = bf16 ? (float*)((uint8_t*)wsB + dynca_bf16_weight_bytes(g)) : nullptr;
     rc = bf16 ? dynca_bf16_prep_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s);
     if (rc) return rc;
     const size_t n = (size_t)g.B * g.C * g.H * g.W;
@@ -119,7 +120,7 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
         fm.t = (uint32_t)(t0 + t);
         const float* xin = keep_history ? states + (size_t)t * n : states + (size_t)(t & 1) * n;
         float* xout = keep_history ? states + (size_t)(t + 1) * n : states + (size_t)((t + 1) & 1) * n;
-        rc = bf16 ? dynca_bf16_forward_step(g, wsB, xin, xout, cond, fm, s) : dynca_f32_forward_step(g, wsW, xin, xout, cond, fm, s);
+        rc = bf16 ? dynca_bf16_forward_step(g, wsB, wsXc, xin, xout, cond, fm, s) : dynca_f32_forward_step(g, wsW, xin, xout, cond, fm, s);
         if (rc) return rc;
     }
     return NCA_OK;
@@ -153,6 +154,7 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
     float* wsG = wsW + dynca_f32_weight_floats(g);
     float* gbuf[2] = {wsG + dynca_f32_grad_floats(g), wsG + dynca_f32_grad_floats(g) + nca_align_up(n, 64)};
     void* wsB = (void*)(gbuf[1] + nca_align_up(n, 64));
+    float* wsXc = (float*)((uint8_t*)wsB + dynca_bf16_bwd_weight_bytes(g));
     rc = bf16 ? dynca_bf16_prep_bwd_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s);
     if (rc) return rc;
     NCA_CUDA_OK(cudaMemsetAsync(wsG, 0, dynca_f32_grad_floats(g) * sizeof(float), s));
@@ -170,7 +172,7 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         NCA_CUDA_OK(cudaMemsetAsync(gout, 0, nb, s));
         const float* tap = nullptr;   // gradient injected at states[t+1]
         if (ti >= 0 && tap_steps[ti] == t + 1) tap = g_taps[ti--];
-        rc = bf16 ? dynca_bf16_backward_step(g, wsB, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s)
+        rc = bf16 ? dynca_bf16_backward_step(g, wsB, wsXc, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s)
                   : dynca_f32_backward_step(g, wsW, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s);
         if (rc) return rc;
         gnext = gout;

@@ -19,11 +19,12 @@ int nca_philox_mask_launch(int B, int H, int W, float rate, int enc, uint64_t se
 // dynca_bf16.cu (tcgen05 path)
 size_t dynca_bf16_weight_bytes(const DyncaGeom& g);
 int dynca_bf16_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s);
-int dynca_bf16_forward_step(const DyncaGeom& g, const void* ws, const float* x_in, float* x_out, const float* cond,
+int dynca_bf16_forward_step(const DyncaGeom& g, const void* ws, float* xc, const float* x_in, float* x_out, const float* cond,
                             const FireMask& fm, cudaStream_t s);
+size_t dynca_bf16_coarse_floats(const DyncaGeom& g);
 size_t dynca_bf16_bwd_weight_bytes(const DyncaGeom& g);
 bool dynca_bf16_bwd_supported(const DyncaGeom& g);
 int dynca_bf16_prep_bwd_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s);
-int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const float* x_in, const float* g_next,
+int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* xc, float* wsG, const float* x_in, const float* g_next,
                              const float* g_tap, int tap_c, float tap_scale, float* g_out, const float* cond,
                              const FireMask& fm, cudaStream_t s);
