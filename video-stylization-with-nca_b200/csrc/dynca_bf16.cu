@@ -15,6 +15,7 @@
 // i.e. 8x8 core matrices of 128 contiguous bytes, SBO = 128 (next 8 rows), LBO = rows*16 (next 8 k).
 #include <cuda_bf16.h>
 #include "dynca_stage2.cuh"
+#include "dynca_scatter2.cuh"
 #include "nca_internal.h"
 
 #define BT_THREADS 128
@@ -306,6 +307,15 @@ __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaB
             }
             umma_commit(bar);
         }
+        // while GEMM1 runs: fetch this cell's state (residual) and fire decision for epilogue 2
+        float xin[16];
+        float fire = 0.0f;
+        const size_t off = (size_t)t.b * C * plane + (size_t)gy * W + gx;
+        if (inimg) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) xin[c] = c < C ? __ldg(a.x_in + off + c * plane) : 0.0f;
+            fire = dynca_fire(a.fm, t.b, gy, gx, H, W);
+        }
         mbar_wait(bar, phase);
         phase ^= 1u;
         __syncwarp();            // tcgen05.ld is .sync.aligned: reconverge after the single-thread issue branch
@@ -357,11 +367,9 @@ __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaB
             tmem_ld16(tmem_lane + tmem_d2_col, v);
             tmem_ld_wait();
             if (inimg) {
-                const float fire = dynca_fire(a.fm, t.b, gy, gx, H, W);
-                const size_t off = (size_t)t.b * C * plane + (size_t)gy * W + gx;
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
-                    if (c < C) a.x_out[off + c * plane] = __ldg(a.x_in + off + c * plane) + (__uint_as_float(v[c]) + sB2[c]) * fire;
+                    if (c < C) a.x_out[off + c * plane] = xin[c] + (__uint_as_float(v[c]) + sB2[c]) * fire;
             }
         }
         tc_fence_before();
@@ -449,8 +457,8 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
     uint8_t* sB1t = sB1 + bg.b1_bytes;
     uint8_t* sB2d = sB1t + bg.b1_bytes;
     float* sStage = reinterpret_cast<float*>(sB2d + (size_t)2 * (g.fc / 8) * 128);
-    float* sGz = reinterpret_cast<float*>(sH);       // fp32 [8*npairs][DT_TMS], overlays H | Ga after S2 completes
-    float* sScr = reinterpret_cast<float*>(sA1);     // scatter scratch (NS == 2), overlays A1 after S2 completes
+    float* sGz = reinterpret_cast<float*>(sH);       // fp32 zero-padded planes [8*npairs][4][SP2_S], overlay H | Ga after S2
+    float* sScr = sGz + 8 * bg.npairs * SP2_PLANE;   // coarse planes of the scatter (NS == 2), same overlay
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = tid & 127, half = tid >> 7;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
@@ -512,9 +520,6 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
             }
             if (half == 0)
                 *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = dynca_cond_chunk(g, a.cond, t.b, gy, gx, inimg);
-            // chunks past the cond chunk were overwritten by the scatter scratch of the previous tile: re-zero
-            for (uint32_t i = tid + (uint32_t)(bg.npairs + 1) * 128; i < bg.a1_bytes / 16; i += BB_THREADS)
-                reinterpret_cast<uint4*>(sA1)[i] = make_uint4(0, 0, 0, 0);
         }
         // ---- g_y = fire * g_{t+1}: this thread's 8 channels of its cell ----
         {
@@ -611,12 +616,17 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (k0 + i < 8 * bg.npairs) sGz[(k0 + i) * DT_TMS + m] = __uint_as_float(v[i]) * g.s0;
+                    if (k0 + i < 8 * bg.npairs) sGz[(k0 + i) * SP2_PLANE + py * SP2_S + px + 1] = __uint_as_float(v[i]) * g.s0;
+            }
+            // zero columns 0 and 33..39 of every plane row
+            for (int i = tid; i < 8 * bg.npairs * DT_TH * 8; i += BB_THREADS) {
+                const int q = i & 7, r = i >> 3;
+                sGz[r * SP2_S + (q == 0 ? 0 : 32 + q)] = 0.0f;
             }
         }
         tc_fence_before();
         __syncthreads();
-        dynca_scatter_tile<NS, BB_THREADS, true>(g, t, sGz, sScr, a.g_out, a.g_next, a.g_tap, a.tap_c, a.tap_scale);
+        dynca_scatter_tile_v2<NS, BB_THREADS>(g, t, sGz, sScr, a.g_out, a.g_next, a.g_tap, a.tap_c, a.tap_scale);
         __syncthreads();
         // H / Ga rows past fc and the zero tail were clobbered by sGz: restore the zeros the next S2 relies on
         if (fc < 128)
