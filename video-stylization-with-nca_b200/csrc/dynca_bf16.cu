@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
     uint8_t* sB2d = sB1t + bg.b1_bytes;
     float* sStage = reinterpret_cast<float*>(sB2d + (size_t)2 * (g.fc / 8) * 128);
     float* sGz = reinterpret_cast<float*>(sH);       // fp32 zero-padded planes [8*npairs][4][SP2_S], overlay H | Ga after S2
-    float* sScr = sGz + 8 * bg.npairs * SP2_PLANE;   // coarse planes of the scatter (NS == 2), same overlay
+    float* sScr = sGz + 8 * bg.npairs * SP2_PLANE;   // coarse planes + bilinear weights of the scatter (NS == 2), same overlay
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = tid & 127, half = tid >> 7;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
         }
         tc_fence_before();
         __syncthreads();
-        dynca_scatter_tile_v2<NS, BB_THREADS>(g, t, sGz, sScr, a.g_out, a.g_next, a.g_tap, a.tap_c, a.tap_scale);
+        dynca_scatter_tile_v2<NS, BB_THREADS>(g, t, sGz, sScr, reinterpret_cast<float*>(sGy), a.g_out, a.g_next, a.g_tap, a.tap_c, a.tap_scale);
         __syncthreads();
         // H / Ga rows past fc and the zero tail were clobbered by sGz: restore the zeros the next S2 relies on
         if (fc < 128)

@@ -66,11 +66,12 @@ __device__ __forceinline__ float sp2_point(const float* __restrict__ px_, const 
     return v;
 }
 
-// sP: padded fine planes, rows indexed by dynca_krow<true>; sG: scratch for 4C coarse planes (SG2_PLANE floats each).
+// sP: padded fine planes, rows indexed by dynca_krow<true>; sG: scratch for 4C coarse planes (SG2_PLANE floats each);
+// sW: 88 floats of scratch for the bilinear weight tables.
 // Caller: __syncthreads() before (sP complete incl. zero columns) and after.
 template <int NS, int NT>
 __device__ __forceinline__ void dynca_scatter_tile_v2(const DyncaGeom& g, const DyncaTile& t, const float* __restrict__ sP,
-                                                      float* __restrict__ sG, float* __restrict__ g_out,
+                                                      float* __restrict__ sG, float* __restrict__ sW, float* __restrict__ g_out,
                                                       const float* __restrict__ g_next, const float* __restrict__ g_tap,
                                                       int tap_c, float tap_scale) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -142,36 +143,37 @@ __device__ __forceinline__ void dynca_scatter_tile_v2(const DyncaGeom& g, const 
         // ---------------- scale 1 ----------------
         const int Hc = H >> 1, Wc = W >> 1;
         const int cy0 = (t.y0 >> 1) - 1, cx0 = (t.x0 >> 1) - 1;
-        constexpr int ps = DT_PCH * DT_PCW;
-        constexpr int NG = NT / ps;
-        // Up^T: sG[f*C+c][pr][pq] = sum_{4x4 fine cells} wy * wx * s0 g_z ; zero outside the coarse image
-        if (tid < NG * ps) {
-            const int cell = tid % ps, grp = tid / ps;
-            const int pr = cell / DT_PCW, pq = cell % DT_PCW;
-            const int qy = cy0 + pr, qx = cx0 + pq;
-            const bool cell_ok = qy >= 0 && qy < Hc && qx >= 0 && qx < Wc;
-            float wy[4], wx[4];
-            int oy[4], ox[4];
+        // Up^T, separable: T[py] = sum_i wx[pq][i] * g[py][2pq-3+i]  (x pass, zero padding supplies the out-of-tile taps),
+        // sG[f*C+c][pr][pq] = sum_py wy[pr][py] * T[py] (y pass).  The bilinear weights (edge clamped, dynca.py:93-94)
+        // depend on the tile only: 16 + 72 values in shared memory (sW, 88 floats).  Coarse column pq reads the 4 padded
+        // columns starting at max(2pq-2, 0), i.e. tile cells px = base-1 .. base+2; dynca_up_weight is 0 off the footprint.
+        float* sWy = sW;                            // [4 pr][4 py]
+        float* sWx = sW + 16;                       // [18 pq][4 j]
+        if (tid < 16) {
+            const int fy = t.y0 + (tid & 3);
+            sWy[tid] = fy < H ? dynca_up_weight(fy, cy0 + (tid >> 2), Hc) : 0.0f;
+        } else if (tid >= 32 && tid < 32 + 4 * DT_PCW) {
+            const int pq = (tid - 32) >> 2, j = (tid - 32) & 3;
+            const int base = 2 * pq - 2 > 0 ? 2 * pq - 2 : 0;
+            const int px = base - 1 + j, fx = t.x0 + px, qx = cx0 + pq;
+            sWx[tid - 32] = (px >= 0 && px < DT_TW && fx < W && qx >= 0 && qx < Wc) ? dynca_up_weight(fx, qx, Wc) : 0.0f;
+        }
+        __syncthreads();
+        for (int it = tid; it < 4 * C * DT_PCW; it += NT) {
+            const int k = it / DT_PCW, pq = it % DT_PCW;
+            const float* src = sP + dynca_krow<true>(C, k % C, k / C) * SP2_PLANE + (2 * pq - 2 > 0 ? 2 * pq - 2 : 0);
+            const float4 wx = *reinterpret_cast<const float4*>(sWx + 4 * pq);
+            float T[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int fy = 2 * qy - 1 + i, py = fy - t.y0;
-                const bool oky = cell_ok && py >= 0 && py < DT_TH && fy < H;
-                wy[i] = oky ? dynca_up_weight(fy, qy, Hc) : 0.0f;
-                oy[i] = oky ? py * SP2_S : 0;
-                const int fx = 2 * qx - 1 + i, px = fx - t.x0;
-                const bool okx = cell_ok && px >= 0 && px < DT_TW && fx < W;
-                wx[i] = okx ? dynca_up_weight(fx, qx, Wc) : 0.0f;
-                ox[i] = okx ? px + 1 : 0;
+            for (int py = 0; py < DT_TH; ++py) {
+                const float2 v0 = *reinterpret_cast<const float2*>(src + py * SP2_S), v1 = *reinterpret_cast<const float2*>(src + py * SP2_S + 2);
+                T[py] = fmaf(wx.x, v0.x, fmaf(wx.y, v0.y, fmaf(wx.z, v1.x, wx.w * v1.y)));
             }
-            for (int k = grp; k < 4 * C; k += NG) {
-                const float* zr = sP + dynca_krow<true>(C, k % C, k / C) * SP2_PLANE;
-                float v = 0.0f;
+            float* dst = sG + k * SG2_PLANE + pq;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float* r = zr + oy[i];
-                    v = fmaf(wy[i], fmaf(wx[0], r[ox[0]], fmaf(wx[1], r[ox[1]], fmaf(wx[2], r[ox[2]], wx[3] * r[ox[3]]))), v);
-                }
-                sG[k * SG2_PLANE + pr * SG2_S + pq] = v;
+            for (int pr = 0; pr < DT_PCH; ++pr) {
+                const float4 wy = *reinterpret_cast<const float4*>(sWy + 4 * pr);
+                dst[pr * SG2_S] = fmaf(wy.x, T[0], fmaf(wy.y, T[1], fmaf(wy.z, T[2], wy.w * T[3])));
             }
         }
         for (int it = tid; it < 4 * C * DT_PCH * (SG2_S - DT_PCW); it += NT) {   // zero columns 18..23
