@@ -120,7 +120,7 @@ ORACLE_CASES = [
 @pytest.mark.parametrize("case", ORACLE_CASES, ids=lambda c: "B%d_C%d_fc%d_%dx%d_T%d_%s_s%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], len(c[7]), c[8]))
 def test_against_oracle_seeded(case):
     B, C, fc, H, W, T, pad, scales, cond = case
-    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    g = torch.Generator().manual_seed(1234 + ORACLE_CASES.index(case))   # fixed inputs (hash() of a tuple with str is per-process)
     cc = {"cpe": 2, None: 0, "tensor": 3}[cond]
     P = 4 * C + cc
     w1 = torch.randn(fc, P, generator=g) * 0.15
