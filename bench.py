@@ -6,7 +6,11 @@ BPTT through it with gradients injected at the final state and at two rgb taps (
 pattern).  Workload = BASELINE.json configs[1] ("c2"): 256x256, C=16, fc=128, CPE, perception
 scales [0,1], replicate padding, batch 8 per GPU, T=128, synthetic random state / reference-init weights.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+Default precision is bf16: the update MLP and every GEMM of the BPTT step run on tcgen05 with BF16 operands and fp32
+accumulation in TMEM, state / perception / gradients stay fp32 (north_star: 1e-2 per-step tolerance in this mode);
+--precision fp32 times the CUDA-core parity path.
 
 value      = fwd+BPTT cell-updates/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed, max over ranks
 fwd_value  = forward-only (no_grad, no history) cell-updates/s, measured the same way
@@ -135,7 +139,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
