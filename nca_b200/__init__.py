@@ -9,4 +9,4 @@ from ._lib import NcaError, lib_path, load_library  # noqa: E402,F401
 from . import functional, parallel  # noqa: E402,F401
 from .dynca_ec import DyNCA as DyNCA_EC, CPE2D  # noqa: E402,F401
 from .dynca_cd import DyNCA as DyNCA_CD, EdgeExtractor  # noqa: E402,F401
-# from .nca import ConditionedNCA, UpdateNet  # noqa: E402,F401
+from .nca import ConditionedNCA, UpdateNet, ImageEncoder  # noqa: E402,F401

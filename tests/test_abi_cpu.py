@@ -36,6 +36,10 @@ def test_abi_version_and_workspace(lib):
     bwd = lib.nca_dynca_workspace_bytes(C.byref(d), 1)
     assert 0 < fwd < bwd
     assert bwd >= 2 * 8 * 16 * 256 * 256 * 4
+    e = _lib.EncDesc(4, 20, 64, 64, 64, 3, _lib.NCA_MASK_PHILOX, 0.1, 0.5, 10.0)
+    assert 0 < lib.nca_enc_workspace_bytes(C.byref(e), 0) < lib.nca_enc_workspace_bytes(C.byref(e), 1)
+    e.hid = 32
+    assert lib.nca_enc_workspace_bytes(C.byref(e), 0) == 0
 
 
 def test_bad_arguments_are_reported(lib):

@@ -1,0 +1,130 @@
+"""Parity of the ConditionedNCA CUDA path (csrc/enc_f32.cu) with the reference (golden vectors made by the unmodified
+EncoderConditioning/nca.py) and with the oracle on seeded inputs.  Tolerances (BASELINE.json north_star): state 1e-5
+relative, gradients 1e-4 relative (fp32)."""
+import pytest
+import torch
+
+import nca_b200
+from nca_b200 import functional as Fn
+from oracle import nca_oracle as O
+from helpers import ENC_CASES, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+STATE_TOL, GRAD_TOL = 1e-5, 1e-4
+NAMES = ("wp", "wa", "ba", "wb", "bb", "wc")
+
+
+def _cuda_run(t, m, T, grads=True):
+    cfg = Fn.EncConfig(m["C"], m["living_dim"], m["thr"], m["rate"])
+    ps = [t[k].to(DEV).requires_grad_(grads) for k in NAMES]
+    x0 = t["x0"].to(DEV).requires_grad_(grads)
+    goal = t["goal_enc"].to(DEV).requires_grad_(grads)
+    final = Fn.enc_rollout(cfg, x0, goal, *ps, T, masks=t["fires"][:T].to(DEV))
+    return final, ps, x0, goal
+
+
+@pytest.mark.parametrize("name", ENC_CASES)
+def test_enc_golden_rollout_and_gradients(name):
+    t, m = load_case(name)
+    final, ps, x0, goal = _cuda_run(t, m, m["T"])
+    assert rel_err(final.detach().cpu(), t["final"]) < STATE_TOL
+    (final * t["coef_final"].to(DEV)).sum().backward()
+    for p, k in zip(ps + [x0, goal], ["g_" + n for n in NAMES] + ["g_x0", "g_goal"]):
+        assert rel_err(p.grad.cpu(), t[k]) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("name", ENC_CASES)
+def test_enc_single_steps_match_oracle(name):
+    t, m = load_case(name)
+    with torch.no_grad():
+        x = t["x0"]
+        for s in range(min(3, m["T"])):
+            want = O.enc_step(x, t["goal_enc"], *[t[k] for k in NAMES], t["fires"][s], m["living_dim"], m["thr"])
+            cfg = Fn.EncConfig(m["C"], m["living_dim"], m["thr"], m["rate"])
+            got = Fn.enc_rollout(cfg, x.to(DEV), t["goal_enc"].to(DEV), *[t[k].to(DEV) for k in NAMES], 1,
+                                 masks=t["fires"][s:s + 1].to(DEV))
+            assert rel_err(got.cpu(), want) < STATE_TOL
+            x = want
+
+
+CASES = [  # B, C, H, W, T, living_dim
+    (2, 20, 9, 37, 4, 3),       # ragged in both directions, two tiles in x
+    (1, 20, 64, 64, 3, 3),      # c4 frame size
+    (3, 12, 5, 70, 3, 3),       # fewer channels, three tiles in x
+    (1, 20, 16, 16, 3, -1),     # use_living_channel=False
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_C%d_%dx%d_T%d_l%d" % c)
+def test_enc_against_oracle_seeded(case):
+    B, C, H, W, T, liv = case
+    g = torch.Generator().manual_seed(31)
+    K = 3 * C
+    wp = torch.randn(K, 1, 3, 3, generator=g) * 0.3
+    wa = torch.randn(64, K, generator=g) * 0.2
+    ba = torch.randn(64, generator=g) * 0.1
+    wb = torch.randn(64, 64, generator=g) * 0.15
+    bb = torch.randn(64, generator=g) * 0.1
+    wc = torch.randn(C, 64, generator=g) * 0.1
+    x0 = torch.randn(B, C, H, W, generator=g) * 0.4
+    if liv >= 0:
+        x0[:, liv] = torch.rand(B, H, W, generator=g) * 0.5 - 0.15
+    x0[:, 0] *= 30.0                                              # some cells hit the +-10 clamp
+    goal = torch.rand(B, C, H, W, generator=g)
+    fires = (torch.rand(T, B, 1, H, W, generator=g) < 0.5).float()
+    coef = torch.randn(B, C, H, W, generator=g)
+    po = [p.clone().requires_grad_(True) for p in (x0, goal, wp, wa, ba, wb, bb, wc)]
+    if liv >= 0:
+        fo = O.enc_rollout(*po, fires, liv, 0.1)
+    else:   # no living channel: alive == all ones
+        x = po[0]
+        for s in range(T):
+            p = O.enc_perception_fast(x + po[1], po[2])
+            h1 = torch.relu(torch.einsum("jk,bkhw->bjhw", po[3], p) + po[4][None, :, None, None])
+            h2 = torch.relu(torch.einsum("jk,bkhw->bjhw", po[5], h1) + po[6][None, :, None, None])
+            x = torch.clamp(x + fires[s] * torch.einsum("cj,bjhw->bchw", po[7], h2), -10.0, 10.0)
+        fo = x
+    (fo * coef).sum().backward()
+    cfg = Fn.EncConfig(C, liv, 0.1, 0.5)
+    pg = [p.clone().to(DEV).requires_grad_(True) for p in (x0, goal, wp, wa, ba, wb, bb, wc)]
+    fg = Fn.enc_rollout(cfg, *pg, T, masks=fires.to(DEV))
+    (fg * coef.to(DEV)).sum().backward()
+    assert rel_err(fg.detach().cpu(), fo.detach()) < STATE_TOL
+    for a, b, n in zip(pg, po, ("x0", "goal") + NAMES):
+        assert rel_err(a.grad.cpu(), b.grad) < GRAD_TOL, n
+
+
+def test_enc_module_grow_with_encoder_gradient():
+    """drop-in module: grow() = encoder (PyTorch) + CUDA rollout; gradients reach the encoder; Philox == supplied"""
+    torch.manual_seed(5)
+    H = W = 32
+    nca = nca_b200.ConditionedNCA(target_shape=(3, H, W), num_hidden_channels=16, living_channel_dim=3).to(DEV)
+    sd = nca.state_dict()
+    assert tuple(sd["perception_net.weight"].shape) == (60, 1, 3, 3)
+    assert tuple(sd["update_net.out.0.weight"].shape) == (64, 60, 1, 1) and tuple(sd["update_net.out.4.weight"].shape) == (20, 64, 1, 1)
+    assert "update_net.out.4.bias" not in sd and "encoder.embed.0.weight" in sd
+    x = nca.generate_seed(4).to(DEV) + 0.05 * torch.randn(4, 20, H, W, device=DEV)
+    goal = torch.rand(4, 3, H, W, device=DEV)
+    T = 6
+    out = nca.grow(x, T, goal, seed=11)
+    masks = Fn.philox_mask(4, H, W, 0.5, 11, T, enc=True)
+    out2 = nca.grow(x, T, goal, masks=masks)
+    assert torch.equal(out, out2)
+    out.square().mean().backward()
+    for n, p in nca.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert float(nca.encoder.embed[0].weight.grad.abs().max()) > 0
+    # oracle on the same masks, encoder run on CPU
+    cpu = nca_b200.ConditionedNCA(target_shape=(3, H, W), num_hidden_channels=16, living_channel_dim=3)
+    cpu.load_state_dict({k: v.cpu() for k, v in nca.state_dict().items()})
+    ge = cpu._pad_goal(cpu.encoder(goal.cpu())).detach()
+    wp, *mlp = [w.detach() for w in cpu._w()]
+    mlp = [w.reshape(w.shape[0], -1) if w.dim() == 4 else w for w in mlp]
+    want = O.enc_rollout(x.cpu(), ge, wp, *mlp, masks.cpu(), 3, 0.1)
+    assert rel_err(out.detach().cpu(), want) < 5e-5
+    with torch.no_grad():
+        y, _ = nca((x, ge.to(DEV)), masks=masks[:1])
+    assert rel_err(y.cpu(), O.enc_step(x.cpu(), ge, wp, *mlp, masks[0].cpu(), 3, 0.1)) < STATE_TOL
+    assert nca.alive(out).dtype == torch.bool

@@ -231,3 +231,90 @@ def dynca_rollout(cfg, x0, w1, b1, w2, b2, T, rate=0.5, cond=None, masks=None, s
         handle.hist = states
         return states[T], RgbTaps(handle, None, T)
     return states[T & 1], None
+
+
+# ------------------------------------------------------------------------------------------------
+# ConditionedNCA (EncoderConditioning/nca.py)
+# ------------------------------------------------------------------------------------------------
+class EncConfig:
+    """Static description of a ConditionedNCA (ctor arguments of nca.py:62-74)."""
+
+    def __init__(self, C_, living_dim, alive_thr=0.1, fire_rate=0.5, hid=64, clamp=10.0):
+        self.C, self.living_dim, self.alive_thr, self.fire_rate, self.hid, self.clamp = C_, living_dim, alive_thr, fire_rate, hid, clamp
+
+    def desc(self, B, H, W, supplied):
+        return _lib.EncDesc(B, self.C, H, W, self.hid, self.living_dim,
+                            _lib.NCA_MASK_SUPPLIED if supplied else _lib.NCA_MASK_PHILOX,
+                            float(self.alive_thr), float(self.fire_rate), float(self.clamp))
+
+
+def _enc_weights_struct(ws):
+    return _lib.EncWeights(*[t.data_ptr() for t in ws])
+
+
+def _enc_forward_raw(cfg, x0, goal, ws, masks, seed, T, keep_history):
+    lib = load_library()
+    B, Cc, H, W = x0.shape
+    d = cfg.desc(B, H, W, masks is not None)
+    states = torch.empty(T + 1 if keep_history else 2, B, Cc, H, W, device=x0.device, dtype=torch.float32)
+    states[0].copy_(x0)
+    life = torch.empty(T, B, H, W, device=x0.device, dtype=torch.uint8) if keep_history else None
+    with torch.cuda.device(x0.device):
+        nbytes = lib.nca_enc_workspace_bytes(C.byref(d), 0)
+        wsb = torch.empty(max(nbytes, 16), device=x0.device, dtype=torch.uint8)
+        wst = _enc_weights_struct(ws)
+        check(lib.nca_enc_forward(C.byref(d), C.byref(wst), _ptr(goal), _ptr(masks), C.c_uint64(seed), 0, T,
+                                  int(keep_history), _ptr(states), _ptr(life), _ptr(wsb), nbytes, _stream()))
+    return states, life
+
+
+class _EncRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, goal, wp, wa, ba, wb, bb, wc, masks, cfg, T, seed):
+        ws = [_c(t) for t in (wp, wa, ba, wb, bb, wc)]
+        x0c, goalc, masks = _c(x0), _c(goal), _c(masks)
+        hist, life = _enc_forward_raw(cfg, x0c, goalc, ws, masks, seed, T, True)
+        ctx.cfg, ctx.T, ctx.seed = cfg, T, seed
+        ctx.w_shapes = tuple(t.shape for t in (wp, wa, ba, wb, bb, wc))
+        ctx.save_for_backward(goalc, masks, *ws)
+        ctx.hist, ctx.life = hist, life
+        return hist[T]
+
+    @staticmethod
+    def backward(ctx, g_final):
+        lib = load_library()
+        goal, masks, *ws = ctx.saved_tensors
+        hist, life, cfg, T = ctx.hist, ctx.life, ctx.cfg, ctx.T
+        _, B, Cc, H, W = hist.shape
+        d = cfg.desc(B, H, W, masks is not None)
+        g_final = _c(g_final)
+        gx0 = torch.empty(B, Cc, H, W, device=hist.device, dtype=torch.float32)
+        ggoal = torch.empty_like(gx0)
+        gws = [torch.empty_like(t) for t in ws]
+        with torch.cuda.device(hist.device):
+            nbytes = lib.nca_enc_workspace_bytes(C.byref(d), 1)
+            wsb = torch.empty(nbytes, device=hist.device, dtype=torch.uint8)
+            wst, gst = _enc_weights_struct(ws), _enc_weights_struct(gws)
+            check(lib.nca_enc_backward(C.byref(d), C.byref(wst), _ptr(goal), _ptr(masks), C.c_uint64(ctx.seed), 0, T,
+                                       _ptr(hist), _ptr(life), _ptr(g_final), _ptr(gx0), _ptr(ggoal), C.byref(gst),
+                                       _ptr(wsb), nbytes, _stream()))
+        return (gx0, ggoal, *[g.view(s) for g, s in zip(gws, ctx.w_shapes)], None, None, None, None)
+
+
+def enc_rollout(cfg, x0, goal, wp, wa, ba, wb, bb, wc, T, masks=None, seed=None):
+    """T ConditionedNCA steps (the loop of ConditionedNCA.grow, nca.py:207-208) on an already encoded, zero-padded
+    goal [B,C,H,W].  masks: optional supplied fire masks [T,B,1,H,W] (1 = fire, i.e. u < rate)."""
+    _need_cuda(x0, goal, wp, wa, ba, wb, bb, wc, masks)
+    if tuple(goal.shape) != tuple(x0.shape):
+        raise NcaError(f"goal encoding must have the state's shape {tuple(x0.shape)}, got {tuple(goal.shape)}")
+    if seed is None:
+        seed = new_seed() if masks is None else 0
+    if masks is not None and tuple(masks.shape) != (T, x0.shape[0], 1, x0.shape[2], x0.shape[3]):
+        raise NcaError(f"masks must be [T,B,1,H,W], got {tuple(masks.shape)}")
+    if T == 0:
+        return x0
+    ts = (x0, goal, wp, wa, ba, wb, bb, wc)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
+        return _EncRollout.apply(*ts, masks, cfg, T, seed)
+    states, _ = _enc_forward_raw(cfg, _c(x0), _c(goal), [_c(t) for t in ts[2:]], _c(masks), seed, T, False)
+    return states[T & 1]
