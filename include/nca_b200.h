@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NCA_B200_ABI_VERSION 1
+#define NCA_B200_ABI_VERSION 2
 
 enum { NCA_OK = 0, NCA_ERR_ARG = -1, NCA_ERR_UNSUPPORTED = -2, NCA_ERR_CUDA = -3, NCA_ERR_WORKSPACE = -4 };
 
@@ -85,9 +85,12 @@ int nca_edge_extract(int B, int H, int W, const float* img, int tanh_transform, 
  *   cond   : [B,cc,H,W] when cond_kind == NCA_COND_TENSOR else NULL
  *   masks  : [T,B,1,H,W] when mask_mode == NCA_MASK_SUPPLIED else NULL
  *   seed,t0: Philox key / first step counter when mask_mode == NCA_MASK_PHILOX
+ *   coarse_hist: optional (may be NULL), only used when n_scales == 2 and keep_history != 0: float
+ *            [T+1,B,C,H/2,W/2]; the forward writes the 2x2-mean coarse state of every states[t] there so that
+ *            nca_dynca_backward does not have to recompute it (pass the same buffer to it)
  *   workspace: nca_dynca_workspace_bytes(d, 0) bytes                                              */
 int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
-                      uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states,
+                      uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, float* coarse_hist,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* BPTT through the T steps recorded in `states` ([T+1,B,C,H,W] from nca_dynca_forward with keep_history).
@@ -99,15 +102,21 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
  *   tap_steps: host array [n_taps], strictly increasing, each in 1..T
  *   gx0      : dL/d states[0]  [B,C,H,W] (written)
  *   gw       : weight gradients, reference layout (written)
+ *   coarse_hist: NULL or the buffer nca_dynca_forward filled (n_scales == 2)
  *   workspace: nca_dynca_workspace_bytes(d, 1) bytes
  * State gradients are accumulated with red.add (fp32 summation order is not deterministic).          */
 int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
-                       uint64_t seed, int32_t t0, int32_t T, const float* states,
+                       uint64_t seed, int32_t t0, int32_t T, const float* states, const float* coarse_hist,
                        const float* g_final, const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps,
                        int32_t tap_c, float tap_scale, float* gx0, const NcaDyncaWeightGrads* gw,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward);
+
+/* Which step kernel a description dispatches to (tests / reports): 0 = fp32 CUDA cores, 1 = tcgen05 with 4x32 tiles
+ * and cp.async staging (any shape), 2 = tcgen05 with 8x16 tiles, TMA staging and the coarse scale on the tensor
+ * cores (W % 4 == 0, W % 8 == 0 for two scales, fc % 32 == 0).  Negative = invalid description. */
+int nca_dynca_kernel_variant(const NcaDyncaDesc* d, int32_t backward);
 
 /* The Philox fire mask the kernels generate, materialised as float [T,B,1,H,W] (tests / debugging).
  * enc != 0 uses the ConditionedNCA rule (u < rate, EncoderConditioning/nca.py:165-174). */

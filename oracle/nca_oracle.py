@@ -227,9 +227,44 @@ def _hilo(t):
     return hi + bf16r(t - hi)
 
 
-def dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, mode, cond, g_final, taps=None):
+def perceive_coarse(x, mode):
+    """[id | sobel_x | sobel_y | lap] of the 2x2-mean coarse state, NOT upsampled: [B,4C,H/2,W/2]."""
+    xc = down2(x)
+    return torch.cat([xc, _stencil(xc, SOBEL_X, mode), _stencil(xc, SOBEL_Y, mode), _stencil(xc, LAPLACE, mode)], dim=1)
+
+
+def _emu_preact(xr, w1q, b1q, scales, mode, cond, variant):
+    """pre-activation a of one step with the rounding points of kernel `variant` (1: dynca_bf16.cu, 2: dynca_tc2.cu).
+    Returns (a, zp, zq): zp = fp32 perception that autograd can differentiate, zq = the rounded GEMM operand the
+    weight gradient pairs with (variant 1 layout)."""
+    C = xr.shape[1]
+    with torch.enable_grad():
+        zp = perceive_multiscale(xr, scales, mode, None)
+    zq = bf16r(zp.detach())
+    if cond is not None:
+        zq = torch.cat([zq, _hilo(cond)], dim=1)
+    if variant == 2 and len(scales) == 2:
+        # tcgen05 v2: fine and coarse perception are rounded separately, the coarse pre-activation is rounded to bf16
+        # before the (exact, constant-matrix) bilinear upsample; W1 / n_scales is exact
+        xd = xr.detach()
+        zf = bf16r(perceive(xd, 0, mode))
+        zc = bf16r(perceive_coarse(xd, mode))
+        w1h = w1q[:, :4 * C] * 0.5
+        a = torch.einsum("jk,bkhw->bjhw", w1h, zf) + up2(bf16r(torch.einsum("jk,bkhw->bjhw", w1h, zc)))
+        if cond is not None:
+            a = a + torch.einsum("jk,bkhw->bjhw", w1q[:, 4 * C:], _hilo(cond))
+        a = a + b1q[None, :, None, None]
+    else:
+        a = torch.einsum("jk,bkhw->bjhw", w1q, zq) + b1q[None, :, None, None]
+    return a, zp, zq
+
+
+def dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, mode, cond, g_final, taps=None, fwd_variant=1,
+                                bwd_variant=1):
     """T steps forward with bf16-rounded GEMM operands, then manual BPTT with the kernel's rounding points.
-    taps: {step t in 1..T: dL/d(2 * states[t][:, :3])}.  Returns (final, dict of gradients)."""
+    taps: {step t in 1..T: dL/d(2 * states[t][:, :3])}.  fwd_variant / bwd_variant: which tensor-core kernel generation
+    ran the forward rollout / recomputes the step inside the BPTT (nca_dynca_kernel_variant).
+    Returns (final, dict of gradients, states)."""
     taps = taps or {}
     T = masks.shape[0]
     C = x0.shape[1]
@@ -239,15 +274,13 @@ def dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, mode, cond, g
     x = x0
     for t in range(T):
         xr = x.detach().clone().requires_grad_(True)
-        with torch.enable_grad():
-            zp = perceive_multiscale(xr, scales, mode, None)
-        zq = bf16r(zp.detach())
-        if cond is not None:
-            zq = torch.cat([zq, _hilo(cond)], dim=1)
-        a = torch.einsum("jk,bkhw->bjhw", w1q, zq) + b1q[None, :, None, None]
+        a, zp, zq = _emu_preact(xr, w1q, b1q, scales, mode, cond, fwd_variant)
         hq = bf16r(torch.relu(a))
         y = torch.einsum("cj,bjhw->bchw", w2q, hq) + b2[None, :, None, None]
         x = x.detach() + y * masks[t]
+        if bwd_variant != fwd_variant:          # the BPTT kernel recomputes the step with its own rounding points
+            a, zp, zq = _emu_preact(xr, w1q, b1q, scales, mode, cond, bwd_variant)
+            hq = bf16r(torch.relu(a))
         saved.append((xr, zp, zq, a, hq))
         xs.append(x)
     g = g_final.clone() if g_final is not None else torch.zeros_like(x0)

@@ -105,8 +105,12 @@ def _emu_errors(name, T):
     taps = [tp for tp in m["taps"] if tp <= T]
     coefs = [t["coef_final"].to(DEV)] + [t[f"coef_tap{tp}"].to(DEV) for tp in taps]
     fb, gb = _cuda_grads(mb, x0, T, masks[:T], taps, coefs, **kwargs)
+    kind, cc = {"cpe": (_lib.NCA_COND_CPE, 2), "edges": (_lib.NCA_COND_TENSOR, 3), None: (_lib.NCA_COND_NONE, 0)}[m["cond"]]
+    cfg = Fn.DyncaConfig(m["C"], m["fc"], m["pad"], m["scales"], kind, cc, precision="bf16")
+    fv, bv = (Fn.dynca_kernel_variant(cfg, m["B"], m["H"], m["W"], backward=bw) for bw in (False, True))
     fe, ge, _ = O.dynca_bf16emu_rollout_grads(t["x0"], t["w1"], t["b1"], t["w2"], t["b2"], t["masks"][:T], m["scales"], m["pad"],
-                                              cond_for(t, m), t["coef_final"], {tp: t[f"coef_tap{tp}"] for tp in taps})
+                                              cond_for(t, m), t["coef_final"], {tp: t[f"coef_tap{tp}"] for tp in taps},
+                                              fwd_variant=fv, bwd_variant=bv)
     shapes = dict(x0=x0.shape, w1=(m["fc"], -1), b1=(-1,), w2=(m["C"], m["fc"]), b2=(-1,))
     gmax = {n: rel_err(a.reshape(shapes[n]), ge[n]) for a, n in zip(gb, shapes)}
     grms = {n: float((a.reshape(shapes[n]) - ge[n]).norm() / (ge[n].norm() + 1e-30)) for a, n in zip(gb, shapes)}

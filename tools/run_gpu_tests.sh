@@ -1,0 +1,3 @@
+#!/bin/bash
+# full GPU parity suite (run under gpurun)
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25

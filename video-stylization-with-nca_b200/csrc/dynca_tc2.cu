@@ -1,0 +1,630 @@
+// DyNCA step on the 5th-gen tensor cores, second generation (NCA_PREC_BF16 when the shape allows it):
+//   8x16 tiles, TMA staging, register-blocked perception, coarse scale through the tensor cores.
+// Reference semantics: ExtraChannels/models/dynca.py:71-128 (same step as dynca_f32.cu / dynca_bf16.cu).
+//
+// One CTA = 256 threads = one 8x16 tile of cells (row r = py*16 + px of every M=128 operand, TMEM lane r); warps w and
+// w+4 share the lane quarter w%4 and split columns.  Per tile:
+//   TMA  : state tile + 1-cell ring [C][10][20] fp32 (zero filled outside the image; other padding modes are patched
+//          on border tiles) and, for two perception scales, the coarse (2x2-mean) tile + 2-cell ring [C][8][12]
+//   fine perception (fp32, 4 vertically adjacent cells x 2 channels per thread, separable Sobel / Laplacian)
+//          -> A1 [128 x K1] bf16, K-major UMMA layout (K order k' = 8*(c/2) + 4*(c%2) + filter, then the cond chunk)
+//   coarse perception -> Zc [64 x 64] bf16 (60 coarse cells of the 6x10 footprint, replicate-extended at the image
+//          border so that the x2 bilinear upsample, dynca.py:93-94, becomes a constant matrix U)
+//   MMA  : Dc = Zc . W1h^T   (W1h = W1 / n_scales)            -> TMEM -> bf16 -> DcB  (B operand, MN-major)
+//          D1 = A1 . W1h^T + U . DcB                           = W1h (z_fine + up(z_coarse)) + cond / bias terms
+//   E1   : h = relu(D1) -> bf16 A2 ;  MMA: D2 = A2 . W2^T ;  E2: x' = x + (D2 + b2) * fire, coalesced NCHW store, and
+//          the 2x2 means of x' (the coarse state of the next step) by warp shuffles.
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+#include "dynca_tc_common.cuh"
+
+#define T2_TH 8
+#define T2_TW 16
+// TMA (fp32, no swizzle) needs the innermost box coordinate to be a multiple of 4 elements (16 bytes; measured: any
+// other start raises an illegal-instruction fault), so the boxes start 4 columns left of the tile: fine box columns
+// x0-4 .. x0+19 (ring column x0-1 at index T2_XO), coarse box columns x0/2-4 .. x0/2+11 (footprint column x0/2-2 at T2_CO)
+#define T2_XR 10
+#define T2_XS 24
+#define T2_XO 3
+#define T2_CR 8
+#define T2_CS 16
+#define T2_CO 2
+#define T2_QH 6
+#define T2_QW 10
+#define T2_THREADS 256
+#define T2_HDR 1024u
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// two floats -> bf16x2 with relu fused (lo in the low half)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+struct T2FwdArgs {
+    DyncaGeom g;
+    Bf16Geom bg;
+    const float* cond;
+    const float* x_in;      // states slot of this step (border patches, supplied-mask independent)
+    const float* xc_in;     // coarse state of this step (border patches)
+    float* x_out;
+    float* xc_out;          // coarse state of the next step (NS == 2), may be NULL
+    int slot_in, cslot_in;  // slot coordinates of x_in / xc_in in the tensor maps
+    const __nv_bfloat16* B1; const __nv_bfloat16* B2; const float* b2p; const __nv_bfloat16* U;
+    FireMask fm;
+    int tiles_x, tiles_y, n_tiles;
+    int dbg;
+};
+
+struct T2Smem {
+    uint32_t b1, b2w, u, x, xc, uni, a1, zc, dcb, total;
+};
+__host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16Geom& bg) {
+    T2Smem s;
+    uint32_t o = T2_HDR;
+    s.b1 = o; o += bg.b1_bytes;
+    s.b2w = o; o += bg.b2_bytes;
+    s.u = o; o += g.ns == 2 ? 16384u : 0u;
+    o = (o + 127u) & ~127u;
+    s.x = o; o += (uint32_t)g.C * T2_XR * T2_XS * 4u;
+    o = (o + 127u) & ~127u;
+    s.xc = o; o += g.ns == 2 ? (uint32_t)g.C * T2_CR * T2_CS * 4u : 0u;
+    o = (o + 127u) & ~127u;
+    s.uni = o;
+    s.a1 = o;
+    s.zc = s.a1 + bg.a1_bytes;
+    s.dcb = s.zc + (g.ns == 2 ? 8192u : 0u);
+    uint32_t first = bg.a1_bytes + (g.ns == 2 ? 8192u + (uint32_t)(g.fc / 8) * 1024u : 0u);
+    o += first > bg.a2_bytes ? first : bg.a2_bytes;
+    s.total = o;
+    return s;
+}
+
+// perception of 4 vertically adjacent cells (rows r0 .. r0+3 of the tile) of one channel; col = stage column of the
+// left neighbour.  Separable: s = [1 2 1]^T, d = [-1 0 1]^T over rows.
+__device__ __forceinline__ void t2_percept4(const float* __restrict__ ch, int r0, int col, float id[4], float sx[4], float sy[4], float lp[4]) {
+    float s[3][4], d[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = ch[(r0 + k) * T2_XS + T2_XO + col + j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s[j][k] = fmaf(2.0f, v[k + 1], v[k] + v[k + 2]);
+            d[j][k] = v[k + 2] - v[k];
+            if (j == 1) id[k] = v[k + 1];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sx[k] = s[2][k] - s[0][k];
+        sy[k] = fmaf(2.0f, d[1][k], d[0][k] + d[2][k]);
+        lp[k] = fmaf(-16.0f, id[k], fmaf(2.0f, s[1][k], s[0][k] + s[2][k]));
+    }
+}
+// same for 3 vertically adjacent coarse cells (coarse stage stride T2_CS)
+__device__ __forceinline__ void t2_percept3c(const float* __restrict__ ch, int r0, int col, float id[3], float sx[3], float sy[3], float lp[3]) {
+    float s[3][3], d[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = ch[(r0 + k) * T2_CS + T2_CO + col + j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s[j][k] = fmaf(2.0f, v[k + 1], v[k] + v[k + 2]);
+            d[j][k] = v[k + 2] - v[k];
+            if (j == 1) id[k] = v[k + 1];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        sx[k] = s[2][k] - s[0][k];
+        sy[k] = fmaf(2.0f, d[1][k], d[0][k] + d[2][k]);
+        lp[k] = fmaf(-16.0f, id[k], fmaf(2.0f, s[1][k], s[0][k] + s[2][k]));
+    }
+}
+
+// patch the staged tiles of a border tile: every staged position outside the image takes the value the padding mode
+// prescribes (TMA filled it with zero, which is already right for constant padding)
+template <int NS>
+__device__ __forceinline__ void t2_patch_border(const DyncaGeom& g, const float* __restrict__ x, const float* __restrict__ xc, int b,
+                                                int y0, int x0, float* __restrict__ sX, float* __restrict__ sXc) {
+    const int C = g.C, H = g.H, W = g.W;
+    if (g.pad == NCA_PAD_CONSTANT) return;
+    const size_t plane = (size_t)H * W;
+    for (int i = threadIdx.x; i < C * T2_XR * 18; i += T2_THREADS) {
+        const int q = i % 18, r = (i / 18) % T2_XR, c = i / (18 * T2_XR);
+        const int yy = y0 - 1 + r, xx = x0 - 1 + q;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) continue;
+        const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
+        sX[(c * T2_XR + r) * T2_XS + T2_XO + q] = __ldg(x + ((size_t)b * C + c) * plane + (size_t)iy * W + ix);
+    }
+    if (NS == 2) {
+        const int Hc = H >> 1, Wc = W >> 1;
+        const size_t cplane = (size_t)Hc * Wc;
+        for (int i = threadIdx.x; i < C * T2_CR * 12; i += T2_THREADS) {
+            const int q = i % 12, r = (i / 12) % T2_CR, c = i / (12 * T2_CR);
+            const int yy = (y0 >> 1) - 2 + r, xx = (x0 >> 1) - 2 + q;
+            if (yy >= 0 && yy < Hc && xx >= 0 && xx < Wc) continue;
+            const int iy = nca_padmap(yy, Hc, g.pad), ix = nca_padmap(xx, Wc, g.pad);
+            sXc[(c * T2_CR + r) * T2_CS + T2_CO + q] = __ldg(xc + ((size_t)b * C + c) * cplane + (size_t)iy * Wc + ix);
+        }
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(T2_THREADS) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                    const __grid_constant__ CUtensorMap tm_xc, const T2FwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const DyncaGeom& g = a.g;
+    const Bf16Geom& bg = a.bg;
+    const T2Smem L = t2_smem(g, bg);
+    uint64_t* barM = reinterpret_cast<uint64_t*>(smem);         // MMA completion
+    uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);     // TMA completion
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+    float* sB2 = reinterpret_cast<float*>(smem + 64);           // 16 floats
+    float* sFire = reinterpret_cast<float*>(smem + 128);        // 128 floats
+    uint8_t* sB1 = smem + L.b1;
+    uint8_t* sB2w = smem + L.b2w;
+    uint8_t* sU = smem + L.u;
+    float* sX = reinterpret_cast<float*>(smem + L.x);
+    float* sXc = reinterpret_cast<float*>(smem + L.xc);
+    uint8_t* sA1 = smem + L.a1;
+    uint8_t* sZc = smem + L.zc;
+    uint8_t* sDcB = smem + L.dcb;
+    uint8_t* sA2 = smem + L.uni;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = tid & 127, half = tid >> 7;
+    const int C = g.C, H = g.H, W = g.W, fc = g.fc;
+    const size_t plane = (size_t)H * W;
+    const uint32_t stage_bytes = (uint32_t)C * T2_XR * T2_XS * 4u + (NS == 2 ? (uint32_t)C * T2_CR * T2_CS * 4u : 0u);
+    const uint32_t tmem_cols = NS == 2 ? 256u : 128u;
+
+    // ---- one-time setup ----
+    for (uint32_t i = tid; i < bg.b1_bytes / 16; i += T2_THREADS)
+        reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
+    for (uint32_t i = tid; i < bg.b2_bytes / 16; i += T2_THREADS)
+        reinterpret_cast<uint4*>(sB2w)[i] = __ldg(reinterpret_cast<const uint4*>(a.B2) + i);
+    if (NS == 2)
+        for (uint32_t i = tid; i < 16384u / 16; i += T2_THREADS)
+            reinterpret_cast<uint4*>(sU)[i] = __ldg(reinterpret_cast<const uint4*>(a.U) + i);
+    if (tid < 16) sB2[tid] = a.b2p[tid];
+    if (tid == 0) {
+        mbar_init(barM, 1);
+        mbar_init(barT, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = 0u;
+    const uint32_t idesc1 = umma_idesc_bf16(128, fc), idesc2 = umma_idesc_bf16(128, 16);
+    const uint32_t idescU = umma_idesc_bf16(128, fc) | (1u << 16);      // B operand MN-major
+    const uint32_t lbo_b1 = (uint32_t)(fc / 8) * 128u;
+    const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    uint32_t phM = 0, phT = 0;
+    const int py = r >> 4, px = r & 15;
+
+    const CUtensorMap* const ptm_x = &tm_x;
+    const CUtensorMap* const ptm_xc = &tm_xc;
+#define T2_ISSUE_TMA(tile_)                                                                                              \
+    do {                                                                                                                 \
+        const int tt_ = (tile_);                                                                                         \
+        const int tb_ = tt_ / (a.tiles_x * a.tiles_y), ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
+        mbar_expect_tx(barT, stage_bytes);                                                                               \
+        tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
+        if (NS == 2) tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                 \
+    } while (0)
+    const int n_tiles = a.dbg == 1 ? 0 : a.n_tiles;
+    if (tid == 0 && (int)blockIdx.x < n_tiles) T2_ISSUE_TMA(blockIdx.x);
+
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        const int b = tile / (a.tiles_x * a.tiles_y);
+        const int y0 = ((tile / a.tiles_x) % a.tiles_y) * T2_TH, x0 = (tile % a.tiles_x) * T2_TW;
+        const int gy = y0 + py, gx = x0 + px;
+        const bool inimg = gy < H && gx < W;
+        const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W;
+        mbar_wait(barT, phT);
+        phT ^= 1u;
+        if (a.dbg == 2) break;
+        if (border) {     // CTA-uniform
+            t2_patch_border<NS>(g, a.x_in, a.xc_in, b, y0, x0, sX, sXc);
+            __syncthreads();
+        }
+        // ---- fire decisions of the tile ----
+        if (a.fm.supplied) {
+            if (tid < 128) sFire[r] = inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f;
+        } else if (warp == (iter & 7)) {
+            const int fy = y0 + (lane >> 2), fx = x0 + 4 * (lane & 3);
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fy < H && fx < W) {
+                const uint32_t p = (uint32_t)(fy * W + fx);
+                const uint4 rr = nca_philox4x32_10(p >> 2, (uint32_t)b, a.fm.t, NCA_PHILOX_STREAM, a.fm.k0, a.fm.k1);
+                f.x = nca_fire(rr.x, a.fm.thr, 0); f.y = nca_fire(rr.y, a.fm.thr, 0);
+                f.z = nca_fire(rr.z, a.fm.thr, 0); f.w = nca_fire(rr.w, a.fm.thr, 0);
+            }
+            *reinterpret_cast<float4*>(sFire + (lane >> 2) * 16 + 4 * (lane & 3)) = f;
+        }
+        // ---- fine perception -> A1: warp = channel pair, lane = (column px, channel of the pair), two vertical blocks.
+        //      (channel planes are 240 floats apart = 16 banks, so the two half-warps never collide) ----
+        {
+            const int cp = warp, hc = lane >> 4, pxx = lane & 15, c = 2 * cp + hc;
+            if (cp < bg.npairs) {
+#pragma unroll
+                for (int vb = 0; vb < 2; ++vb) {
+                    float id[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (c < C) t2_percept4(sX + c * T2_XR * T2_XS, 4 * vb, pxx, id, sx, sy, lp);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = (4 * vb + k) * 16 + pxx;
+                        uint2 v;
+                        v.x = pack_bf16(id[k], sx[k]); v.y = pack_bf16(sy[k], lp[k]);
+                        *reinterpret_cast<uint2*>(sA1 + (uint32_t)cp * 2048u + (uint32_t)rr * 16u + (uint32_t)hc * 8u) = v;
+                    }
+                }
+            }
+        }
+        // residual state of this thread's cell (channels 8*half ..), cond chunk, zero tail chunks of A1
+        float xres[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = 8 * half + i;
+            xres[i] = c < C ? sX[(c * T2_XR + py + 1) * T2_XS + T2_XO + px + 1] : 0.0f;
+        }
+        if (half == 0) {
+            *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
+        } else {
+            for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
+                *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
+        }
+        if (NS == 2) {
+            // ---- coarse perception -> Zc rows q = qy*10 + qx: warp = channel pair, lane = (qx, 3-row block) ----
+            const int cp = warp, qx = lane % T2_QW, hb = lane / T2_QW;
+            if (lane < 2 * T2_QW && cp < bg.npairs) {
+                float id0[3], sx0[3], sy0[3], lp0[3], id1[3] = {0.f, 0.f, 0.f}, sx1[3] = {0.f, 0.f, 0.f}, sy1[3] = {0.f, 0.f, 0.f},
+                      lp1[3] = {0.f, 0.f, 0.f};
+                t2_percept3c(sXc + (2 * cp) * T2_CR * T2_CS, 3 * hb, qx, id0, sx0, sy0, lp0);
+                if (2 * cp + 1 < C) t2_percept3c(sXc + (2 * cp + 1) * T2_CR * T2_CS, 3 * hb, qx, id1, sx1, sy1, lp1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int q = (3 * hb + k) * T2_QW + qx;
+                    uint4 v;
+                    v.x = pack_bf16(id0[k], sx0[k]); v.y = pack_bf16(sy0[k], lp0[k]);
+                    v.z = pack_bf16(id1[k], sx1[k]); v.w = pack_bf16(sy1[k], lp1[k]);
+                    *reinterpret_cast<uint4*>(sZc + (uint32_t)cp * 1024u + (uint32_t)q * 16u) = v;
+                }
+            }
+            // rows 60..63 of every chunk and the chunks of absent channel pairs must be finite (they meet zero columns of
+            // U / zero rows of W1h): zero them; A2 overlays this area, so every tile
+            if (tid < 32) *reinterpret_cast<uint4*>(sZc + (uint32_t)(tid >> 2) * 1024u + (uint32_t)(60 + (tid & 3)) * 16u) = make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < (8 - bg.npairs) * 64; i += T2_THREADS)
+                *reinterpret_cast<uint4*>(sZc + (uint32_t)(bg.npairs + (i >> 6)) * 1024u + (uint32_t)(i & 63) * 16u) = make_uint4(0, 0, 0, 0);
+            if (border) {
+                // replicate-extend the coarse perception over the image border (edge clamp of the upsample)
+                __syncthreads();
+                const int Hc = H >> 1, Wc = W >> 1;
+                for (int i = tid; i < T2_QH * T2_QW * 8; i += T2_THREADS) {
+                    const int ch = i & 7, q = i >> 3;
+                    const int qy = q / T2_QW, qxx = q % T2_QW;
+                    const int Qy = (y0 >> 1) - 1 + qy, Qx = (x0 >> 1) - 1 + qxx;
+                    const int Cy = min(max(Qy, 0), Hc - 1), Cx = min(max(Qx, 0), Wc - 1);
+                    if (Cy == Qy && Cx == Qx) continue;
+                    int sy_ = Cy - ((y0 >> 1) - 1), sx_ = Cx - ((x0 >> 1) - 1);
+                    // a ragged last tile can clamp to a cell outside the 6x10 footprint only if that cell is outside
+                    // every in-image fine cell's support; keep the index in range
+                    sy_ = min(max(sy_, 0), T2_QH - 1); sx_ = min(max(sx_, 0), T2_QW - 1);
+                    const int qs = sy_ * T2_QW + sx_;
+                    *reinterpret_cast<uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)q * 16u) =
+                        *reinterpret_cast<const uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)qs * 16u);
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();                                   // ---- sync A: operands complete, stage free ----
+        if (a.dbg == 3) break;
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA1), b_addr = smem_u32(sB1);
+            if (NS == 2) {
+                const uint32_t z_addr = smem_u32(sZc);
+                // Dc = Zc . W1h^T over the perception columns.  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of
+                // the M = 128 instruction alias the next chunk (finite values) and produce rows of Dc nobody reads
+                for (int ks = 0; ks < (bg.npairs + 1) / 2; ++ks)
+                    umma_f16_ss(tmem_base + TM_DC, umma_desc(z_addr + (uint32_t)ks * 2048u, 1024u, 128u),
+                                umma_desc(b_addr + (uint32_t)ks * 2u * lbo_b1, lbo_b1, 128u), idesc1, ks > 0 ? 1u : 0u);
+                umma_commit(barM);
+            }
+            for (int ks = 0; ks < bg.K1 / 16; ++ks)
+                umma_f16_ss(tmem_base + TM_D1, umma_desc(a_addr + (uint32_t)ks * 4096u, 2048u, 128u),
+                            umma_desc(b_addr + (uint32_t)ks * 2u * lbo_b1, lbo_b1, 128u), idesc1, ks > 0 ? 1u : 0u);
+            if (NS == 1) umma_commit(barM);
+            if (tile + (int)gridDim.x < n_tiles) T2_ISSUE_TMA(tile + gridDim.x);
+        }
+        if (NS == 2) {
+            mbar_wait(barM, phM);
+            phM ^= 1u;
+            __syncwarp();
+            tc_fence_after();
+            // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
+            if ((warp & 3) < 2) {
+                const int q = r;                          // 0..63
+#pragma unroll 1
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int j0 = 64 * half + 32 * blk;
+                    if (j0 < fc) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_lane + TM_DC + (uint32_t)j0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            uint4 o;
+                            o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                            o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                            o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                            o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                            *reinterpret_cast<uint4*>(sDcB + (uint32_t)(j0 / 8 + qq) * 1024u + (uint32_t)(q >> 3) * 128u + (uint32_t)(q & 7) * 16u) = o;
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();                               // ---- sync B ----
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t u_addr = smem_u32(sU), d_addr = smem_u32(sDcB);
+                for (int ks = 0; ks < 4; ++ks)             // D1 += U . DcB
+                    umma_f16_ss(tmem_base + TM_D1, umma_desc(u_addr + (uint32_t)ks * 4096u, 2048u, 128u),
+                                umma_desc(d_addr + (uint32_t)ks * 256u, 128u, 1024u), idescU, 1u);
+                umma_commit(barM);
+            }
+        }
+        mbar_wait(barM, phM);
+        phM ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+        if (a.dbg == 4) break;
+        // ---- E1: relu(D1) -> bf16 -> A2 ----
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+            const int j0 = 64 * half + 32 * blk;
+            if (j0 < fc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_lane + TM_D1 + (uint32_t)j0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint4 o;
+                    o.x = pack_bf16_relu(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                    o.y = pack_bf16_relu(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                    o.z = pack_bf16_relu(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                    o.w = pack_bf16_relu(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                    *reinterpret_cast<uint4*>(sA2 + (uint32_t)(j0 / 8 + qq) * 2048u + row_off) = o;
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();                                   // ---- sync C ----
+        if (a.dbg == 5) break;
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA2), b_addr = smem_u32(sB2w);
+            for (int ks = 0; ks < fc / 16; ++ks)
+                umma_f16_ss(tmem_base + TM_D2, umma_desc(a_addr + (uint32_t)ks * 4096u, 2048u, 128u),
+                            umma_desc(b_addr + (uint32_t)ks * 512u, 256u, 128u), idesc2, ks > 0 ? 1u : 0u);
+            umma_commit(barM);
+        }
+        mbar_wait(barM, phM);
+        phM ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+        if (a.dbg == 6) break;
+        // ---- E2: x' = x + (D2 + b2) * fire ; coarse state of the next step ----
+        {
+            uint32_t v[8];
+            tmem_ld8(tmem_lane + TM_D2 + 8u * (uint32_t)half, v);
+            tmem_ld_wait();
+            const float fire = sFire[r];
+            const size_t off = ((size_t)b * C + 8 * half) * plane + (size_t)gy * W + gx;
+            const bool cst = NS == 2 && a.xc_out != nullptr && inimg && ((lane & 17) == 0);
+            const size_t coff = NS == 2 ? ((size_t)b * C + 8 * half) * (plane >> 2) + (size_t)(gy >> 1) * (W >> 1) + (gx >> 1) : 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float xn = fmaf(__uint_as_float(v[i]) + sB2[8 * half + i], fire, xres[i]);
+                if (8 * half + i < C) {     // CTA-uniform per (half, i)
+                    if (inimg) a.x_out[off + (size_t)i * plane] = xn;
+                    if (NS == 2 && a.xc_out != nullptr) {
+                        const float a01 = __shfl_xor_sync(0xffffffffu, xn, 1);
+                        const float a10 = __shfl_xor_sync(0xffffffffu, xn, 16);
+                        const float a11 = __shfl_xor_sync(0xffffffffu, xn, 17);
+                        if (cst) a.xc_out[coff + (size_t)i * (plane >> 2)] = 0.25f * (((xn + a01) + a10) + a11);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                   // ---- sync D: TMEM / A2 / sFire reuse ----
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- weight / constant operand packing ------------------------------------------------------------------
+// B1 [N = fc][K = K1] with the perception columns scaled by 1/n_scales (exact: power of two), B2, b2, and the
+// upsample matrix U [128 cells][64 coarse cells] (K-major A operand)
+__global__ void dynca_tc2_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __restrict__ w1, const float* __restrict__ b1,
+                                      const float* __restrict__ w2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ B1,
+                                      __nv_bfloat16* __restrict__ B2, float* __restrict__ b2p, __nv_bfloat16* __restrict__ U) {
+    const int n1 = bg.K1 * g.fc, n2 = g.fc * 16, n3 = g.ns == 2 ? 128 * 64 : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + 16 + n3; i += gridDim.x * blockDim.x) {
+        if (i < n1) {
+            const int kp = i / g.fc, j = i % g.fc;
+            const int kc = kp >> 3, s = kp & 7;
+            float v = 0.0f;
+            if (kc < bg.npairs) {
+                const int c = 2 * kc + (s >> 2), f = s & 3;
+                if (c < g.C) v = __bfloat162float(__float2bfloat16_rn(w1[j * g.P + f * g.C + c])) * g.s0;
+            } else if (kc == bg.npairs) {
+                const int src = dynca_cond_slot_src(g.cc, s);
+                if (src >= 0) v = w1[j * g.P + 4 * g.C + src];
+                else if (src == -2) v = __bfloat162float(__float2bfloat16_rn(b1[j]));
+                else if (src == -3) v = b1[j] - __bfloat162float(__float2bfloat16_rn(b1[j]));
+            }
+            B1[(size_t)kc * (g.fc / 8) * 64 + (size_t)(j >> 3) * 64 + (j & 7) * 8 + s] = __float2bfloat16_rn(v);
+        } else if (i < n1 + n2) {
+            const int e = i - n1, j = e / 16, c = e % 16;
+            const float v = c < g.C ? w2[c * g.fc + j] : 0.0f;
+            B2[(size_t)(j >> 3) * 128 + (size_t)(c >> 3) * 64 + (c & 7) * 8 + (j & 7)] = __float2bfloat16_rn(v);
+        } else if (i < n1 + n2 + 16) {
+            const int c = i - n1 - n2;
+            b2p[c] = c < g.C ? b2[c] : 0.0f;
+        } else {
+            const int e = i - n1 - n2 - 16, rr = e / 64, q = e % 64;
+            const int py = rr >> 4, px = rr & 15, qy = q / T2_QW, qx = q % T2_QW;
+            float wy = 0.0f, wx = 0.0f;
+            if (q < T2_QH * T2_QW) {
+                const int ly = (py >> 1) + 1, lx = (px >> 1) + 1;
+                if (py & 1) wy = qy == ly ? 0.75f : (qy == ly + 1 ? 0.25f : 0.0f);
+                else wy = qy == ly ? 0.75f : (qy == ly - 1 ? 0.25f : 0.0f);
+                if (px & 1) wx = qx == lx ? 0.75f : (qx == lx + 1 ? 0.25f : 0.0f);
+                else wx = qx == lx ? 0.75f : (qx == lx - 1 ? 0.25f : 0.0f);
+            }
+            U[(size_t)(q >> 3) * 1024 + (size_t)(rr >> 3) * 64 + (rr & 7) * 8 + (q & 7)] = __float2bfloat16_rn(wy * wx);
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+typedef CUresult (*T2EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static T2EncodeFn t2_encode_fn() {
+    static T2EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (T2EncodeFn)p;
+    }
+    return fn;
+}
+// 5-D map over [slots][B][C][Hh][Ww] fp32 with box [1][1][C][bh][bw]
+static int t2_make_map(CUtensorMap* tm, const float* base, int slots, size_t slot_floats, int B, int C, int Hh, int Ww, int bh, int bw) {
+    T2EncodeFn fn = t2_encode_fn();
+    if (!fn) { nca_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NCA_ERR_CUDA; }
+    cuuint64_t dims[5] = {(cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)C, (cuuint64_t)B, (cuuint64_t)slots};
+    cuuint64_t strides[4] = {(cuuint64_t)Ww * 4, (cuuint64_t)Hh * Ww * 4, (cuuint64_t)C * Hh * Ww * 4, (cuuint64_t)slot_floats * 4};
+    cuuint32_t box[5] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)C, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { nca_set_error("cuTensorMapEncodeTiled failed with %d", (int)rc); return NCA_ERR_CUDA; }
+    return NCA_OK;
+}
+
+static int t2_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+bool dynca_tc2_supported(const DyncaGeom& g) {
+    Bf16Geom bg;
+    if (g.fc % 32 != 0 || g.fc < 32 || g.fc > 128 || g.cc + 2 > 8 || g.C > 16) return false;
+    if ((g.W & 3) != 0 || (g.ns == 2 && (g.W & 7) != 0)) return false;      // TMA strides: 16-byte multiples
+    if ((long long)g.H * g.W >= (1ll << 30)) return false;
+    if (dynca_bf16_geom(g, &bg)) return false;
+    return bg.K1 <= 80 && t2_smem(g, bg).total <= 227u * 1024u;
+}
+
+size_t dynca_tc2_weight_bytes(const DyncaGeom& g) {
+    Bf16Geom bg;
+    if (dynca_bf16_geom(g, &bg)) return 0;
+    return nca_align_up((size_t)bg.b1_bytes + bg.b2_bytes + 64 + (g.ns == 2 ? 16384 : 0), 256);
+}
+
+int dynca_tc2_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s) {
+    Bf16Geom bg;
+    int rc = dynca_bf16_geom(g, &bg);
+    if (rc) return rc;
+    __nv_bfloat16* B1 = (__nv_bfloat16*)ws;
+    __nv_bfloat16* B2 = (__nv_bfloat16*)((uint8_t*)ws + bg.b1_bytes);
+    float* b2p = (float*)((uint8_t*)ws + bg.b1_bytes + bg.b2_bytes);
+    __nv_bfloat16* U = (__nv_bfloat16*)((uint8_t*)ws + bg.b1_bytes + bg.b2_bytes + 64);
+    dynca_tc2_prep_kernel<<<32, 256, 0, s>>>(g, bg, w->w1, w->b1, w->w2, w->b2, B1, B2, b2p, U);
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+// tensor maps of one rollout: states [slots][B][C][H][W] and (two scales) coarse states [cslots][B][C][H/2][W/2]
+int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, const float* coarse, int cslots, size_t cslot_floats, DyncaTc2Maps* m) {
+    static_assert(sizeof(CUtensorMap) == sizeof(m->x), "tensor map size");
+    int rc = t2_make_map((CUtensorMap*)m->x, states, slots, (size_t)g.B * g.C * g.H * g.W, g.B, g.C, g.H, g.W, T2_XR, T2_XS);
+    if (rc) return rc;
+    if (g.ns == 2) rc = t2_make_map((CUtensorMap*)m->xc, coarse, cslots, cslot_floats, g.B, g.C, g.H / 2, g.W / 2, T2_CR, T2_CS);
+    else memcpy(m->xc, m->x, sizeof(m->x));
+    return rc;
+}
+
+int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Maps* m, int slot_in, const float* x_in, float* x_out,
+                           int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s) {
+    T2FwdArgs a;
+    int rc = dynca_bf16_geom(g, &a.bg);
+    if (rc) return rc;
+    a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.x_out = x_out; a.xc_out = xc_out;
+    a.slot_in = slot_in; a.cslot_in = cslot_in;
+    a.B1 = (const __nv_bfloat16*)ws;
+    a.B2 = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes);
+    a.b2p = (const float*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes);
+    a.U = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes + 64);
+    a.fm = fm;
+    { const char* e = getenv("NCA_T2_DBG"); a.dbg = e ? atoi(e) : 0; }
+    a.tiles_x = (g.W + T2_TW - 1) / T2_TW; a.tiles_y = (g.H + T2_TH - 1) / T2_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
+    const size_t smem = t2_smem(g, a.bg).total;
+    const uint32_t tcols = g.ns == 2 ? 256u : 128u;
+    int occ = (int)((227 * 1024) / (smem + 1024));
+    if (occ > (int)(512u / tcols)) occ = (int)(512u / tcols);
+    if (occ < 1) occ = 1;
+    int grid = t2_num_sms() * occ;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    const CUtensorMap* tx = (const CUtensorMap*)m->x;
+    const CUtensorMap* txc = (const CUtensorMap*)m->xc;
+    if (g.ns == 2) {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_fwd_tc2_kernel<2><<<grid, T2_THREADS, smem, s>>>(*tx, *txc, a);
+    } else {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_fwd_tc2_kernel<1><<<grid, T2_THREADS, smem, s>>>(*tx, *txc, a);
+    }
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}

@@ -53,17 +53,32 @@ static int check_common(const NcaDyncaDesc* d, DyncaGeom* g, const float* cond, 
     return check_device();
 }
 
+// kernel variant of a description: 0 fp32, 1 tcgen05 (4x32 tiles, cp.async), 2 tcgen05 (8x16 tiles, TMA)
+static int dynca_variant(const NcaDyncaDesc* d, const DyncaGeom& g, int backward) {
+    if (d->precision != NCA_PREC_BF16) return 0;
+    if (backward) return dynca_bf16_bwd_supported(g) ? 1 : 0;
+    return dynca_tc2_supported(g) ? 2 : 1;
+}
+int nca_dynca_kernel_variant(const NcaDyncaDesc* d, int32_t backward) {
+    DyncaGeom g;
+    if (dynca_make_geom(d, &g)) return -1;
+    if (d->precision != NCA_PREC_FP32 && d->precision != NCA_PREC_BF16) return -1;
+    return dynca_variant(d, g, backward);
+}
+
 size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward) {
     DyncaGeom g;
     if (dynca_make_geom(d, &g)) return 0;
-    // layout: [fp32 padded weights | (backward) grad accumulators, 2 state-gradient buffers | (bf16) operand images]
+    // layout: [fp32 padded weights | (backward) grad accumulators, 2 state-gradient buffers | (bf16) operand images |
+    //          2 coarse-state slots]
     size_t n = dynca_f32_weight_floats(g);
     if (backward) n += dynca_f32_grad_floats(g) + 2 * nca_align_up((size_t)g.B * g.C * g.H * g.W, 64);
     size_t bytes = n * sizeof(float);
     if (d->precision == NCA_PREC_BF16) {
         size_t b = backward ? dynca_bf16_bwd_weight_bytes(g) : dynca_bf16_weight_bytes(g);
         if (b == 0) return 0;
-        bytes += b + dynca_bf16_coarse_floats(g) * sizeof(float);   // + coarse (2x2-mean) state of the current step
+        const size_t b2 = dynca_tc2_weight_bytes(g);
+        bytes += (b > b2 ? b : b2) + 2 * dynca_bf16_coarse_floats(g) * sizeof(float);
     }
     return bytes;
 }
@@ -95,41 +110,65 @@ int nca_philox_mask(int32_t B, int32_t H, int32_t W, float rate, int32_t enc, ui
 }
 
 int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
-                      uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, float* coarse_hist,
+                      void* workspace, size_t workspace_bytes, void* stream) {
     DyncaGeom g;
     int rc = check_common(d, &g, cond, masks);
     if (rc) return rc;
     NCA_CHECK_ARG(w && w->w1 && w->b1 && w->w2 && w->b2, "weights are NULL");
     NCA_CHECK_ARG(states != nullptr && T >= 0, "states is NULL or T < 0");
-    NCA_CHECK_ARG(NCA_ALIGNED16(states) && NCA_ALIGNED16(workspace), "states / workspace must be 16-byte aligned");
+    NCA_CHECK_ARG(NCA_ALIGNED16(states) && NCA_ALIGNED16(workspace) && NCA_ALIGNED16(coarse_hist), "states / coarse_hist / workspace must be 16-byte aligned");
     if (workspace == nullptr || workspace_bytes < nca_dynca_workspace_bytes(d, 0)) {
         nca_set_error("workspace too small: %zu < %zu", workspace_bytes, nca_dynca_workspace_bytes(d, 0));
         return NCA_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    const int variant = dynca_variant(d, g, 0);
     float* wsW = (float*)workspace;
     void* wsB = (uint8_t*)workspace + dynca_f32_weight_floats(g) * sizeof(float);
-    const bool bf16 = d->precision == NCA_PREC_BF16;
-    float* wsXc = bf16 ? (float*)((uint8_t*)wsB + dynca_bf16_weight_bytes(g)) : nullptr;
-    rc = bf16 ? dynca_bf16_prep_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s);
+    const size_t imgb = dynca_bf16_weight_bytes(g) > dynca_tc2_weight_bytes(g) ? dynca_bf16_weight_bytes(g) : dynca_tc2_weight_bytes(g);
+    float* wsXc = variant ? (float*)((uint8_t*)wsB + imgb) : nullptr;      // 2 coarse slots
+    const size_t n = (size_t)g.B * g.C * g.H * g.W, nc = dynca_bf16_coarse_floats(g);
+    if (T == 0) return NCA_OK;
+    rc = variant == 2 ? dynca_tc2_prep_weights(g, w, wsB, s) : (variant == 1 ? dynca_bf16_prep_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s));
     if (rc) return rc;
-    const size_t n = (size_t)g.B * g.C * g.H * g.W;
+    // coarse states (two perception scales on the tensor-core paths): a history when the caller keeps one, else ping-pong
+    const bool chist = keep_history && coarse_hist != nullptr && g.ns == 2;
+    float* cbase = chist ? coarse_hist : wsXc;
+    const size_t cstride = chist ? (size_t)g.B * g.C * (g.H / 2) * (g.W / 2) : nc;
+    DyncaTc2Maps maps;
+    if (variant == 2) {
+        rc = dynca_tc2_make_maps(g, states, keep_history ? T + 1 : 2, cbase, chist ? T + 1 : 2, cstride, &maps);
+        if (rc) return rc;
+    }
     for (int t = 0; t < T; ++t) {
         FireMask fm = make_mask(d, g, masks, seed, t);
         fm.t = (uint32_t)(t0 + t);
-        const float* xin = keep_history ? states + (size_t)t * n : states + (size_t)(t & 1) * n;
-        float* xout = keep_history ? states + (size_t)(t + 1) * n : states + (size_t)((t + 1) & 1) * n;
-        rc = bf16 ? dynca_bf16_forward_step(g, wsB, wsXc, xin, xout, cond, fm, s) : dynca_f32_forward_step(g, wsW, xin, xout, cond, fm, s);
+        const int si = keep_history ? t : (t & 1), so = keep_history ? t + 1 : ((t + 1) & 1);
+        const int ci = chist ? t : (t & 1), co = chist ? t + 1 : ((t + 1) & 1);
+        const float* xin = states + (size_t)si * n;
+        float* xout = states + (size_t)so * n;
+        if (variant == 2) {
+            if (g.ns == 2 && t == 0) { rc = dynca_bf16_coarsen(g, xin, cbase + (size_t)ci * cstride, s); if (rc) return rc; }
+            const bool need_next = g.ns == 2 && (t + 1 < T || chist);
+            rc = dynca_tc2_forward_step(g, wsB, &maps, si, xin, xout, ci, g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr,
+                                        need_next ? cbase + (size_t)co * cstride : nullptr, cond, fm, s);
+        } else if (variant == 1) {
+            float* xc = g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr;
+            rc = dynca_bf16_forward_step(g, wsB, xc, xin, xout, cond, fm, s);
+            if (!rc && chist && t + 1 == T) rc = dynca_bf16_coarsen(g, xout, cbase + (size_t)co * cstride, s);
+        } else {
+            rc = dynca_f32_forward_step(g, wsW, xin, xout, cond, fm, s);
+        }
         if (rc) return rc;
     }
     return NCA_OK;
 }
 
 int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
-                       uint64_t seed, int32_t t0, int32_t T, const float* states, const float* g_final,
-                       const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps, int32_t tap_c,
-                       float tap_scale, float* gx0, const NcaDyncaWeightGrads* gw, void* workspace,
+                       uint64_t seed, int32_t t0, int32_t T, const float* states, const float* coarse_hist,
+                       const float* g_final, const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps,
+                       int32_t tap_c, float tap_scale, float* gx0, const NcaDyncaWeightGrads* gw, void* workspace,
                        size_t workspace_bytes, void* stream) {
     DyncaGeom g;
     int rc = check_common(d, &g, cond, masks);
@@ -147,7 +186,7 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         return NCA_ERR_WORKSPACE;
     }
     // NCA_PREC_BF16: tcgen05 BPTT kernel when the shape is supported (fc % 32 == 0, fc <= 128), else the fp32 kernel
-    const bool bf16 = d->precision == NCA_PREC_BF16 && dynca_bf16_bwd_supported(g);
+    const bool bf16 = dynca_variant(d, g, 1) != 0;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)g.B * g.C * g.H * g.W, nb = n * sizeof(float);
     float* wsW = (float*)workspace;
@@ -172,7 +211,8 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         NCA_CUDA_OK(cudaMemsetAsync(gout, 0, nb, s));
         const float* tap = nullptr;   // gradient injected at states[t+1]
         if (ti >= 0 && tap_steps[ti] == t + 1) tap = g_taps[ti--];
-        rc = bf16 ? dynca_bf16_backward_step(g, wsB, wsXc, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s)
+        const float* xc_t = (coarse_hist && g.ns == 2) ? coarse_hist + (size_t)t * g.B * g.C * (g.H / 2) * (g.W / 2) : nullptr;
+        rc = bf16 ? dynca_bf16_backward_step(g, wsB, wsXc, xc_t, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s)
                   : dynca_f32_backward_step(g, wsW, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s);
         if (rc) return rc;
         gnext = gout;

@@ -63,6 +63,12 @@ def _weights_struct(w1, b1, w2, b2):
     return _lib.DyncaWeights(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr())
 
 
+def dynca_kernel_variant(cfg, B, H, W, backward=False):
+    """Which step kernel the library dispatches this shape to (0 fp32, 1 tcgen05 4x32 tiles, 2 tcgen05 8x16 + TMA)."""
+    d = cfg.desc(B, H, W, 0.5, False)
+    return int(load_library().nca_dynca_kernel_variant(C.byref(d), int(backward)))
+
+
 def dynca_perceive(cfg, x, cond=None):
     """DyNCA.perceive_multiscale (dynca.py:98-111) -> [B, 4C+cc, H, W]."""
     _need_cuda(x, cond)
@@ -106,12 +112,17 @@ def _dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, masks, seed, T, rate, keep
     n_slots = T + 1 if keep_history else 2
     states = torch.empty(n_slots, B, Cc, H, W, device=x0.device, dtype=torch.float32)
     states[0].copy_(x0)
+    coarse = None
+    if keep_history and cfg.ns == 2:     # coarse (2x2-mean) state history, reused by the BPTT
+        coarse = torch.empty(n_slots, B, Cc, H // 2, W // 2, device=x0.device, dtype=torch.float32)
     with torch.cuda.device(x0.device):
         nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
         ws = torch.empty(max(nbytes, 16), device=x0.device, dtype=torch.uint8)
         wst = _weights_struct(w1, b1, w2, b2)
         check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(seed), 0, T,
-                                    int(keep_history), _ptr(states), _ptr(ws), nbytes, _stream()))
+                                    int(keep_history), _ptr(states), _ptr(coarse), _ptr(ws), nbytes, _stream()))
+    if keep_history:
+        return states, coarse
     return states
 
 
@@ -129,7 +140,8 @@ class _DyncaRollout(torch.autograd.Function):
     def forward(ctx, x0, w1, b1, w2, b2, cond, masks, cfg, T, rate, seed, handle):
         x0c, w1c, b1c, w2c, b2c = _c(x0), _c(w1), _c(b1), _c(w2), _c(b2)
         cond, masks = _c(cond), _c(masks)
-        hist = _dynca_forward_raw(cfg, x0c, w1c, b1c, w2c, b2c, cond, masks, seed, T, rate, True)
+        hist, coarse = _dynca_forward_raw(cfg, x0c, w1c, b1c, w2c, b2c, cond, masks, seed, T, rate, True)
+        ctx.coarse = coarse
         ctx.cfg, ctx.T, ctx.rate, ctx.seed, ctx.handle = cfg, T, rate, seed, handle
         ctx.w_shapes = (w1.shape, b1.shape, w2.shape, b2.shape)
         ctx.save_for_backward(w1c, b1c, w2c, b2c, cond, masks)
@@ -160,7 +172,7 @@ class _DyncaRollout(torch.autograd.Function):
             wst = _weights_struct(w1, b1, w2, b2)
             gst = _weights_struct(gw1, gb1, gw2, gb2)
             check(lib.nca_dynca_backward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(ctx.seed), 0, T,
-                                         _ptr(hist), _ptr(g_final), tap_ptrs, tap_steps, n_taps, max(tap_c, 1), 2.0,
+                                         _ptr(hist), _ptr(ctx.coarse), _ptr(g_final), tap_ptrs, tap_steps, n_taps, max(tap_c, 1), 2.0,
                                          _ptr(gx0), C.byref(gst), _ptr(ws), nbytes, _stream()))
         ctx.handle.tap_grads = {}
         s1, sb1, s2, sb2 = ctx.w_shapes
@@ -228,6 +240,7 @@ def dynca_rollout(cfg, x0, w1, b1, w2, b2, T, rate=0.5, cond=None, masks=None, s
     states = _dynca_forward_raw(cfg, _c(x0), _c(w1), _c(b1), _c(w2), _c(b2), _c(cond), _c(masks), seed, T, rate,
                                 return_taps)
     if return_taps:
+        states = states[0]
         handle.hist = states
         return states[T], RgbTaps(handle, None, T)
     return states[T & 1], None
