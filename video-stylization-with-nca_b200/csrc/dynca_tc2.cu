@@ -143,29 +143,35 @@ __device__ __forceinline__ void t2_percept3c(const float* __restrict__ ch, int r
 }
 
 // patch the staged tiles of a border tile: every staged position outside the image takes the value the padding mode
-// prescribes (TMA filled it with zero, which is already right for constant padding)
+// prescribes (TMA filled it with zero, which is already right for constant padding).  One staged position per thread
+// (fine: threads 0..179, coarse: threads 160..255), channel loop inside, so the index math runs once per tile.
 template <int NS>
 __device__ __forceinline__ void t2_patch_border(const DyncaGeom& g, const float* __restrict__ x, const float* __restrict__ xc, int b,
                                                 int y0, int x0, float* __restrict__ sX, float* __restrict__ sXc) {
-    const int C = g.C, H = g.H, W = g.W;
+    const int C = g.C, H = g.H, W = g.W, tid = threadIdx.x;
     if (g.pad == NCA_PAD_CONSTANT) return;
-    const size_t plane = (size_t)H * W;
-    for (int i = threadIdx.x; i < C * T2_XR * 18; i += T2_THREADS) {
-        const int q = i % 18, r = (i / 18) % T2_XR, c = i / (18 * T2_XR);
+    if (tid < T2_XR * 18) {
+        const int q = tid % 18, r = tid / 18;
         const int yy = y0 - 1 + r, xx = x0 - 1 + q;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) continue;
-        const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
-        sX[(c * T2_XR + r) * T2_XS + T2_XO + q] = __ldg(x + ((size_t)b * C + c) * plane + (size_t)iy * W + ix);
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
+            const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
+            const size_t plane = (size_t)H * W;
+            const float* src = x + (size_t)b * C * plane + (size_t)iy * W + ix;
+            float* dst = sX + r * T2_XS + T2_XO + q;
+            for (int c = 0; c < C; ++c) dst[c * T2_XR * T2_XS] = __ldg(src + c * plane);
+        }
     }
-    if (NS == 2) {
+    if (NS == 2 && tid >= T2_THREADS - T2_CR * 12) {
+        const int i = tid - (T2_THREADS - T2_CR * 12);
+        const int q = i % 12, r = i / 12;
         const int Hc = H >> 1, Wc = W >> 1;
-        const size_t cplane = (size_t)Hc * Wc;
-        for (int i = threadIdx.x; i < C * T2_CR * 12; i += T2_THREADS) {
-            const int q = i % 12, r = (i / 12) % T2_CR, c = i / (12 * T2_CR);
-            const int yy = (y0 >> 1) - 2 + r, xx = (x0 >> 1) - 2 + q;
-            if (yy >= 0 && yy < Hc && xx >= 0 && xx < Wc) continue;
+        const int yy = (y0 >> 1) - 2 + r, xx = (x0 >> 1) - 2 + q;
+        if (yy < 0 || yy >= Hc || xx < 0 || xx >= Wc) {
             const int iy = nca_padmap(yy, Hc, g.pad), ix = nca_padmap(xx, Wc, g.pad);
-            sXc[(c * T2_CR + r) * T2_CS + T2_CO + q] = __ldg(xc + ((size_t)b * C + c) * cplane + (size_t)iy * Wc + ix);
+            const size_t cplane = (size_t)Hc * Wc;
+            const float* src = xc + (size_t)b * C * cplane + (size_t)iy * Wc + ix;
+            float* dst = sXc + r * T2_CS + T2_CO + q;
+            for (int c = 0; c < C; ++c) dst[c * T2_CR * T2_CS] = __ldg(src + c * cplane);
         }
     }
 }
@@ -182,6 +188,7 @@ __global__ void __launch_bounds__(T2_THREADS) dynca_fwd_tc2_kernel(const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
     float* sB2 = reinterpret_cast<float*>(smem + 64);           // 16 floats
     float* sFire = reinterpret_cast<float*>(smem + 128);        // 128 floats
+    uint32_t* sCpe = reinterpret_cast<uint32_t*>(smem + 640);   // 8 rows + 16 columns: bf16 hi | lo << 16 of the CPE value
     uint8_t* sB1 = smem + L.b1;
     uint8_t* sB2w = smem + L.b2w;
     uint8_t* sU = smem + L.u;
@@ -237,7 +244,20 @@ __global__ void __launch_bounds__(T2_THREADS) dynca_fwd_tc2_kernel(const __grid_
         tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
         if (NS == 2) tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                 \
     } while (0)
+    // CPE values of the 8 rows / 16 columns of a tile as bf16 hi | lo << 16 (warp 7, lanes 0..23); written one tile ahead
+#define T2_CPE_TABLE(tile_)                                                                                              \
+    do {                                                                                                                 \
+        if (g.cond_kind == NCA_COND_CPE && warp == 7 && lane < T2_TH + T2_TW) {                                          \
+            const int tt_ = (tile_);                                                                                     \
+            const int ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW;                    \
+            const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow); \
+            const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_)); \
+            sCpe[lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16);              \
+        }                                                                                                                \
+    } while (0)
     const int n_tiles = a.dbg == 1 ? 0 : a.n_tiles;
+    if ((int)blockIdx.x < n_tiles) T2_CPE_TABLE(blockIdx.x);
+    __syncthreads();
     if (tid == 0 && (int)blockIdx.x < n_tiles) T2_ISSUE_TMA(blockIdx.x);
 
     int iter = 0;
@@ -295,7 +315,14 @@ __global__ void __launch_bounds__(T2_THREADS) dynca_fwd_tc2_kernel(const __grid_
             xres[i] = c < C ? sX[(c * T2_XR + py + 1) * T2_XS + T2_XO + px + 1] : 0.0f;
         }
         if (half == 0) {
-            *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
+            uint4 cv;
+            if (g.cond_kind == NCA_COND_CPE) {           // [cpe_y hi, cpe_x hi, 1, 1, cpe_y lo, cpe_x lo, 0, 0]
+                const uint32_t ry = sCpe[py], cx = sCpe[T2_TH + px];
+                cv = make_uint4((ry & 0xffffu) | (cx << 16), 0x3F803F80u, (ry >> 16) | (cx & 0xffff0000u), 0u);
+            } else {
+                cv = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
+            }
+            *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = cv;
         } else {
             for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
                 *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
@@ -450,23 +477,35 @@ __global__ void __launch_bounds__(T2_THREADS) dynca_fwd_tc2_kernel(const __grid_
             tmem_ld8(tmem_lane + TM_D2 + 8u * (uint32_t)half, v);
             tmem_ld_wait();
             const float fire = sFire[r];
-            const size_t off = ((size_t)b * C + 8 * half) * plane + (size_t)gy * W + gx;
-            const bool cst = NS == 2 && a.xc_out != nullptr && inimg && ((lane & 17) == 0);
-            const size_t coff = NS == 2 ? ((size_t)b * C + 8 * half) * (plane >> 2) + (size_t)(gy >> 1) * (W >> 1) + (gx >> 1) : 0;
+            float xn[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xn = fmaf(__uint_as_float(v[i]) + sB2[8 * half + i], fire, xres[i]);
-                if (8 * half + i < C) {     // CTA-uniform per (half, i)
-                    if (inimg) a.x_out[off + (size_t)i * plane] = xn;
-                    if (NS == 2 && a.xc_out != nullptr) {
-                        const float a01 = __shfl_xor_sync(0xffffffffu, xn, 1);
-                        const float a10 = __shfl_xor_sync(0xffffffffu, xn, 16);
-                        const float a11 = __shfl_xor_sync(0xffffffffu, xn, 17);
-                        if (cst) a.xc_out[coff + (size_t)i * (plane >> 2)] = 0.25f * (((xn + a01) + a10) + a11);
-                    }
+            for (int i = 0; i < 8; ++i) xn[i] = fmaf(__uint_as_float(v[i]) + sB2[8 * half + i], fire, xres[i]);
+            const int nch = min(8, C - 8 * half);                  // warp-uniform
+            if (inimg) {
+                float* xo = a.x_out + ((size_t)b * C + 8 * half) * plane + (size_t)gy * W + gx;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < nch) xo[(size_t)i * plane] = xn[i];
+            }
+            if (NS == 2 && a.xc_out != nullptr) {
+                float m4[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a01 = __shfl_xor_sync(0xffffffffu, xn[i], 1);
+                    const float a10 = __shfl_xor_sync(0xffffffffu, xn[i], 16);
+                    const float a11 = __shfl_xor_sync(0xffffffffu, xn[i], 17);
+                    m4[i] = 0.25f * (((xn[i] + a01) + a10) + a11);
+                }
+                if (inimg && (lane & 17) == 0) {
+                    const size_t cpl = plane >> 2;
+                    float* co = a.xc_out + ((size_t)b * C + 8 * half) * cpl + (size_t)(gy >> 1) * (W >> 1) + (gx >> 1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < nch) co[(size_t)i * cpl] = m4[i];
                 }
             }
         }
+        if (tile + (int)gridDim.x < n_tiles) T2_CPE_TABLE(tile + gridDim.x);
         tc_fence_before();
         __syncthreads();                                   // ---- sync D: TMEM / A2 / sFire reuse ----
     }
