@@ -33,7 +33,7 @@
 #define T2_QH 6
 #define T2_QW 10
 #define T2_THREADS 256
-#define T2_HDR 1024u
+#define T2_HDR 1536u
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -70,6 +70,7 @@ struct T2FwdArgs {
     FireMask fm;
     int tiles_x, tiles_y, n_tiles;
     int dbg;
+    long long* tdbg;   // optional phase timestamps of CTA 0 (debug)
 };
 
 struct T2Smem {
@@ -142,6 +143,17 @@ __device__ __forceinline__ void t2_percept3c(const float* __restrict__ ch, int r
     }
 }
 
+// padding index map for coordinates at most one period outside the image (no generic modulo); ragged tiles reach
+// further out only for cells nobody reads, so clamp
+__device__ __forceinline__ int t2_padmap(int r, int n, int mode) {
+    if (r >= 0 && r < n) return r;
+    int v;
+    if (mode == NCA_PAD_CIRCULAR) v = r < 0 ? r + n : r - n;
+    else if (mode == NCA_PAD_REPLICATE) v = r;
+    else v = r < 0 ? -r : 2 * (n - 1) - r;           // reflect
+    return min(max(v, 0), n - 1);
+}
+
 // patch the staged tiles of a border tile: every staged position outside the image takes the value the padding mode
 // prescribes (TMA filled it with zero, which is already right for constant padding).  One staged position per thread
 // (fine: threads 0..179, coarse: threads 160..255), channel loop inside, so the index math runs once per tile.
@@ -150,15 +162,27 @@ __device__ __forceinline__ void t2_patch_border(const DyncaGeom& g, const float*
                                                 int y0, int x0, float* __restrict__ sX, float* __restrict__ sXc) {
     const int C = g.C, H = g.H, W = g.W, tid = threadIdx.x;
     if (g.pad == NCA_PAD_CONSTANT) return;
+    const bool wrap = g.pad == NCA_PAD_CIRCULAR;   // replicate / reflect sources lie inside the staged tile: smem -> smem
     if (tid < T2_XR * 18) {
         const int q = tid % 18, r = tid / 18;
         const int yy = y0 - 1 + r, xx = x0 - 1 + q;
         if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
-            const int iy = nca_padmap(yy, H, g.pad), ix = nca_padmap(xx, W, g.pad);
-            const size_t plane = (size_t)H * W;
-            const float* src = x + (size_t)b * C * plane + (size_t)iy * W + ix;
+            const int iy = t2_padmap(yy, H, g.pad), ix = t2_padmap(xx, W, g.pad);
             float* dst = sX + r * T2_XS + T2_XO + q;
-            for (int c = 0; c < C; ++c) dst[c * T2_XR * T2_XS] = __ldg(src + c * plane);
+            if (wrap) {
+                const size_t plane = (size_t)H * W;
+                const float* src = x + (size_t)b * C * plane + (size_t)iy * W + ix;
+                float v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(src + c * plane) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) if (c < C) dst[c * T2_XR * T2_XS] = v[c];
+            } else {
+                const int sr = min(max(iy - (y0 - 1), 0), T2_XR - 1), sq = min(max(ix - (x0 - 1), 0), 17);
+                const float* src = sX + sr * T2_XS + T2_XO + sq;
+#pragma unroll 8
+                for (int c = 0; c < C; ++c) dst[c * T2_XR * T2_XS] = src[c * T2_XR * T2_XS];
+            }
         }
     }
     if (NS == 2 && tid >= T2_THREADS - T2_CR * 12) {
@@ -167,28 +191,62 @@ __device__ __forceinline__ void t2_patch_border(const DyncaGeom& g, const float*
         const int Hc = H >> 1, Wc = W >> 1;
         const int yy = (y0 >> 1) - 2 + r, xx = (x0 >> 1) - 2 + q;
         if (yy < 0 || yy >= Hc || xx < 0 || xx >= Wc) {
-            const int iy = nca_padmap(yy, Hc, g.pad), ix = nca_padmap(xx, Wc, g.pad);
-            const size_t cplane = (size_t)Hc * Wc;
-            const float* src = xc + (size_t)b * C * cplane + (size_t)iy * Wc + ix;
+            const int iy = t2_padmap(yy, Hc, g.pad), ix = t2_padmap(xx, Wc, g.pad);
             float* dst = sXc + r * T2_CS + T2_CO + q;
-            for (int c = 0; c < C; ++c) dst[c * T2_CR * T2_CS] = __ldg(src + c * cplane);
+            if (wrap) {
+                const size_t cplane = (size_t)Hc * Wc;
+                const float* src = xc + (size_t)b * C * cplane + (size_t)iy * Wc + ix;
+                float v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(src + c * cplane) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) if (c < C) dst[c * T2_CR * T2_CS] = v[c];
+            } else {
+                const int sr = min(max(iy - ((y0 >> 1) - 2), 0), T2_CR - 1), sq = min(max(ix - ((x0 >> 1) - 2), 0), 11);
+                const float* src = sXc + sr * T2_CS + T2_CO + sq;
+#pragma unroll 8
+                for (int c = 0; c < C; ++c) dst[c * T2_CR * T2_CS] = src[c * T2_CR * T2_CS];
+            }
         }
     }
 }
 
+// ---- synchronisation helpers: compute threads -> MMA warp hand-offs are mbarriers, not CTA barriers ----
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 compute warps
+// D[tmem] (+)= A . B with precomputed 64-bit descriptors
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+
+#define T2_NTHREADS 288     // 8 compute warps + 1 MMA / TMA warp
+
 template <int NS>
-__global__ void __launch_bounds__(T2_THREADS) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
-                                                                    const __grid_constant__ CUtensorMap tm_xc, const T2FwdArgs a) {
+__global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                     const __grid_constant__ CUtensorMap tm_xc, const T2FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
     const T2Smem L = t2_smem(g, bg);
-    uint64_t* barM = reinterpret_cast<uint64_t*>(smem);         // MMA completion
-    uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);     // TMA completion
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+    uint64_t* barM = reinterpret_cast<uint64_t*>(smem);         // MMA batch complete (tcgen05.commit)
+    uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);     // TMA complete
+    uint64_t* barA = reinterpret_cast<uint64_t*>(smem + 16);    // 256 arrivals: A1 / Zc written, stage consumed
+    uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 24);    // 256 arrivals: DcB written
+    uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 32);    // 256 arrivals: A2 written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 40);
     float* sB2 = reinterpret_cast<float*>(smem + 64);           // 16 floats
-    float* sFire = reinterpret_cast<float*>(smem + 128);        // 128 floats
-    uint32_t* sCpe = reinterpret_cast<uint32_t*>(smem + 640);   // 8 rows + 16 columns: bf16 hi | lo << 16 of the CPE value
+    float* sFire2 = reinterpret_cast<float*>(smem + 128);       // 2 x 128 floats (double buffered over tiles)
+    uint32_t* sCpe2 = reinterpret_cast<uint32_t*>(smem + 128 + 1024);   // 2 x 24: bf16 hi | lo << 16 of the CPE rows / columns
     uint8_t* sB1 = smem + L.b1;
     uint8_t* sB2w = smem + L.b2w;
     uint8_t* sU = smem + L.u;
@@ -199,319 +257,359 @@ __global__ void __launch_bounds__(T2_THREADS) dynca_fwd_tc2_kernel(const __grid_
     uint8_t* sDcB = smem + L.dcb;
     uint8_t* sA2 = smem + L.uni;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r = tid & 127, half = tid >> 7;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
     const size_t plane = (size_t)H * W;
     const uint32_t stage_bytes = (uint32_t)C * T2_XR * T2_XS * 4u + (NS == 2 ? (uint32_t)C * T2_CR * T2_CS * 4u : 0u);
     const uint32_t tmem_cols = NS == 2 ? 256u : 128u;
+    const int n_tiles = a.n_tiles, tiles_per_b = a.tiles_x * a.tiles_y;
 
     // ---- one-time setup ----
-    for (uint32_t i = tid; i < bg.b1_bytes / 16; i += T2_THREADS)
+    for (uint32_t i = tid; i < bg.b1_bytes / 16; i += T2_NTHREADS)
         reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
-    for (uint32_t i = tid; i < bg.b2_bytes / 16; i += T2_THREADS)
+    for (uint32_t i = tid; i < bg.b2_bytes / 16; i += T2_NTHREADS)
         reinterpret_cast<uint4*>(sB2w)[i] = __ldg(reinterpret_cast<const uint4*>(a.B2) + i);
     if (NS == 2)
-        for (uint32_t i = tid; i < 16384u / 16; i += T2_THREADS)
+        for (uint32_t i = tid; i < 16384u / 16; i += T2_NTHREADS)
             reinterpret_cast<uint4*>(sU)[i] = __ldg(reinterpret_cast<const uint4*>(a.U) + i);
     if (tid < 16) sB2[tid] = a.b2p[tid];
     if (tid == 0) {
         mbar_init(barM, 1);
         mbar_init(barT, 1);
+        mbar_init(barA, 256);
+        mbar_init(barB, 256);
+        mbar_init(barC, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = 0u;
-    const uint32_t idesc1 = umma_idesc_bf16(128, fc), idesc2 = umma_idesc_bf16(128, 16);
-    const uint32_t idescU = umma_idesc_bf16(128, fc) | (1u << 16);      // B operand MN-major
-    const uint32_t lbo_b1 = (uint32_t)(fc / 8) * 128u;
-    const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
-    uint32_t phM = 0, phT = 0;
-    const int py = r >> 4, px = r & 15;
 
-    const CUtensorMap* const ptm_x = &tm_x;
-    const CUtensorMap* const ptm_xc = &tm_xc;
+    if (warp == 8) {
+        // =========================== MMA / TMA warp ===========================
+        const uint32_t idesc1 = umma_idesc_bf16(128, fc), idesc2 = umma_idesc_bf16(128, 16);
+        const uint32_t idescU = umma_idesc_bf16(128, fc) | (1u << 16);      // B operand MN-major
+        const uint32_t lbo_b1 = (uint32_t)(fc / 8) * 128u;
+        // every operand lives at a fixed shared-memory address: descriptors are kernel constants, K steps are adds
+        const uint64_t dA1 = umma_desc(smem_u32(sA1), 2048u, 128u), dB1 = umma_desc(smem_u32(sB1), lbo_b1, 128u);
+        const uint64_t dZc = umma_desc(smem_u32(sZc), 1024u, 128u), dU = umma_desc(smem_u32(sU), 2048u, 128u);
+        const uint64_t dDcB = umma_desc(smem_u32(sDcB), 128u, 1024u);
+        const uint64_t dA2 = umma_desc(smem_u32(sA2), 2048u, 128u), dB2 = umma_desc(smem_u32(sB2w), 256u, 128u);
+        const uint64_t sB1k = (uint64_t)((2u * lbo_b1) >> 4);
+        const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, k2steps = fc / 16;
+        const CUtensorMap* const ptm_x = &tm_x;
+        const CUtensorMap* const ptm_xc = &tm_xc;
+        uint32_t phA = 0, phB = 0, phC = 0;
+        const bool leader = elect_one();
 #define T2_ISSUE_TMA(tile_)                                                                                              \
     do {                                                                                                                 \
         const int tt_ = (tile_);                                                                                         \
-        const int tb_ = tt_ / (a.tiles_x * a.tiles_y), ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
+        const int tb_ = tt_ / tiles_per_b, ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
         mbar_expect_tx(barT, stage_bytes);                                                                               \
         tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
         if (NS == 2) tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                 \
     } while (0)
-    // CPE values of the 8 rows / 16 columns of a tile as bf16 hi | lo << 16 (warp 7, lanes 0..23); written one tile ahead
-#define T2_CPE_TABLE(tile_)                                                                                              \
+        if (leader && (int)blockIdx.x < n_tiles) T2_ISSUE_TMA(blockIdx.x);
+#define T2_MSTAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && leader && miter < 8) a.tdbg[128 + miter * 8 + (k_)] = clock64(); } while (0)
+        int miter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++miter) {
+            T2_MSTAMP(0);
+            mbar_wait(barA, phA);
+            phA ^= 1u;
+            tc_fence_after();
+            T2_MSTAMP(1);
+            if (leader) {
+                if (NS == 2) {
+                    // Dc = Zc . W1h^T over the perception columns.  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of
+                    // the M = 128 instruction alias the next chunk (finite values) and produce rows of Dc nobody reads
+#pragma unroll 4
+                    for (int ks = 0; ks < kcsteps; ++ks)
+                        umma_ss(tmem_base + TM_DC, dZc + (uint64_t)(ks * (2048 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
+                    umma_commit(barM);
+                }
+#pragma unroll 5
+                for (int ks = 0; ks < k1steps; ++ks)
+                    umma_ss(tmem_base + TM_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
+                if (NS == 1) umma_commit(barM);
+                if (tile + (int)gridDim.x < n_tiles) T2_ISSUE_TMA(tile + gridDim.x);     // the stage is free
+            }
+            T2_MSTAMP(2);
+            if (NS == 2) {
+                mbar_wait(barB, phB);
+                phB ^= 1u;
+                tc_fence_after();
+                T2_MSTAMP(3);
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)         // D1 += U . DcB
+                        umma_ss(tmem_base + TM_D1, dU + (uint64_t)(ks * (4096 >> 4)), dDcB + (uint64_t)(ks * (256 >> 4)), idescU, true);
+                    umma_commit(barM);
+                }
+            }
+            T2_MSTAMP(4);
+            mbar_wait(barC, phC);
+            phC ^= 1u;
+            tc_fence_after();
+            T2_MSTAMP(5);
+            if (leader) {
+#pragma unroll 8
+                for (int ks = 0; ks < k2steps; ++ks)
+                    umma_ss(tmem_base + TM_D2, dA2 + (uint64_t)(ks * (4096 >> 4)), dB2 + (uint64_t)(ks * (512 >> 4)), idesc2, ks > 0);
+                umma_commit(barM);
+            }
+            T2_MSTAMP(6);
+        }
+    } else {
+        // =========================== compute warps ===========================
+        const int r = tid & 127, half = tid >> 7;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t row_off = (uint32_t)r * 16u;
+        uint32_t phM = 0, phT = 0;
+        const int py = r >> 4, px = r & 15;
+        // CPE values of the 8 rows / 16 columns of a tile (warp 7, lanes 0..23), double buffered over tiles
+#define T2_CPE_TABLE(tile_, buf_)                                                                                        \
     do {                                                                                                                 \
         if (g.cond_kind == NCA_COND_CPE && warp == 7 && lane < T2_TH + T2_TW) {                                          \
             const int tt_ = (tile_);                                                                                     \
             const int ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW;                    \
             const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow); \
             const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_)); \
-            sCpe[lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16);              \
+            sCpe2[(buf_) * 24 + lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16); \
         }                                                                                                                \
     } while (0)
-    const int n_tiles = a.dbg == 1 ? 0 : a.n_tiles;
-    if ((int)blockIdx.x < n_tiles) T2_CPE_TABLE(blockIdx.x);
-    __syncthreads();
-    if (tid == 0 && (int)blockIdx.x < n_tiles) T2_ISSUE_TMA(blockIdx.x);
-
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
-        const int b = tile / (a.tiles_x * a.tiles_y);
-        const int y0 = ((tile / a.tiles_x) % a.tiles_y) * T2_TH, x0 = (tile % a.tiles_x) * T2_TW;
-        const int gy = y0 + py, gx = x0 + px;
-        const bool inimg = gy < H && gx < W;
-        const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W;
-        mbar_wait(barT, phT);
-        phT ^= 1u;
-        if (a.dbg == 2) break;
-        if (border) {     // CTA-uniform
-            t2_patch_border<NS>(g, a.x_in, a.xc_in, b, y0, x0, sX, sXc);
-            __syncthreads();
-        }
-        // ---- fire decisions of the tile ----
-        if (a.fm.supplied) {
-            if (tid < 128) sFire[r] = inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f;
-        } else if (warp == (iter & 7)) {
-            const int fy = y0 + (lane >> 2), fx = x0 + 4 * (lane & 3);
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (fy < H && fx < W) {
-                const uint32_t p = (uint32_t)(fy * W + fx);
-                const uint4 rr = nca_philox4x32_10(p >> 2, (uint32_t)b, a.fm.t, NCA_PHILOX_STREAM, a.fm.k0, a.fm.k1);
-                f.x = nca_fire(rr.x, a.fm.thr, 0); f.y = nca_fire(rr.y, a.fm.thr, 0);
-                f.z = nca_fire(rr.z, a.fm.thr, 0); f.w = nca_fire(rr.w, a.fm.thr, 0);
+        if ((int)blockIdx.x < n_tiles) T2_CPE_TABLE(blockIdx.x, 0);
+        bar_compute();
+#define T2_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+            const int b = tile / tiles_per_b;
+            const int y0 = ((tile / a.tiles_x) % a.tiles_y) * T2_TH, x0 = (tile % a.tiles_x) * T2_TW;
+            const int gy = y0 + py, gx = x0 + px;
+            const bool inimg = gy < H && gx < W;
+            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W;
+            float* sFire = sFire2 + (iter & 1) * 128;
+            const uint32_t* sCpe = sCpe2 + (iter & 1) * 24;
+            T2_STAMP(0);
+            mbar_wait(barT, phT);
+            phT ^= 1u;
+            T2_STAMP(1);
+            if (border && g.pad != NCA_PAD_CONSTANT) {     // uniform over the compute warps
+                t2_patch_border<NS>(g, a.x_in, a.xc_in, b, y0, x0, sX, sXc);
+                T2_STAMP(4);
+                bar_compute();
             }
-            *reinterpret_cast<float4*>(sFire + (lane >> 2) * 16 + 4 * (lane & 3)) = f;
-        }
-        // ---- fine perception -> A1: warp = channel pair, lane = (column px, channel of the pair), two vertical blocks.
-        //      (channel planes are 240 floats apart = 16 banks, so the two half-warps never collide) ----
-        {
-            const int cp = warp, hc = lane >> 4, pxx = lane & 15, c = 2 * cp + hc;
-            if (cp < bg.npairs) {
-#pragma unroll
-                for (int vb = 0; vb < 2; ++vb) {
-                    float id[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (c < C) t2_percept4(sX + c * T2_XR * T2_XS, 4 * vb, pxx, id, sx, sy, lp);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int rr = (4 * vb + k) * 16 + pxx;
-                        uint2 v;
-                        v.x = pack_bf16(id[k], sx[k]); v.y = pack_bf16(sy[k], lp[k]);
-                        *reinterpret_cast<uint2*>(sA1 + (uint32_t)cp * 2048u + (uint32_t)rr * 16u + (uint32_t)hc * 8u) = v;
-                    }
+            T2_STAMP(7);
+            // ---- fire decisions of the tile ----
+            if (a.fm.supplied) {
+                if (tid < 128) sFire[r] = inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f;
+            } else if (warp == (iter & 7)) {
+                const int fy = y0 + (lane >> 2), fx = x0 + 4 * (lane & 3);
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fy < H && fx < W) {
+                    const uint32_t p = (uint32_t)(fy * W + fx);
+                    const uint4 rr = nca_philox4x32_10(p >> 2, (uint32_t)b, a.fm.t, NCA_PHILOX_STREAM, a.fm.k0, a.fm.k1);
+                    f.x = nca_fire(rr.x, a.fm.thr, 0); f.y = nca_fire(rr.y, a.fm.thr, 0);
+                    f.z = nca_fire(rr.z, a.fm.thr, 0); f.w = nca_fire(rr.w, a.fm.thr, 0);
                 }
+                *reinterpret_cast<float4*>(sFire + (lane >> 2) * 16 + 4 * (lane & 3)) = f;
             }
-        }
-        // residual state of this thread's cell (channels 8*half ..), cond chunk, zero tail chunks of A1
-        float xres[8];
+            // ---- fine perception -> A1: warp = channel pair, lane = (column px, channel of the pair), two vertical blocks.
+            //      (channel planes are 240 floats apart = 16 banks, so the two half-warps never collide) ----
+            {
+                const int cp = warp, hc = lane >> 4, pxx = lane & 15, c = 2 * cp + hc;
+                if (cp < bg.npairs) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = 8 * half + i;
-            xres[i] = c < C ? sX[(c * T2_XR + py + 1) * T2_XS + T2_XO + px + 1] : 0.0f;
-        }
-        if (half == 0) {
-            uint4 cv;
-            if (g.cond_kind == NCA_COND_CPE) {           // [cpe_y hi, cpe_x hi, 1, 1, cpe_y lo, cpe_x lo, 0, 0]
-                const uint32_t ry = sCpe[py], cx = sCpe[T2_TH + px];
-                cv = make_uint4((ry & 0xffffu) | (cx << 16), 0x3F803F80u, (ry >> 16) | (cx & 0xffff0000u), 0u);
-            } else {
-                cv = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
-            }
-            *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = cv;
-        } else {
-            for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
-                *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
-        }
-        if (NS == 2) {
-            // ---- coarse perception -> Zc rows q = qy*10 + qx: warp = channel pair, lane = (qx, 3-row block) ----
-            const int cp = warp, qx = lane % T2_QW, hb = lane / T2_QW;
-            if (lane < 2 * T2_QW && cp < bg.npairs) {
-                float id0[3], sx0[3], sy0[3], lp0[3], id1[3] = {0.f, 0.f, 0.f}, sx1[3] = {0.f, 0.f, 0.f}, sy1[3] = {0.f, 0.f, 0.f},
-                      lp1[3] = {0.f, 0.f, 0.f};
-                t2_percept3c(sXc + (2 * cp) * T2_CR * T2_CS, 3 * hb, qx, id0, sx0, sy0, lp0);
-                if (2 * cp + 1 < C) t2_percept3c(sXc + (2 * cp + 1) * T2_CR * T2_CS, 3 * hb, qx, id1, sx1, sy1, lp1);
+                    for (int vb = 0; vb < 2; ++vb) {
+                        float id[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (c < C) t2_percept4(sX + c * T2_XR * T2_XS, 4 * vb, pxx, id, sx, sy, lp);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int q = (3 * hb + k) * T2_QW + qx;
-                    uint4 v;
-                    v.x = pack_bf16(id0[k], sx0[k]); v.y = pack_bf16(sy0[k], lp0[k]);
-                    v.z = pack_bf16(id1[k], sx1[k]); v.w = pack_bf16(sy1[k], lp1[k]);
-                    *reinterpret_cast<uint4*>(sZc + (uint32_t)cp * 1024u + (uint32_t)q * 16u) = v;
-                }
-            }
-            // rows 60..63 of every chunk and the chunks of absent channel pairs must be finite (they meet zero columns of
-            // U / zero rows of W1h): zero them; A2 overlays this area, so every tile
-            if (tid < 32) *reinterpret_cast<uint4*>(sZc + (uint32_t)(tid >> 2) * 1024u + (uint32_t)(60 + (tid & 3)) * 16u) = make_uint4(0, 0, 0, 0);
-            for (int i = tid; i < (8 - bg.npairs) * 64; i += T2_THREADS)
-                *reinterpret_cast<uint4*>(sZc + (uint32_t)(bg.npairs + (i >> 6)) * 1024u + (uint32_t)(i & 63) * 16u) = make_uint4(0, 0, 0, 0);
-            if (border) {
-                // replicate-extend the coarse perception over the image border (edge clamp of the upsample)
-                __syncthreads();
-                const int Hc = H >> 1, Wc = W >> 1;
-                for (int i = tid; i < T2_QH * T2_QW * 8; i += T2_THREADS) {
-                    const int ch = i & 7, q = i >> 3;
-                    const int qy = q / T2_QW, qxx = q % T2_QW;
-                    const int Qy = (y0 >> 1) - 1 + qy, Qx = (x0 >> 1) - 1 + qxx;
-                    const int Cy = min(max(Qy, 0), Hc - 1), Cx = min(max(Qx, 0), Wc - 1);
-                    if (Cy == Qy && Cx == Qx) continue;
-                    int sy_ = Cy - ((y0 >> 1) - 1), sx_ = Cx - ((x0 >> 1) - 1);
-                    // a ragged last tile can clamp to a cell outside the 6x10 footprint only if that cell is outside
-                    // every in-image fine cell's support; keep the index in range
-                    sy_ = min(max(sy_, 0), T2_QH - 1); sx_ = min(max(sx_, 0), T2_QW - 1);
-                    const int qs = sy_ * T2_QW + sx_;
-                    *reinterpret_cast<uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)q * 16u) =
-                        *reinterpret_cast<const uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)qs * 16u);
-                }
-            }
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();                                   // ---- sync A: operands complete, stage free ----
-        if (a.dbg == 3) break;
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA1), b_addr = smem_u32(sB1);
-            if (NS == 2) {
-                const uint32_t z_addr = smem_u32(sZc);
-                // Dc = Zc . W1h^T over the perception columns.  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of
-                // the M = 128 instruction alias the next chunk (finite values) and produce rows of Dc nobody reads
-                for (int ks = 0; ks < (bg.npairs + 1) / 2; ++ks)
-                    umma_f16_ss(tmem_base + TM_DC, umma_desc(z_addr + (uint32_t)ks * 2048u, 1024u, 128u),
-                                umma_desc(b_addr + (uint32_t)ks * 2u * lbo_b1, lbo_b1, 128u), idesc1, ks > 0 ? 1u : 0u);
-                umma_commit(barM);
-            }
-            for (int ks = 0; ks < bg.K1 / 16; ++ks)
-                umma_f16_ss(tmem_base + TM_D1, umma_desc(a_addr + (uint32_t)ks * 4096u, 2048u, 128u),
-                            umma_desc(b_addr + (uint32_t)ks * 2u * lbo_b1, lbo_b1, 128u), idesc1, ks > 0 ? 1u : 0u);
-            if (NS == 1) umma_commit(barM);
-            if (tile + (int)gridDim.x < n_tiles) T2_ISSUE_TMA(tile + gridDim.x);
-        }
-        if (NS == 2) {
-            mbar_wait(barM, phM);
-            phM ^= 1u;
-            __syncwarp();
-            tc_fence_after();
-            // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
-            if ((warp & 3) < 2) {
-                const int q = r;                          // 0..63
-#pragma unroll 1
-                for (int blk = 0; blk < 2; ++blk) {
-                    const int j0 = 64 * half + 32 * blk;
-                    if (j0 < fc) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_lane + TM_DC + (uint32_t)j0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            uint4 o;
-                            o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                            o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                            o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                            o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                            *reinterpret_cast<uint4*>(sDcB + (uint32_t)(j0 / 8 + qq) * 1024u + (uint32_t)(q >> 3) * 128u + (uint32_t)(q & 7) * 16u) = o;
+                        for (int k = 0; k < 4; ++k) {
+                            const int rr = (4 * vb + k) * 16 + pxx;
+                            uint2 v;
+                            v.x = pack_bf16(id[k], sx[k]); v.y = pack_bf16(sy[k], lp[k]);
+                            *reinterpret_cast<uint2*>(sA1 + (uint32_t)cp * 2048u + (uint32_t)rr * 16u + (uint32_t)hc * 8u) = v;
                         }
                     }
                 }
             }
+            T2_STAMP(11);
+            // residual state of this thread's cell (channels 8*half ..), cond chunk, zero tail chunks of A1
+            float xres[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = 8 * half + i;
+                xres[i] = c < C ? sX[(c * T2_XR + py + 1) * T2_XS + T2_XO + px + 1] : 0.0f;
+            }
+            if (half == 0) {
+                uint4 cv;
+                if (g.cond_kind == NCA_COND_CPE) {           // [cpe_y hi, cpe_x hi, 1, 1, cpe_y lo, cpe_x lo, 0, 0]
+                    const uint32_t ry = sCpe[py], cx = sCpe[T2_TH + px];
+                    cv = make_uint4((ry & 0xffffu) | (cx << 16), 0x3F803F80u, (ry >> 16) | (cx & 0xffff0000u), 0u);
+                } else {
+                    cv = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
+                }
+                *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = cv;
+            } else {
+                for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
+                    *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
+            }
+            if (NS == 2) {
+                // ---- coarse perception -> Zc rows q = qy*10 + qx: warp = channel pair, lane = (qx, 3-row block) ----
+                const int cp = warp, qx = lane % T2_QW, hb = lane / T2_QW;
+                if (lane < 2 * T2_QW && cp < bg.npairs) {
+                    float id0[3], sx0[3], sy0[3], lp0[3], id1[3] = {0.f, 0.f, 0.f}, sx1[3] = {0.f, 0.f, 0.f}, sy1[3] = {0.f, 0.f, 0.f},
+                          lp1[3] = {0.f, 0.f, 0.f};
+                    t2_percept3c(sXc + (2 * cp) * T2_CR * T2_CS, 3 * hb, qx, id0, sx0, sy0, lp0);
+                    if (2 * cp + 1 < C) t2_percept3c(sXc + (2 * cp + 1) * T2_CR * T2_CS, 3 * hb, qx, id1, sx1, sy1, lp1);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int q = (3 * hb + k) * T2_QW + qx;
+                        uint4 v;
+                        v.x = pack_bf16(id0[k], sx0[k]); v.y = pack_bf16(sy0[k], lp0[k]);
+                        v.z = pack_bf16(id1[k], sx1[k]); v.w = pack_bf16(sy1[k], lp1[k]);
+                        *reinterpret_cast<uint4*>(sZc + (uint32_t)cp * 1024u + (uint32_t)q * 16u) = v;
+                    }
+                }
+                // rows 60..63 of every chunk and the chunks of absent channel pairs must be finite (they meet zero columns of
+                // U / zero rows of W1h): zero them; A2 overlays this area, so every tile
+                if (tid < 32) *reinterpret_cast<uint4*>(sZc + (uint32_t)(tid >> 2) * 1024u + (uint32_t)(60 + (tid & 3)) * 16u) = make_uint4(0, 0, 0, 0);
+                for (int i = tid; i < (8 - bg.npairs) * 64; i += T2_THREADS)
+                    *reinterpret_cast<uint4*>(sZc + (uint32_t)(bg.npairs + (i >> 6)) * 1024u + (uint32_t)(i & 63) * 16u) = make_uint4(0, 0, 0, 0);
+                T2_STAMP(15);
+                if (border) {
+                    // replicate-extend the coarse perception over the image border (edge clamp of the upsample)
+                    bar_compute();
+                    const int Hc = H >> 1, Wc = W >> 1;
+                    for (int i = tid; i < T2_QH * T2_QW * 8; i += T2_THREADS) {
+                        const int ch = i & 7, q = i >> 3;
+                        const int qy = q / T2_QW, qxx = q % T2_QW;
+                        const int Qy = (y0 >> 1) - 1 + qy, Qx = (x0 >> 1) - 1 + qxx;
+                        const int Cy = min(max(Qy, 0), Hc - 1), Cx = min(max(Qx, 0), Wc - 1);
+                        if (Cy == Qy && Cx == Qx) continue;
+                        int sy_ = Cy - ((y0 >> 1) - 1), sx_ = Cx - ((x0 >> 1) - 1);
+                        // a ragged last tile can clamp to a cell outside the 6x10 footprint only if that cell is outside
+                        // every in-image fine cell's support; keep the index in range
+                        sy_ = min(max(sy_, 0), T2_QH - 1); sx_ = min(max(sx_, 0), T2_QW - 1);
+                        const int qs = sy_ * T2_QW + sx_;
+                        *reinterpret_cast<uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)q * 16u) =
+                            *reinterpret_cast<const uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)qs * 16u);
+                    }
+                }
+            }
+            T2_STAMP(2);
             fence_proxy_async();
             tc_fence_before();
-            __syncthreads();                               // ---- sync B ----
-            if (tid == 0) {
+            mbar_arrive(barA);                                 // ---- A: operands complete, stage consumed ----
+            T2_STAMP(3);
+            if (NS == 2) {
+                mbar_wait(barM, phM);
+                phM ^= 1u;
                 tc_fence_after();
-                const uint32_t u_addr = smem_u32(sU), d_addr = smem_u32(sDcB);
-                for (int ks = 0; ks < 4; ++ks)             // D1 += U . DcB
-                    umma_f16_ss(tmem_base + TM_D1, umma_desc(u_addr + (uint32_t)ks * 4096u, 2048u, 128u),
-                                umma_desc(d_addr + (uint32_t)ks * 256u, 128u, 1024u), idescU, 1u);
-                umma_commit(barM);
-            }
-        }
-        mbar_wait(barM, phM);
-        phM ^= 1u;
-        __syncwarp();
-        tc_fence_after();
-        if (a.dbg == 4) break;
-        // ---- E1: relu(D1) -> bf16 -> A2 ----
+                T2_STAMP(5);
+                // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
+                if ((warp & 3) < 2) {
+                    const int q = r;                          // 0..63
 #pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-            const int j0 = 64 * half + 32 * blk;
-            if (j0 < fc) {
-                uint32_t v[32];
-                tmem_ld32(tmem_lane + TM_D1 + (uint32_t)j0, v);
-                tmem_ld_wait();
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const int j0 = 64 * half + 32 * blk;
+                        if (j0 < fc) {
+                            uint32_t v[32];
+                            tmem_ld32(tmem_lane + TM_DC + (uint32_t)j0, v);
+                            tmem_ld_wait();
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    uint4 o;
-                    o.x = pack_bf16_relu(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                    o.y = pack_bf16_relu(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                    o.z = pack_bf16_relu(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                    o.w = pack_bf16_relu(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                    *reinterpret_cast<uint4*>(sA2 + (uint32_t)(j0 / 8 + qq) * 2048u + row_off) = o;
+                            for (int qq = 0; qq < 4; ++qq) {
+                                uint4 o;
+                                o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                                o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                                o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                                o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                                *reinterpret_cast<uint4*>(sDcB + (uint32_t)(j0 / 8 + qq) * 1024u + (uint32_t)q * 16u) = o;
+                            }
+                        }
+                    }
                 }
+                T2_STAMP(6);
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(barB);                             // ---- B: DcB complete ----
             }
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();                                   // ---- sync C ----
-        if (a.dbg == 5) break;
-        if (tid == 0) {
+            T2_STAMP(8);
+            mbar_wait(barM, phM);
+            phM ^= 1u;
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA2), b_addr = smem_u32(sB2w);
-            for (int ks = 0; ks < fc / 16; ++ks)
-                umma_f16_ss(tmem_base + TM_D2, umma_desc(a_addr + (uint32_t)ks * 4096u, 2048u, 128u),
-                            umma_desc(b_addr + (uint32_t)ks * 512u, 256u, 128u), idesc2, ks > 0 ? 1u : 0u);
-            umma_commit(barM);
-        }
-        mbar_wait(barM, phM);
-        phM ^= 1u;
-        __syncwarp();
-        tc_fence_after();
-        if (a.dbg == 6) break;
-        // ---- E2: x' = x + (D2 + b2) * fire ; coarse state of the next step ----
-        {
-            uint32_t v[8];
-            tmem_ld8(tmem_lane + TM_D2 + 8u * (uint32_t)half, v);
-            tmem_ld_wait();
-            const float fire = sFire[r];
-            float xn[8];
+            T2_STAMP(9);
+            // ---- E1: relu(D1) -> bf16 -> A2 ----
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                const int j0 = 64 * half + 32 * blk;
+                if (j0 < fc) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_lane + TM_D1 + (uint32_t)j0, v);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xn[i] = fmaf(__uint_as_float(v[i]) + sB2[8 * half + i], fire, xres[i]);
-            const int nch = min(8, C - 8 * half);                  // warp-uniform
-            if (inimg) {
-                float* xo = a.x_out + ((size_t)b * C + 8 * half) * plane + (size_t)gy * W + gx;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < nch) xo[(size_t)i * plane] = xn[i];
-            }
-            if (NS == 2 && a.xc_out != nullptr) {
-                float m4[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float a01 = __shfl_xor_sync(0xffffffffu, xn[i], 1);
-                    const float a10 = __shfl_xor_sync(0xffffffffu, xn[i], 16);
-                    const float a11 = __shfl_xor_sync(0xffffffffu, xn[i], 17);
-                    m4[i] = 0.25f * (((xn[i] + a01) + a10) + a11);
+                    for (int qq = 0; qq < 4; ++qq) {
+                        uint4 o;
+                        o.x = pack_bf16_relu(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                        o.y = pack_bf16_relu(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                        o.z = pack_bf16_relu(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                        o.w = pack_bf16_relu(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                        *reinterpret_cast<uint4*>(sA2 + (uint32_t)(j0 / 8 + qq) * 2048u + row_off) = o;
+                    }
                 }
-                if (inimg && (lane & 17) == 0) {
+            }
+            T2_STAMP(10);
+            if (tile + (int)gridDim.x < n_tiles) T2_CPE_TABLE(tile + gridDim.x, (iter + 1) & 1);   // published by the arrive below
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(barC);                                 // ---- C: A2 complete ----
+            T2_STAMP(12);
+            mbar_wait(barM, phM);
+            phM ^= 1u;
+            tc_fence_after();
+            T2_STAMP(13);
+            // ---- E2: x' = x + (D2 + b2) * fire ; coarse state of the next step ----
+            {
+                uint32_t v[8];
+                tmem_ld8(tmem_lane + TM_D2 + 8u * (uint32_t)half, v);
+                tmem_ld_wait();
+                const float fire = sFire[r];
+                float xn[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xn[i] = fmaf(__uint_as_float(v[i]) + sB2[8 * half + i], fire, xres[i]);
+                const int nch = min(8, C - 8 * half);                  // warp-uniform
+                {
+                    float* xo = a.x_out + ((size_t)b * C + 8 * half) * plane + (size_t)gy * W + gx;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (inimg && i < nch) *xo = xn[i];
+                        xo += plane;
+                    }
+                }
+                if (NS == 2 && a.xc_out != nullptr) {
                     const size_t cpl = plane >> 2;
                     float* co = a.xc_out + ((size_t)b * C + 8 * half) * cpl + (size_t)(gy >> 1) * (W >> 1) + (gx >> 1);
+                    const bool cst = inimg && (lane & 17) == 0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < nch) co[(size_t)i * cpl] = m4[i];
+                    for (int i = 0; i < 8; ++i) {
+                        const float a01 = __shfl_xor_sync(0xffffffffu, xn[i], 1);
+                        const float a10 = __shfl_xor_sync(0xffffffffu, xn[i], 16);
+                        const float a11 = __shfl_xor_sync(0xffffffffu, xn[i], 17);
+                        if (cst && i < nch) *co = 0.25f * (((xn[i] + a01) + a10) + a11);
+                        co += cpl;
+                    }
                 }
             }
+            T2_STAMP(14);
+            // no CTA barrier here: the next tile's MMAs are gated by barrier A, which every compute thread reaches only
+            // after its TMEM reads of this tile; shared operands of this tile were released by the MMA completions
         }
-        if (tile + (int)gridDim.x < n_tiles) T2_CPE_TABLE(tile + gridDim.x);
         tc_fence_before();
-        __syncthreads();                                   // ---- sync D: TMEM / A2 / sFire reuse ----
     }
-    tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ---- weight / constant operand packing ------------------------------------------------------------------
@@ -647,6 +745,10 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     a.U = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes + 64);
     a.fm = fm;
     { const char* e = getenv("NCA_T2_DBG"); a.dbg = e ? atoi(e) : 0; }
+    static long long* tdbg = nullptr;
+    const bool timing = getenv("NCA_T2_TDBG") != nullptr;
+    if (timing && !tdbg) { cudaMalloc(&tdbg, 256 * sizeof(long long)); }
+    a.tdbg = timing ? tdbg : nullptr;
     a.tiles_x = (g.W + T2_TW - 1) / T2_TW; a.tiles_y = (g.H + T2_TH - 1) / T2_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
     const size_t smem = t2_smem(g, a.bg).total;
     const uint32_t tcols = g.ns == 2 ? 256u : 128u;
@@ -659,11 +761,25 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     const CUtensorMap* txc = (const CUtensorMap*)m->xc;
     if (g.ns == 2) {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_fwd_tc2_kernel<2><<<grid, T2_THREADS, smem, s>>>(*tx, *txc, a);
+        dynca_fwd_tc2_kernel<2><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, a);
     } else {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_fwd_tc2_kernel<1><<<grid, T2_THREADS, smem, s>>>(*tx, *txc, a);
+        dynca_fwd_tc2_kernel<1><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, a);
     }
     NCA_LAUNCH_OK();
+    if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps (cycles since the tile's first stamp)
+        long long h[256];
+        cudaMemcpy(h, tdbg, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int it = 0; it < 8; ++it) {
+            fprintf(stderr, "tc2 mma-warp iter %d (vs compute tile start):", it);
+            for (int k = 0; k < 7; ++k) fprintf(stderr, " %lld", h[128 + it * 8 + k] - h[it * 16]);
+            fprintf(stderr, "\n");
+        }
+        for (int it = 0; it < 8; ++it) {
+            fprintf(stderr, "tc2 timing iter %d:", it);
+            for (int k = 0; k < 16; ++k) fprintf(stderr, " %lld", h[it * 16 + k] - h[it * 16]);
+            fprintf(stderr, "  | since prev tile start %lld\n", it ? h[it * 16] - h[(it - 1) * 16] : 0);
+        }
+    }
     return NCA_OK;
 }
