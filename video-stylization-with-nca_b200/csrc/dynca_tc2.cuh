@@ -1,0 +1,294 @@
+// Shared pieces of the second-generation tensor-core DyNCA kernels (dynca_tc2.cu forward, dynca_tc2_bwd.cu BPTT):
+// tile / staging geometry, TMA + mbarrier + tcgen05 helpers, register-blocked perception, border patches, tensor maps.
+#pragma once
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+#include "dynca_tc_common.cuh"
+
+#define T2_TH 8
+#define T2_TW 16
+// TMA (fp32, no swizzle) needs the innermost box coordinate to be a multiple of 4 elements (16 bytes; measured: any
+// other start raises an illegal-instruction fault), so the boxes start 4 columns left of the tile: fine box columns
+// x0-4 .. x0+19 (ring column x0-1 at index T2_XO), coarse box columns x0/2-4 .. x0/2+11 (footprint column x0/2-2 at T2_CO)
+#define T2_XR 10
+#define T2_XS 24
+#define T2_XO 3
+#define T2_CR 8
+#define T2_CS 16
+#define T2_CO 2
+#define T2_QH 6
+#define T2_QW 10
+#define T2_THREADS 256
+#define T2_HDR 1536u
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// two floats -> bf16x2 with relu fused (lo in the low half)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// perception of 4 vertically adjacent cells (rows r0 .. r0+3 of the tile) of one channel; col = stage column of the
+// left neighbour.  Separable: s = [1 2 1]^T, d = [-1 0 1]^T over rows.
+__device__ __forceinline__ void t2_percept4(const float* __restrict__ ch, int r0, int col, float id[4], float sx[4], float sy[4], float lp[4]) {
+    float s[3][4], d[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = ch[(r0 + k) * T2_XS + T2_XO + col + j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s[j][k] = fmaf(2.0f, v[k + 1], v[k] + v[k + 2]);
+            d[j][k] = v[k + 2] - v[k];
+            if (j == 1) id[k] = v[k + 1];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sx[k] = s[2][k] - s[0][k];
+        sy[k] = fmaf(2.0f, d[1][k], d[0][k] + d[2][k]);
+        lp[k] = fmaf(-16.0f, id[k], fmaf(2.0f, s[1][k], s[0][k] + s[2][k]));
+    }
+}
+// same for 3 vertically adjacent coarse cells (coarse stage stride T2_CS)
+__device__ __forceinline__ void t2_percept3c(const float* __restrict__ ch, int r0, int col, float id[3], float sx[3], float sy[3], float lp[3]) {
+    float s[3][3], d[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = ch[(r0 + k) * T2_CS + T2_CO + col + j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s[j][k] = fmaf(2.0f, v[k + 1], v[k] + v[k + 2]);
+            d[j][k] = v[k + 2] - v[k];
+            if (j == 1) id[k] = v[k + 1];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        sx[k] = s[2][k] - s[0][k];
+        sy[k] = fmaf(2.0f, d[1][k], d[0][k] + d[2][k]);
+        lp[k] = fmaf(-16.0f, id[k], fmaf(2.0f, s[1][k], s[0][k] + s[2][k]));
+    }
+}
+
+// padding index map for coordinates at most one period outside the image (no generic modulo); ragged tiles reach
+// further out only for cells nobody reads, so clamp
+__device__ __forceinline__ int t2_padmap(int r, int n, int mode) {
+    if (r >= 0 && r < n) return r;
+    int v;
+    if (mode == NCA_PAD_CIRCULAR) v = r < 0 ? r + n : r - n;
+    else if (mode == NCA_PAD_REPLICATE) v = r;
+    else v = r < 0 ? -r : 2 * (n - 1) - r;           // reflect
+    return min(max(v, 0), n - 1);
+}
+
+// patch the staged tiles of a border tile: every staged position outside the image takes the value the padding mode
+// prescribes (TMA filled it with zero, which is already right for constant padding).  One staged position per thread
+// (fine: threads 0..179, coarse: threads 160..255), channel loop inside, so the index math runs once per tile.
+template <int NS, int NT>
+__device__ __forceinline__ void t2_patch_border(const DyncaGeom& g, const float* __restrict__ x, const float* __restrict__ xc, int b,
+                                                int y0, int x0, float* __restrict__ sX, float* __restrict__ sXc) {
+    const int C = g.C, H = g.H, W = g.W, tid = threadIdx.x;
+    if (g.pad == NCA_PAD_CONSTANT) return;
+    const bool wrap = g.pad == NCA_PAD_CIRCULAR;   // replicate / reflect sources lie inside the staged tile: smem -> smem
+    if (tid < T2_XR * 18) {
+        const int q = tid % 18, r = tid / 18;
+        const int yy = y0 - 1 + r, xx = x0 - 1 + q;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
+            const int iy = t2_padmap(yy, H, g.pad), ix = t2_padmap(xx, W, g.pad);
+            float* dst = sX + r * T2_XS + T2_XO + q;
+            if (wrap) {
+                const size_t plane = (size_t)H * W;
+                const float* src = x + (size_t)b * C * plane + (size_t)iy * W + ix;
+                float v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(src + c * plane) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) if (c < C) dst[c * T2_XR * T2_XS] = v[c];
+            } else {
+                const int sr = min(max(iy - (y0 - 1), 0), T2_XR - 1), sq = min(max(ix - (x0 - 1), 0), 17);
+                const float* src = sX + sr * T2_XS + T2_XO + sq;
+#pragma unroll 8
+                for (int c = 0; c < C; ++c) dst[c * T2_XR * T2_XS] = src[c * T2_XR * T2_XS];
+            }
+        }
+    }
+    if (NS == 2 && tid >= NT - T2_CR * 12) {
+        const int i = tid - (NT - T2_CR * 12);
+        const int q = i % 12, r = i / 12;
+        const int Hc = H >> 1, Wc = W >> 1;
+        const int yy = (y0 >> 1) - 2 + r, xx = (x0 >> 1) - 2 + q;
+        if (yy < 0 || yy >= Hc || xx < 0 || xx >= Wc) {
+            const int iy = t2_padmap(yy, Hc, g.pad), ix = t2_padmap(xx, Wc, g.pad);
+            float* dst = sXc + r * T2_CS + T2_CO + q;
+            if (wrap) {
+                const size_t cplane = (size_t)Hc * Wc;
+                const float* src = xc + (size_t)b * C * cplane + (size_t)iy * Wc + ix;
+                float v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(src + c * cplane) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) if (c < C) dst[c * T2_CR * T2_CS] = v[c];
+            } else {
+                const int sr = min(max(iy - ((y0 >> 1) - 2), 0), T2_CR - 1), sq = min(max(ix - ((x0 >> 1) - 2), 0), 11);
+                const float* src = sXc + sr * T2_CS + T2_CO + sq;
+#pragma unroll 8
+                for (int c = 0; c < C; ++c) dst[c * T2_CR * T2_CS] = src[c * T2_CR * T2_CS];
+            }
+        }
+    }
+}
+
+// ---- synchronisation helpers: compute threads -> MMA warp hand-offs are mbarriers, not CTA barriers ----
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }   // named barrier over n threads
+// D[tmem] (+)= A . B with precomputed 64-bit descriptors
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+
+
+// ---- perception phases shared by the forward and the BPTT kernel (NW = number of compute warps, 8 or 16) ----
+// fine perception -> A1: item = (channel pair, vertical block of 4 rows); lane = (column px, channel of the pair).
+// Channel planes are T2_XR * T2_XS = 240 floats apart = 16 banks, so the two half-warps never collide.
+template <int NW>
+__device__ __forceinline__ void t2_fine_to_a1(const float* __restrict__ sX, uint8_t* __restrict__ sA1, int C, int npairs, int warp, int lane) {
+    const int hc = lane >> 4, pxx = lane & 15;
+    for (int item = warp; item < 2 * npairs; item += NW) {
+        const int cp = item >> 1, vb = item & 1, c = 2 * cp + hc;
+        float id[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < C) t2_percept4(sX + c * T2_XR * T2_XS, 4 * vb, pxx, id, sx, sy, lp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rr = (4 * vb + k) * 16 + pxx;
+            uint2 v;
+            v.x = pack_bf16(id[k], sx[k]); v.y = pack_bf16(sy[k], lp[k]);
+            *reinterpret_cast<uint2*>(sA1 + (uint32_t)cp * 2048u + (uint32_t)rr * 16u + (uint32_t)hc * 8u) = v;
+        }
+    }
+}
+// coarse perception -> Zc rows q = qy*10 + qx (64 rows per K chunk, chunk stride 1024): item = channel pair;
+// block); lane = (qx, 3-row block).  Then the rows / chunks nobody writes are zeroed (they meet zero columns of U / zero rows of W1h
+// but must be finite), and on border tiles the footprint is replicate-extended over the image border (edge clamp of
+// the x2 bilinear upsample, dynca.py:93-94).  NT compute threads call this; bar_id = their named barrier.
+template <int NW>
+__device__ __forceinline__ void t2_coarse_to_zc(const DyncaGeom& g, const float* __restrict__ sXc, uint8_t* __restrict__ sZc, int npairs,
+                                                int y0, int x0, bool border, int tid, int warp, int lane) {
+    const int C = g.C;
+    constexpr int NT = NW * 32;
+    if (lane < 2 * T2_QW) {
+        for (int cp = warp; cp < npairs; cp += NW) {
+            const int hb = lane / T2_QW, qx = lane % T2_QW;
+            float id0[3], sx0[3], sy0[3], lp0[3], id1[3] = {0.f, 0.f, 0.f}, sx1[3] = {0.f, 0.f, 0.f}, sy1[3] = {0.f, 0.f, 0.f}, lp1[3] = {0.f, 0.f, 0.f};
+            t2_percept3c(sXc + (2 * cp) * T2_CR * T2_CS, 3 * hb, qx, id0, sx0, sy0, lp0);
+            if (2 * cp + 1 < C) t2_percept3c(sXc + (2 * cp + 1) * T2_CR * T2_CS, 3 * hb, qx, id1, sx1, sy1, lp1);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int q = (3 * hb + k) * T2_QW + qx;
+                uint4 v;
+                v.x = pack_bf16(id0[k], sx0[k]); v.y = pack_bf16(sy0[k], lp0[k]);
+                v.z = pack_bf16(id1[k], sx1[k]); v.w = pack_bf16(sy1[k], lp1[k]);
+                *reinterpret_cast<uint4*>(sZc + (uint32_t)cp * 1024u + (uint32_t)q * 16u) = v;
+            }
+        }
+    }
+    if (tid < 32) *reinterpret_cast<uint4*>(sZc + (uint32_t)(tid >> 2) * 1024u + (uint32_t)(60 + (tid & 3)) * 16u) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (8 - npairs) * 64; i += NT)
+        *reinterpret_cast<uint4*>(sZc + (uint32_t)(npairs + (i >> 6)) * 1024u + (uint32_t)(i & 63) * 16u) = make_uint4(0, 0, 0, 0);
+    if (border) {
+        bar_sync_n(1, NT);
+        const int Hc = g.H >> 1, Wc = g.W >> 1;
+        for (int i = tid; i < T2_QH * T2_QW * 8; i += NT) {
+            const int ch = i & 7, q = i >> 3;
+            const int qy = q / T2_QW, qxx = q % T2_QW;
+            const int Qy = (y0 >> 1) - 1 + qy, Qx = (x0 >> 1) - 1 + qxx;
+            const int Cy = min(max(Qy, 0), Hc - 1), Cx = min(max(Qx, 0), Wc - 1);
+            if (Cy == Qy && Cx == Qx) continue;
+            // a ragged last tile can clamp to a cell outside the 6x10 footprint only if that cell is outside every
+            // in-image fine cell's support; keep the index in range
+            const int sy_ = min(max(Cy - ((y0 >> 1) - 1), 0), T2_QH - 1), sx_ = min(max(Cx - ((x0 >> 1) - 1), 0), T2_QW - 1);
+            const int qs = sy_ * T2_QW + sx_;
+            *reinterpret_cast<uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)q * 16u) =
+                *reinterpret_cast<const uint4*>(sZc + (uint32_t)ch * 1024u + (uint32_t)qs * 16u);
+        }
+    }
+}
+// fire decisions of one 8x16 tile by ONE warp: 32 lanes = 32 quads of 4 consecutive pixels -> sFire[128]
+__device__ __forceinline__ void t2_fire_tile(const FireMask& fm, int b, int y0, int x0, int H, int W, int lane, float* __restrict__ sFire) {
+    const int fy = y0 + (lane >> 2), fx = x0 + 4 * (lane & 3);
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fy < H && fx < W) {
+        const uint32_t p = (uint32_t)(fy * W + fx);
+        const uint4 rr = nca_philox4x32_10(p >> 2, (uint32_t)b, fm.t, NCA_PHILOX_STREAM, fm.k0, fm.k1);
+        f.x = nca_fire(rr.x, fm.thr, 0); f.y = nca_fire(rr.y, fm.thr, 0);
+        f.z = nca_fire(rr.z, fm.thr, 0); f.w = nca_fire(rr.w, fm.thr, 0);
+    }
+    *reinterpret_cast<float4*>(sFire + (lane >> 2) * 16 + 4 * (lane & 3)) = f;
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------------------
+typedef CUresult (*T2EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline T2EncodeFn t2_encode_fn() {
+    static T2EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (T2EncodeFn)p;
+    }
+    return fn;
+}
+// 5-D map over [slots][B][C][Hh][Ww] fp32 with box [1][1][C][bh][bw]
+static inline int t2_make_map(CUtensorMap* tm, const float* base, int slots, size_t slot_floats, int B, int C, int Hh, int Ww, int bh, int bw) {
+    T2EncodeFn fn = t2_encode_fn();
+    if (!fn) { nca_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NCA_ERR_CUDA; }
+    cuuint64_t dims[5] = {(cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)C, (cuuint64_t)B, (cuuint64_t)slots};
+    cuuint64_t strides[4] = {(cuuint64_t)Ww * 4, (cuuint64_t)Hh * Ww * 4, (cuuint64_t)C * Hh * Ww * 4, (cuuint64_t)slot_floats * 4};
+    cuuint32_t box[5] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)C, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { nca_set_error("cuTensorMapEncodeTiled failed with %d", (int)rc); return NCA_ERR_CUDA; }
+    return NCA_OK;
+}
+
+static inline int t2_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
