@@ -233,6 +233,39 @@ def perceive_coarse(x, mode):
     return torch.cat([xc, _stencil(xc, SOBEL_X, mode), _stencil(xc, SOBEL_Y, mode), _stencil(xc, LAPLACE, mode)], dim=1)
 
 
+def _up2T_tiled_bf16(ga, th=8, tw=16):
+    """Transpose of the x2 bilinear upsample applied tile by tile the way dynca_tc2_bwd.cu does it: every 8x16 tile
+    produces its own partial GaU on the (unclamped) 6x10 coarse footprint in fp32, rounds it to bf16, and only then
+    the rows / columns outside the image fold into the clamped border cells and the tiles add up."""
+    B, J, H, W = ga.shape
+    Hc, Wc = H // 2, W // 2
+
+    def umat(n):       # [n fine, n/2 + 2 extended coarse]: unclamped weights, extended index = coarse index + 1
+        m = torch.zeros(n, n // 2 + 2)
+        for y in range(n):
+            Q = y // 2
+            if y % 2 == 0:
+                m[y, Q] += 0.25
+                m[y, Q + 1] += 0.75
+            else:
+                m[y, Q + 1] += 0.75
+                m[y, Q + 2] += 0.25
+        return m
+
+    Uy, Ux = umat(H), umat(W)
+    out = torch.zeros(B, J, Hc, Wc)
+    for y0 in range(0, H, th):
+        for x0 in range(0, W, tw):
+            t = ga[:, :, y0:y0 + th, x0:x0 + tw]
+            ext = bf16r(torch.einsum("yq,bjyx,xp->bjqp", Uy[y0:y0 + th], t, Ux[x0:x0 + tw]))
+            ext[:, :, 1] += ext[:, :, 0]
+            ext[:, :, Hc] += ext[:, :, Hc + 1]
+            ext[:, :, :, 1] += ext[:, :, :, 0]
+            ext[:, :, :, Wc] += ext[:, :, :, Wc + 1]
+            out += ext[:, :, 1:Hc + 1, 1:Wc + 1]
+    return out
+
+
 def _emu_preact(xr, w1q, b1q, scales, mode, cond, variant):
     """pre-activation a of one step with the rounding points of kernel `variant` (1: dynca_bf16.cu, 2: dynca_tc2.cu).
     Returns (a, zp, zq): zp = fp32 perception that autograd can differentiate, zq = the rounded GEMM operand the
@@ -285,6 +318,7 @@ def dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, mode, cond, g
         xs.append(x)
     g = g_final.clone() if g_final is not None else torch.zeros_like(x0)
     gw1 = torch.zeros_like(w1); gb1 = torch.zeros_like(b1); gw2 = torch.zeros_like(w2); gb2 = torch.zeros_like(b2)
+    two = bwd_variant == 2 and len(scales) == 2
     for t in range(T - 1, -1, -1):
         if (t + 1) in taps:
             g = g.clone()
@@ -296,10 +330,27 @@ def dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, mode, cond, g
         gw2 += torch.einsum("bchw,bjhw->cj", gy, hq)
         gh = torch.einsum("bchw,cj->bjhw", gy, w2q)
         ga = bf16r(gh * (a > 0).to(gh.dtype))
-        gw1 += torch.einsum("bjhw,bkhw->jk", ga, zq)
         gb1 += ga.sum(dim=(0, 2, 3))
-        gz = torch.einsum("bjhw,jk->bkhw", ga, w1q[:, :4 * C])
-        (gx,) = torch.autograd.grad(zp, xr, gz)
+        if two:
+            # dynca_tc2_bwd.cu: the coarse scale goes through GaU = U^T g_a (fp32 accumulate, rounded to bf16); the weight
+            # gradient pairs g_a with the rounded fine perception and GaU with the rounded coarse perception
+            xd = xr.detach().clone().requires_grad_(True)
+            with torch.enable_grad():
+                zf = perceive(xd, 0, mode)
+                zc = perceive_coarse(xd, mode)
+            zfq, zcq = bf16r(zf.detach()), bf16r(zc.detach())
+            gaU = _up2T_tiled_bf16(ga)
+            w1h = w1q[:, :4 * C] * 0.5
+            gw1[:, :4 * C] += 0.5 * (torch.einsum("bjhw,bkhw->jk", ga, zfq) + torch.einsum("bjhw,bkhw->jk", gaU, zcq))
+            if cond is not None:
+                gw1[:, 4 * C:] += torch.einsum("bjhw,bkhw->jk", ga, _hilo(cond))
+            gzf = torch.einsum("bjhw,jk->bkhw", ga, w1h)
+            gzc = torch.einsum("bjhw,jk->bkhw", gaU, w1h)
+            (gx,) = torch.autograd.grad([zf, zc], xd, [gzf, gzc])
+        else:
+            gw1 += torch.einsum("bjhw,bkhw->jk", ga, zq)
+            gz = torch.einsum("bjhw,jk->bkhw", ga, w1q[:, :4 * C])
+            (gx,) = torch.autograd.grad(zp, xr, gz)
         g = g + gx
     return xs[-1], dict(x0=g, w1=gw1, b1=gb1, w2=gw2, b2=gb2), xs
 

@@ -264,9 +264,6 @@ __global__ void __launch_bounds__(BT_THREADS) dynca_fwd_bf16_kernel(const DyncaB
 #define BB_TMEM_D5 272u
 #define BB_TMEM_D6 352u
 
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {   // both operands MN-major
-    return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
-}
 
 // B1t [N=K1][K=fc] (dgrad1) and B2d [N=fc][K=16] (dgrad2) operand images
 __global__ void dynca_bf16_prep_bwd_kernel(DyncaGeom g, Bf16Geom bg, const float* __restrict__ w1, const float* __restrict__ b1,

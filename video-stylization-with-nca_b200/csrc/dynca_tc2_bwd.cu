@@ -1,0 +1,757 @@
+// DyNCA BPTT step on the 5th-gen tensor cores, second generation (8x16 tiles, TMA staging; companion of dynca_tc2.cu).
+// Replaces autograd's replay of ExtraChannels/models/dynca.py:113-123 for one step:
+//   given x_t (recomputed perception / hidden layer) and g = dL/dx_{t+1}  ->  dL/dx_t and the weight gradients.
+//
+// One CTA per SM = 16 compute warps (512 threads, one 8x16 tile at a time) + 1 MMA / TMA warp.  Row r = py*16 + px of
+// every M = 128 operand is TMEM lane r; thread (r, q = tid >> 7) owns cell r and channels 4q .. 4q+3 (= 16 columns of
+// the K-permuted perception order k' = 8*(c/2) + 4*(c%2) + filter) or hidden units 32q .. 32q+31.
+//
+//   TMA   : x_t tile + ring, coarse x_t tile, g_{t+1} tile, coarse part of g_{t+1} (see below)
+//   P1    : fine perception -> A1, coarse perception -> Zc (as the forward kernel); g_y = fire * g -> bf16 Gy
+//   MMA   : Dc = Zc.W1h^T | D1 = A1.W1h^T (+ U.DcB after the Dc round trip) | D3 = Gy.W2           (recompute, dgrad 2)
+//   E1    : h = relu(D1) -> H ; g_a = D3 * [D1 > 0] -> Ga                                             (bf16 operands)
+//   MMA   : D4 += H^T.Gy (gW2) | D5 += Ga^T.A1 (gW1, fine part) | D6 = Ga.W1h (g_z fine) | GaU = U^T.Ga
+//   E2    : D6 -> zero-padded fp32 planes ; GaU -> bf16
+//   MMA   : D5 += GaU^T.Zc (gW1, coarse part) | D7 = GaU.W1h (g_z on the coarse footprint)
+//   P5/P6 : transposed perception: fine planes -> red.add into dL/dx_t ; coarse planes -> red.add into a COARSE gradient
+//           buffer gc [B,C,H/2,W/2].  The 2x2-mean transpose (0.25 * gc broadcast to the 4 fine cells) is applied when
+//           the next BPTT step reads its g tile (and once at the end for dL/dx_0), so the coarse scale costs one
+//           reduction per coarse cell instead of four.
+//   P7    : the tile of g_{t+1} (and of its coarse part) this CTA consumed is zeroed in place: those buffers are the
+//           outputs of the next launch (ping-pong), so no per-step memset is needed.
+// Weight gradients stay in TMEM (D4, D5) over all tiles of the CTA and are flushed once with red.add.
+#include "dynca_tc2.cuh"
+
+#define TB_NCOMP 512
+#define TB_NTHREADS 544
+#define TB_HDR 2048u
+// TMEM columns
+#define TB_DC 0u      // Dc, later GaU
+#define TB_D1 128u    // D1, later D6 (128..) and D7 (192..)
+#define TB_D3 256u
+#define TB_D4 384u
+#define TB_D5 400u
+// fp32 plane geometry (zero padded): fine cell (py,px) at [py+2][px+2] of [12][20]; coarse cell (qy,qx) at [qy+2][qx+2] of [10][14]
+#define TB_PR 12
+#define TB_PS 20
+#define TB_PP (TB_PR * TB_PS)
+#define TB_CPR 10
+#define TB_CPS 14
+#define TB_CPP (TB_CPR * TB_CPS)
+
+struct T2BwdArgs {
+    DyncaGeom g;
+    Bf16Geom bg;
+    const float* cond;
+    const float* x_in; const float* xc_in;            // states[t], its coarse state (border patches)
+    int slot_in, cslot_in;
+    float* g_in; float* gc_in;                        // dL/dx_{t+1} and its coarse part (read through TMA; zeroed if zero_in)
+    int zero_in, zero_cin;
+    const float* g_tap; int tap_c; float tap_scale;   // optional rgb tap at states[t+1]
+    float* g_out; float* gc_out;                      // dL/dx_t (red.add) and its coarse part (red.add)
+    const __nv_bfloat16* B1; const __nv_bfloat16* B2d; const __nv_bfloat16* U;
+    float* gW1p; float* gW2p; float* gb2p;            // fp32 accumulators, padded fp32-path layout (red.add)
+    FireMask fm;
+    int tiles_x, tiles_y, n_tiles;
+};
+
+struct TBSmem {
+    uint32_t b1, b2d, u, x, xc, gn, gcn, zc, gau, a1, dcb, gy, h, ga, px, ctr, cpx, cctr, total;
+};
+__host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16Geom& bg) {
+    TBSmem s;
+    const uint32_t C = (uint32_t)g.C, fc8 = (uint32_t)(g.fc / 8);
+    uint32_t o = TB_HDR;
+    s.b1 = o; o += bg.b1_bytes;
+    s.b2d = o; o += fc8 * 256u;
+    s.u = o; o += g.ns == 2 ? 16384u : 0u;
+    o = (o + 127u) & ~127u;
+    s.x = o; o += C * T2_XR * T2_XS * 4u;
+    o = (o + 127u) & ~127u;
+    s.xc = o; o += g.ns == 2 ? C * T2_CR * T2_CS * 4u : 0u;
+    o = (o + 127u) & ~127u;
+    s.gn = o; o += C * T2_TH * T2_TW * 4u;
+    o = (o + 127u) & ~127u;
+    s.gcn = o; o += g.ns == 2 ? C * 4u * 8u * 4u : 0u;
+    o = (o + 127u) & ~127u;
+    s.zc = o; o += g.ns == 2 ? 8192u : 0u;
+    s.gau = o; o += g.ns == 2 ? 16u * 1024u : 0u;      // 16 chunks: the M = 128 views read all of them whatever fc is
+    o = (o + 127u) & ~127u;
+    // ---- operand region, overlaid by the fp32 planes once the MMAs that read it are complete ----
+    const uint32_t base = o;
+    s.a1 = o; o += bg.a1_bytes;
+    s.dcb = o; o += g.ns == 2 ? fc8 * 1024u : 0u;
+    s.gy = o; o += 4096u;
+    s.h = o; o += 16u * 2048u;
+    s.ga = o; o += 16u * 2048u;
+    uint32_t p = base;
+    s.px = p; p += 3u * C * TB_PP * 4u;
+    s.ctr = p; p += C * T2_TH * T2_TW * 4u;
+    s.cpx = p; p += g.ns == 2 ? 3u * C * TB_CPP * 4u : 0u;
+    s.cctr = p; p += g.ns == 2 ? C * T2_QH * T2_QW * 4u : 0u;
+    s.total = (o > p ? o : p) + 1024u;      // + slack: M = 128 reads of 64-row operands run past their end
+    return s;
+}
+
+// transposed stencils at ring position (oy, ox) of zero-padded planes X, Y, L (row stride S, cell (py,px) at [py+2][px+2]):
+//   sum_{a,b} sobel_x[a][b] X[cell(oy-a, ox-b)] + sobel_y[a][b] Y[..] + (lap[a][b] + 16 delta) L[..]
+// for NR vertically adjacent outputs oy0 .. oy0+NR-1 (cells addressed relative to ring coordinates: cell row = oy - a).
+template <int NR, int S>
+__device__ __forceinline__ void tb_stencil_t(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ L,
+                                             int oy0, int ox, float out[NR]) {
+    float hx[NR + 2], hy[NR + 2];
+#pragma unroll
+    for (int k = 0; k < NR + 2; ++k) {
+        // input cell row py = oy0 - 2 + k  -> plane row py + 2 = oy0 + k ; columns px = ox - b, b = 2 - j -> ox + j
+        const int o = (oy0 + k) * S + ox;
+        const float x0 = X[o], x2 = X[o + 2];
+        const float l0 = L[o], l1 = L[o + 1], l2 = L[o + 2];
+        const float y0 = Y[o], y1 = Y[o + 1], y2 = Y[o + 2];
+        hx[k] = (x0 - x2) + fmaf(2.0f, l1, l0 + l2);
+        hy[k] = fmaf(2.0f, y1, y0 + y2);
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k)      // output oy0+k reads input rows (oy0+k) - a, a = 0,1,2 -> hx[k+2], hx[k+1], hx[k]
+        out[k] = fmaf(2.0f, hx[k + 1], hx[k] + hx[k + 2]) + (hy[k] - hy[k + 2]);
+}
+
+// image index that padded coordinate r of an axis of n cells folds back to under the TRANSPOSED padding (-1 = dropped)
+__device__ __forceinline__ int tb_fold(int r, int n, int mode) {
+    if (r >= 0 && r < n) return r;
+    if (mode == NCA_PAD_CONSTANT || r < -1 || r > n) return -1;      // only the 1-cell ring of the image carries gradient
+    if (mode == NCA_PAD_CIRCULAR) return r < 0 ? n - 1 : 0;
+    if (mode == NCA_PAD_REPLICATE) return r < 0 ? 0 : n - 1;
+    return r < 0 ? 1 : n - 2;                                         // reflect
+}
+
+template <int NS>
+__global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                        const __grid_constant__ CUtensorMap tm_xc,
+                                                                        const __grid_constant__ CUtensorMap tm_g,
+                                                                        const __grid_constant__ CUtensorMap tm_gc, const T2BwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const DyncaGeom& g = a.g;
+    const Bf16Geom& bg = a.bg;
+    const TBSmem L = tb_smem(g, bg);
+    uint64_t* barM = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);
+    uint64_t* barA = reinterpret_cast<uint64_t*>(smem + 16);
+    uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 24);
+    uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 32);
+    uint64_t* barD = reinterpret_cast<uint64_t*>(smem + 40);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48);
+    float* sFire2 = reinterpret_cast<float*>(smem + 128);               // 2 x 128 floats
+    uint32_t* sCpe2 = reinterpret_cast<uint32_t*>(smem + 128 + 1024);   // 2 x 24
+    uint8_t* sB1 = smem + L.b1;
+    uint8_t* sB2d = smem + L.b2d;
+    uint8_t* sU = smem + L.u;
+    float* sX = reinterpret_cast<float*>(smem + L.x);
+    float* sXc = reinterpret_cast<float*>(smem + L.xc);
+    float* sGn = reinterpret_cast<float*>(smem + L.gn);
+    float* sGcn = reinterpret_cast<float*>(smem + L.gcn);
+    uint8_t* sZc = smem + L.zc;
+    uint8_t* sGaU = smem + L.gau;
+    uint8_t* sA1 = smem + L.a1;
+    uint8_t* sDcB = smem + L.dcb;
+    uint8_t* sGy = smem + L.gy;
+    uint8_t* sH = smem + L.h;
+    uint8_t* sGa = smem + L.ga;
+    float* sPX = reinterpret_cast<float*>(smem + L.px);       // [3][C][12][20]: X, Y, L planes
+    float* sCtr = reinterpret_cast<float*>(smem + L.ctr);     // [C][8][16]: g + g_z(id) - 16 g_z(lap)
+    float* sCPX = reinterpret_cast<float*>(smem + L.cpx);     // [3][C][10][14]
+    float* sCCtr = reinterpret_cast<float*>(smem + L.cctr);   // [C][6][10]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = g.C, H = g.H, W = g.W, fc = g.fc;
+    const size_t plane = (size_t)H * W;
+    const int n_tiles = a.n_tiles, tiles_per_b = a.tiles_x * a.tiles_y;
+    const int N6 = 16 * ((bg.npairs + 1) / 2);                 // perception columns of g_z, padded to the MMA granularity
+    const uint32_t stage_bytes = (uint32_t)C * (T2_XR * T2_XS + T2_TH * T2_TW) * 4u +
+                                 (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u);
+
+    // ---- one-time setup ----
+    for (uint32_t i = tid; i < bg.b1_bytes / 16; i += TB_NTHREADS)
+        reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
+    for (uint32_t i = tid; i < (uint32_t)(fc / 8) * 256u / 16; i += TB_NTHREADS)
+        reinterpret_cast<uint4*>(sB2d)[i] = __ldg(reinterpret_cast<const uint4*>(a.B2d) + i);
+    if (NS == 2)
+        for (uint32_t i = tid; i < 16384u / 16; i += TB_NTHREADS)
+            reinterpret_cast<uint4*>(sU)[i] = __ldg(reinterpret_cast<const uint4*>(a.U) + i);
+    // everything an MMA may read before the tile loop writes it must be finite: clear the dynamic area once
+    for (uint32_t i = L.zc / 16 + tid; i < L.total / 16; i += TB_NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(barM, 1);
+        mbar_init(barT, 1);
+        mbar_init(barA, TB_NCOMP);
+        mbar_init(barB, TB_NCOMP);
+        mbar_init(barC, TB_NCOMP);
+        mbar_init(barD, TB_NCOMP);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) tmem_alloc(tmem_slot, 512u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 16) {
+        // =========================== MMA / TMA warp ===========================
+        const uint32_t lbo_b1 = (uint32_t)(fc / 8) * 128u;
+        const uint32_t id_fc = umma_idesc_bf16(128, fc), id_fc_bmn = id_fc | (1u << 16), id_fc_mn = umma_idesc_bf16_mn(128, fc);
+        const uint32_t id_w2 = umma_idesc_bf16_mn(128, 16), id_w1 = umma_idesc_bf16_mn(128, bg.K1), id_w1c = umma_idesc_bf16_mn(128, N6);
+        const uint32_t id_gz = umma_idesc_bf16(128, N6) | (1u << 16);
+        const uint64_t dA1 = umma_desc(smem_u32(sA1), 2048u, 128u), dB1 = umma_desc(smem_u32(sB1), lbo_b1, 128u);
+        const uint64_t dZc = umma_desc(smem_u32(sZc), 1024u, 128u), dU = umma_desc(smem_u32(sU), 2048u, 128u);
+        const uint64_t dDcB = umma_desc(smem_u32(sDcB), 128u, 1024u);
+        const uint64_t dGy = umma_desc(smem_u32(sGy), 2048u, 128u), dB2d = umma_desc(smem_u32(sB2d), lbo_b1, 128u);
+        // MN-major views (cells / coarse cells / hidden units become K): LBO = 128 (K groups), SBO = group stride of MN
+        const uint64_t dHt = umma_desc(smem_u32(sH), 128u, 2048u), dGat = umma_desc(smem_u32(sGa), 128u, 2048u);
+        const uint64_t dGyt = umma_desc(smem_u32(sGy), 128u, 2048u), dA1t = umma_desc(smem_u32(sA1), 128u, 2048u);
+        const uint64_t dUt = umma_desc(smem_u32(sU), 128u, 2048u);
+        const uint64_t dGa = umma_desc(smem_u32(sGa), 2048u, 128u);
+        const uint64_t dB1t = umma_desc(smem_u32(sB1), 128u, lbo_b1);                 // B1 as [N = k'][K = hidden]
+        const uint64_t dGaUt = umma_desc(smem_u32(sGaU), 128u, 1024u), dZct = umma_desc(smem_u32(sZc), 128u, 1024u);
+        const uint64_t dGaU = umma_desc(smem_u32(sGaU), 1024u, 128u);
+        const uint64_t sB1k = (uint64_t)((2u * lbo_b1) >> 4);
+        const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, kfsteps = fc / 16;
+        const CUtensorMap* const ptm_x = &tm_x;
+        const CUtensorMap* const ptm_xc = &tm_xc;
+        const CUtensorMap* const ptm_g = &tm_g;
+        const CUtensorMap* const ptm_gc = &tm_gc;
+        uint32_t phA = 0, phB = 0, phC = 0, phD = 0;
+        const bool leader = elect_one();
+        bool first = true;
+#define TB_ISSUE_TMA(tile_)                                                                                              \
+    do {                                                                                                                 \
+        const int tt_ = (tile_);                                                                                         \
+        const int tb_ = tt_ / tiles_per_b, ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
+        mbar_expect_tx(barT, stage_bytes);                                                                               \
+        tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
+        tma_load_5d(sGn, ptm_g, barT, tx_, ty_, 0, tb_, 0);                                                              \
+        if (NS == 2) {                                                                                                   \
+            tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                          \
+            tma_load_5d(sGcn, ptm_gc, barT, tx_ >> 1, ty_ >> 1, 0, tb_, 0);                                              \
+        }                                                                                                                \
+    } while (0)
+        if (leader && (int)blockIdx.x < n_tiles) TB_ISSUE_TMA(blockIdx.x);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(barA, phA);
+            phA ^= 1u;
+            tc_fence_after();
+            if (leader) {
+                if (NS == 2) {
+#pragma unroll 4
+                    for (int ks = 0; ks < kcsteps; ++ks)
+                        umma_ss(tmem_base + TB_DC, dZc + (uint64_t)(ks * (2048 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
+                    umma_commit(barM);
+                }
+#pragma unroll 5
+                for (int ks = 0; ks < k1steps; ++ks)
+                    umma_ss(tmem_base + TB_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
+                umma_ss(tmem_base + TB_D3, dGy, dB2d, id_fc, false);
+                if (NS == 1) umma_commit(barM);
+                if (tile + (int)gridDim.x < n_tiles) TB_ISSUE_TMA(tile + gridDim.x);     // the stage is free
+            }
+            if (NS == 2) {
+                mbar_wait(barB, phB);
+                phB ^= 1u;
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_ss(tmem_base + TB_D1, dU + (uint64_t)(ks * (4096 >> 4)), dDcB + (uint64_t)(ks * (256 >> 4)), id_fc_bmn, true);
+                    umma_commit(barM);
+                }
+            }
+            mbar_wait(barC, phC);                              // H, Ga written; D1 / D3 / Dc consumed; stage consumed
+            phC ^= 1u;
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {               // 16 cells per instruction
+                    const uint64_t o = (uint64_t)(ks * (256 >> 4));
+                    umma_ss(tmem_base + TB_D4, dHt + o, dGyt + o, id_w2, !(first && ks == 0));
+                    umma_ss(tmem_base + TB_D5, dGat + o, dA1t + o, id_w1, !(first && ks == 0));
+                }
+#pragma unroll 8
+                for (int ks = 0; ks < kfsteps; ++ks)           // D6 = Ga . W1h  (g_z of the fine scale)
+                    umma_ss(tmem_base + TB_D1, dGa + (uint64_t)(ks * (4096 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
+                if (NS == 2) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {           // GaU = U^T . Ga
+                        const uint64_t o = (uint64_t)(ks * (256 >> 4));
+                        umma_ss(tmem_base + TB_DC, dUt + o, dGat + o, id_fc_mn, ks > 0);
+                    }
+                }
+                umma_commit(barM);
+            }
+            first = false;
+            if (NS == 2) {
+                mbar_wait(barD, phD);                          // GaU (bf16) written
+                phD ^= 1u;
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {           // D5[:, perception columns] += GaU^T . Zc
+                        const uint64_t o = (uint64_t)(ks * (256 >> 4));
+                        umma_ss(tmem_base + TB_D5, dGaUt + o, dZct + o, id_w1c, true);
+                    }
+#pragma unroll 8
+                    for (int ks = 0; ks < kfsteps; ++ks)       // D7 = GaU . W1h  (g_z on the coarse footprint)
+                        umma_ss(tmem_base + TB_D1 + 64u, dGaU + (uint64_t)(ks * (2048 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
+                    umma_commit(barM);
+                }
+            }
+        }
+    } else {
+        // =========================== compute warps ===========================
+        const int r = tid & 127, qtr = tid >> 7;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t row_off = (uint32_t)r * 16u;
+        const int py = r >> 4, px = r & 15;
+        uint32_t phM = 0, phT = 0;
+        float b2acc[4] = {0.f, 0.f, 0.f, 0.f};
+#define TB_TABLES(tile_, buf_)                                                                                           \
+    do {                                                                                                                 \
+        const int tt_ = (tile_);                                                                                         \
+        const int tb_ = tt_ / tiles_per_b, ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
+        if (g.cond_kind == NCA_COND_CPE && warp == 15 && lane < T2_TH + T2_TW) {                                         \
+            const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow); \
+            const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_)); \
+            sCpe2[(buf_) * 24 + lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16); \
+        }                                                                                                                \
+        if (!a.fm.supplied && warp == 14) t2_fire_tile(a.fm, tb_, ty_, tx_, H, W, lane, sFire2 + (buf_) * 128);          \
+    } while (0)
+        if ((int)blockIdx.x < n_tiles) TB_TABLES(blockIdx.x, 0);
+        bar_sync_n(1, TB_NCOMP);
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+            const int b = tile / tiles_per_b;
+            const int y0 = ((tile / a.tiles_x) % a.tiles_y) * T2_TH, x0 = (tile % a.tiles_x) * T2_TW;
+            const int gy = y0 + py, gx = x0 + px;
+            const bool inimg = gy < H && gx < W;
+            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W;
+            const float* sFire = sFire2 + (iter & 1) * 128;
+            const uint32_t* sCpe = sCpe2 + (iter & 1) * 24;
+            mbar_wait(barT, phT);
+            phT ^= 1u;
+            if (border && g.pad != NCA_PAD_CONSTANT) {
+                t2_patch_border<NS, TB_NCOMP>(g, a.x_in, a.xc_in, b, y0, x0, sX, sXc);
+                bar_sync_n(1, TB_NCOMP);
+            }
+            // ---- P1: perception operands ----
+            t2_fine_to_a1<16>(sX, sA1, C, bg.npairs, warp, lane);
+            if (qtr == 0) {
+                uint4 cv;
+                if (g.cond_kind == NCA_COND_CPE) {
+                    const uint32_t ry = sCpe[py], cx = sCpe[T2_TH + px];
+                    cv = make_uint4((ry & 0xffffu) | (cx << 16), 0x3F803F80u, (ry >> 16) | (cx & 0xffff0000u), 0u);
+                    if (!inimg) cv = make_uint4(0, 0, 0, 0);      // rows of A1 are summed over cells by the weight-gradient MMA
+                } else {
+                    cv = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
+                }
+                *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = cv;
+            } else if (qtr == 1) {
+                for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
+                    *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
+            }
+            if (NS == 2) t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
+            // ---- g = dL/dx_{t+1} of this thread's 4 channels (+ coarse part, + tap) ; g_y = fire * g -> Gy ----
+            float gn[4];
+            {
+                const float fire = a.fm.supplied ? (inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f) : sFire[r];
+                float gyv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = 4 * qtr + i;
+                    float v = 0.0f;
+                    if (c < C) {
+                        v = sGn[(c * T2_TH + py) * T2_TW + px];
+                        if (NS == 2) v = fmaf(0.25f, sGcn[(c * 4 + (py >> 1)) * 8 + (px >> 1)], v);
+                        if (a.g_tap != nullptr && c < a.tap_c && inimg)
+                            v = fmaf(a.tap_scale, __ldg(a.g_tap + ((size_t)b * a.tap_c + c) * plane + (size_t)gy * W + gx), v);
+                    }
+                    gn[i] = v;
+                    gyv[i] = fire * v;
+                    b2acc[i] += gyv[i];
+                }
+                uint2 pk;
+                pk.x = pack_bf16(gyv[0], gyv[1]); pk.y = pack_bf16(gyv[2], gyv[3]);
+                *reinterpret_cast<uint2*>(sGy + (uint32_t)(qtr >> 1) * 2048u + row_off + (uint32_t)(qtr & 1) * 8u) = pk;
+            }
+            if (tile + (int)gridDim.x < n_tiles) TB_TABLES(tile + gridDim.x, (iter + 1) & 1);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(barA);
+            if (NS == 2) {
+                mbar_wait(barM, phM);
+                phM ^= 1u;
+                tc_fence_after();
+                // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
+                if ((warp & 3) < 2 && 32 * qtr < fc) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)qtr, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                        o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                        o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                        o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                        *reinterpret_cast<uint4*>(sDcB + (uint32_t)(4 * qtr + qq) * 1024u + row_off) = o;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(barB);
+            }
+            mbar_wait(barM, phM);
+            phM ^= 1u;
+            tc_fence_after();
+            // ---- E1: h = relu(D1), g_a = D3 * [D1 > 0] -> bf16 operands; thread -> hidden units 32q .. 32q+31 ----
+            if (32 * qtr < fc) {
+                uint32_t av[32], gv[32];
+                tmem_ld32(tmem_lane + TB_D1 + 32u * (uint32_t)qtr, av);
+                tmem_ld32(tmem_lane + TB_D3 + 32u * (uint32_t)qtr, gv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint4 o, p;
+                    o.x = pack_bf16_relu(__uint_as_float(av[qq * 8 + 0]), __uint_as_float(av[qq * 8 + 1]));
+                    o.y = pack_bf16_relu(__uint_as_float(av[qq * 8 + 2]), __uint_as_float(av[qq * 8 + 3]));
+                    o.z = pack_bf16_relu(__uint_as_float(av[qq * 8 + 4]), __uint_as_float(av[qq * 8 + 5]));
+                    o.w = pack_bf16_relu(__uint_as_float(av[qq * 8 + 6]), __uint_as_float(av[qq * 8 + 7]));
+                    float ga[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ga[i] = __uint_as_float(av[qq * 8 + i]) > 0.0f ? __uint_as_float(gv[qq * 8 + i]) : 0.0f;
+                    p.x = pack_bf16(ga[0], ga[1]); p.y = pack_bf16(ga[2], ga[3]); p.z = pack_bf16(ga[4], ga[5]); p.w = pack_bf16(ga[6], ga[7]);
+                    *reinterpret_cast<uint4*>(sH + (uint32_t)(4 * qtr + qq) * 2048u + row_off) = o;
+                    *reinterpret_cast<uint4*>(sGa + (uint32_t)(4 * qtr + qq) * 2048u + row_off) = p;
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(barC);
+            mbar_wait(barM, phM);                              // D4, D5 (fine), D6, GaU complete; operand region is free
+            phM ^= 1u;
+            tc_fence_after();
+            if (NS == 2) {
+                // ---- GaU (rows 0..63) -> bf16 -> [(j/8)*1024 + q*16]: K-major A of D7, MN-major A of the gW1 coarse part ----
+                if ((warp & 3) < 2 && 32 * qtr < fc) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)qtr, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                        o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                        o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                        o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                        *reinterpret_cast<uint4*>(sGaU + (uint32_t)(4 * qtr + qq) * 1024u + row_off) = o;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(barD);
+            }
+            // ---- E2: D6 -> fp32 planes (overlay the operand region) ----
+            {
+                // zero ring of the fine planes: rows 0,1,10,11 and columns 0,1,18,19 of rows 2..9
+                for (int i = tid; i < 3 * C * 28; i += TB_NCOMP) {
+                    float* pl = sPX + (i / 28) * TB_PP;
+                    const int k = i % 28;
+                    if (k < 20) {            // 4 full rows, as float4
+                        const int row = k / 5 < 2 ? k / 5 : 8 + k / 5;
+                        *reinterpret_cast<float4*>(pl + row * TB_PS + 4 * (k % 5)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {                 // rows 2..9: columns 0,1 and 18,19
+                        const int row = 2 + (k - 20);
+                        *reinterpret_cast<float2*>(pl + row * TB_PS) = make_float2(0.f, 0.f);
+                        *reinterpret_cast<float2*>(pl + row * TB_PS + 18) = make_float2(0.f, 0.f);
+                    }
+                }
+                if (16 * qtr < N6) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_lane + TB_D1 + 16u * (uint32_t)qtr, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = 4 * qtr + i;
+                        if (c < C) {
+                            const int o = (c * TB_PR + py + 2) * TB_PS + px + 2;
+                            const float lp = __uint_as_float(v[4 * i + 3]);
+                            sPX[o] = __uint_as_float(v[4 * i + 1]);
+                            sPX[C * TB_PP + o] = __uint_as_float(v[4 * i + 2]);
+                            sPX[2 * C * TB_PP + o] = lp;
+                            sCtr[(c * T2_TH + py) * T2_TW + px] = fmaf(-16.0f, lp, gn[i] + __uint_as_float(v[4 * i + 0]));
+                        }
+                    }
+                }
+            }
+            // ---- P7 (early): zero the consumed tile of g_{t+1} in global memory (it is the output of the next launch) ----
+            if (a.zero_in) {
+                const int c = tid >> 5, rr = (tid >> 2) & 7, x4 = (tid & 3) * 4;
+                if (c < C && y0 + rr < H && x0 + x4 < W)
+                    *reinterpret_cast<float4*>(a.g_in + ((size_t)b * C + c) * plane + (size_t)(y0 + rr) * W + x0 + x4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (NS == 2 && a.zero_cin && tid < 128) {
+                const int c = tid >> 3, rr = (tid >> 1) & 3, x4 = (tid & 1) * 4;
+                if (c < C && (y0 >> 1) + rr < (H >> 1) && (x0 >> 1) + x4 < (W >> 1))
+                    *reinterpret_cast<float4*>(a.gc_in + ((size_t)b * C + c) * (plane >> 2) + (size_t)((y0 >> 1) + rr) * (W >> 1) + (x0 >> 1) + x4) =
+                        make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            bar_sync_n(1, TB_NCOMP);
+            // ---- P5: transposed fine perception -> red.add into dL/dx_t.  warp = channel, lane = (5-row block, column) ----
+            {
+                const int c = warp;
+                if (c < C) {
+                    const float* X = sPX + c * TB_PP;
+                    const float* Y = X + C * TB_PP;
+                    const float* Lp = Y + C * TB_PP;
+                    float* gob = a.g_out + ((size_t)b * C + c) * plane;
+                    {
+                        const int vb = lane >> 4, ox = (lane & 15) + 1;      // ring column of the interior cell
+                        float out[5];
+                        tb_stencil_t<5, TB_PS>(X, Y, Lp, 5 * vb, ox, out);
+                        const int xx = x0 + ox - 1;
+                        const int tx = tb_fold(xx, W, g.pad);
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            const int oy = 5 * vb + k, yy = y0 - 1 + oy;
+                            float v = out[k];
+                            if (oy >= 1 && oy <= T2_TH) v += sCtr[(c * T2_TH + oy - 1) * T2_TW + ox - 1];
+                            const int ty = tb_fold(yy, H, g.pad);
+                            if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, v);
+                        }
+                    }
+                    if (lane < 20) {     // the two ring columns: 10 rows x 2 sides
+                        const int oy = lane >> 1, ox = (lane & 1) ? T2_TW + 1 : 0;
+                        float out[1];
+                        tb_stencil_t<1, TB_PS>(X, Y, Lp, oy, ox, out);
+                        const int yy = y0 - 1 + oy, xx = x0 - 1 + ox;
+                        const int ty = tb_fold(yy, H, g.pad), tx = tb_fold(xx, W, g.pad);
+                        if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[0]);
+                    }
+                }
+            }
+            if (NS == 2) {
+                mbar_wait(barM, phM);                          // D5 coarse part, D7 complete
+                phM ^= 1u;
+                tc_fence_after();
+                // ---- D7 -> coarse planes (zero padded [10][14], footprint cell (qy,qx) at [qy+2][qx+2]) ----
+                for (int i = tid; i < 3 * C * TB_CPP / 2; i += TB_NCOMP) reinterpret_cast<float2*>(sCPX)[i] = make_float2(0.f, 0.f);
+                bar_sync_n(1, TB_NCOMP);
+                if ((warp & 3) < 2 && 16 * qtr < N6) {      // warp-uniform: the TMEM load is .sync.aligned
+                    uint32_t v[16];
+                    const int qy = r / T2_QW, qx = r % T2_QW;
+                    tmem_ld16(tmem_lane + TB_D1 + 64u + 16u * (uint32_t)qtr, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = 4 * qtr + i;
+                        if (c < C && r < T2_QH * T2_QW) {
+                            const int o = (c * TB_CPR + qy + 2) * TB_CPS + qx + 2;
+                            const float lp = __uint_as_float(v[4 * i + 3]);
+                            sCPX[o] = __uint_as_float(v[4 * i + 1]);
+                            sCPX[C * TB_CPP + o] = __uint_as_float(v[4 * i + 2]);
+                            sCPX[2 * C * TB_CPP + o] = lp;
+                            sCCtr[(c * T2_QH + qy) * T2_QW + qx] = fmaf(-16.0f, lp, __uint_as_float(v[4 * i + 0]));
+                        }
+                    }
+                }
+                bar_sync_n(1, TB_NCOMP);
+                const int Hc = H >> 1, Wc = W >> 1;
+                const int cy0 = (y0 >> 1) - 1, cx0 = (x0 >> 1) - 1;          // coarse coordinates of footprint cell (0,0)
+                if (border) {
+                    // transpose of the replicate extension: footprint cells outside the image fold into the clamped cell
+                    // (rows first, then columns; one thread per (array, channel, column / row) so nothing races)
+                    for (int i = tid; i < 4 * C * T2_QW; i += TB_NCOMP) {
+                        const int qx = i % T2_QW, c = (i / T2_QW) % C, arr = i / (T2_QW * C);
+                        float* base = arr < 3 ? sCPX + (arr * C + c) * TB_CPP + 2 * TB_CPS + qx + 2 : sCCtr + c * T2_QH * T2_QW + qx;
+                        const int S = arr < 3 ? TB_CPS : T2_QW;
+                        for (int qy = 0; qy < T2_QH; ++qy) {
+                            const int Qy = cy0 + qy;
+                            if (Qy >= 0 && Qy < Hc) continue;
+                            const int ty = min(max(Qy, 0), Hc - 1) - cy0;
+                            if (ty >= 0 && ty < T2_QH) base[ty * S] += base[qy * S];
+                            base[qy * S] = 0.0f;
+                        }
+                    }
+                    bar_sync_n(1, TB_NCOMP);
+                    for (int i = tid; i < 4 * C * T2_QH; i += TB_NCOMP) {
+                        const int qy = i % T2_QH, c = (i / T2_QH) % C, arr = i / (T2_QH * C);
+                        float* base = arr < 3 ? sCPX + (arr * C + c) * TB_CPP + (qy + 2) * TB_CPS + 2 : sCCtr + (c * T2_QH + qy) * T2_QW;
+                        for (int qx = 0; qx < T2_QW; ++qx) {
+                            const int Qx = cx0 + qx;
+                            if (Qx >= 0 && Qx < Wc) continue;
+                            const int tx = min(max(Qx, 0), Wc - 1) - cx0;
+                            if (tx >= 0 && tx < T2_QW) base[tx] += base[qx];
+                            base[qx] = 0.0f;
+                        }
+                    }
+                    bar_sync_n(1, TB_NCOMP);
+                }
+                // ---- P6: transposed coarse perception -> red.add into the coarse gradient buffer.
+                //      warp = channel, lane = (4-row block, column of the 8 x 12 coarse ring) ----
+                {
+                    const int c = warp;
+                    if (c < C && lane < 24) {
+                        const int vb = lane / 12, ox = lane % 12;
+                        const float* X = sCPX + c * TB_CPP;
+                        const float* Y = X + C * TB_CPP;
+                        const float* Lp = Y + C * TB_CPP;
+                        float out[4];
+                        tb_stencil_t<4, TB_CPS>(X, Y, Lp, 4 * vb, ox, out);
+                        float* gcb = a.gc_out + ((size_t)b * C + c) * (plane >> 2);
+                        const int xx = cx0 - 1 + ox;
+                        const int tx = tb_fold(xx, Wc, g.pad);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int oy = 4 * vb + k, yy = cy0 - 1 + oy;
+                            float v = out[k];
+                            if (oy >= 1 && oy <= T2_QH && ox >= 1 && ox <= T2_QW) v += sCCtr[(c * T2_QH + oy - 1) * T2_QW + ox - 1];
+                            const int ty = tb_fold(yy, Hc, g.pad);
+                            if (ty >= 0 && tx >= 0) atomicAdd(gcb + (size_t)ty * Wc + tx, v);
+                        }
+                    }
+                }
+            }
+            bar_sync_n(1, TB_NCOMP);     // the planes overlay the operand region the next tile's P1 writes
+        }
+        // ---- flush: D4 [fc x 16] -> gW2p[j][c];  D5 [fc x K1] -> gW1p[k][j] (k' -> reference k, perception columns x s0) ----
+        {
+            const int j = (warp & 3) * 32 + lane;
+            uint32_t v[32];
+            if (qtr == 0) {
+                tmem_ld16(tmem_lane + TB_D4, v);
+                tmem_ld_wait();
+                if (j < fc)
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        if (c < C) atomicAdd(a.gW2p + j * g.CP + c, __uint_as_float(v[c]));
+            } else {
+                const int k0 = 32 * (qtr - 1);      // qtr 1: 0..31, 2: 32..63, 3: 64..79
+                if (k0 < bg.K1) {
+                    if (bg.K1 - k0 >= 32) tmem_ld32(tmem_lane + TB_D5 + (uint32_t)k0, v);
+                    else tmem_ld16(tmem_lane + TB_D5 + (uint32_t)k0, v);
+                    tmem_ld_wait();
+                    if (j < fc) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int kp = k0 + i;
+                            if (kp >= bg.K1 || (i >= 16 && bg.K1 - k0 < 32)) continue;
+                            const int kc = kp >> 3, s = kp & 7;
+                            int k = -1;
+                            float sc = 1.0f;
+                            if (kc < bg.npairs) { const int c = 2 * kc + (s >> 2); if (c < C) { k = (s & 3) * C + c; sc = g.s0; } }
+                            else if (kc == bg.npairs) { const int src = dynca_cond_slot_src(g.cc, s); if (src >= 0) k = 4 * C + src; else if (src == -2) k = g.P; }
+                            if (k >= 0) atomicAdd(a.gW1p + k * g.FCpad + j, sc * __uint_as_float(v[i]));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = b2acc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && 4 * qtr + i < C) atomicAdd(a.gb2p + 4 * qtr + i, s);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem_base, 512u);
+}
+
+// dL/dx_0 += 0.25 * coarse part (transpose of the 2x2 mean), once per rollout
+__global__ void dynca_tc2_add_coarse_kernel(int BC, int H, int W, const float* __restrict__ gc, float* __restrict__ gx) {
+    const size_t n = (size_t)BC * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        const size_t bc = i / ((size_t)W * H);
+        gx[i] = fmaf(0.25f, __ldg(gc + (bc * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)), gx[i]);
+    }
+}
+
+// B2d [N = fc][K = 16] operand image of the dgrad-2 GEMM (D3 = Gy . W2)
+__global__ void dynca_tc2_prep_b2d_kernel(DyncaGeom g, const float* __restrict__ w2, __nv_bfloat16* __restrict__ B2d) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.fc * 16; i += gridDim.x * blockDim.x) {
+        const int j = i / 16, c = i % 16;
+        const float v = c < g.C ? w2[c * g.fc + j] : 0.0f;
+        B2d[(size_t)(c >> 3) * (g.fc / 8) * 64 + (size_t)(j >> 3) * 64 + (j & 7) * 8 + (c & 7)] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+bool dynca_tc2_bwd_supported(const DyncaGeom& g) {
+    Bf16Geom bg;
+    if (!dynca_tc2_supported(g)) return false;
+    if (dynca_bf16_geom(g, &bg)) return false;
+    return tb_smem(g, bg).total <= 227u * 1024u;
+}
+
+// operand images: [forward block of dynca_tc2_prep_weights (B1 | B2 | b2 | U)] then B2d
+size_t dynca_tc2_bwd_weight_bytes(const DyncaGeom& g) {
+    const size_t f = dynca_tc2_weight_bytes(g);
+    return f ? f + nca_align_up((size_t)(g.fc / 8) * 256, 256) : 0;
+}
+
+int dynca_tc2_prep_bwd_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s) {
+    int rc = dynca_tc2_prep_weights(g, w, ws, s);
+    if (rc) return rc;
+    dynca_tc2_prep_b2d_kernel<<<8, 256, 0, s>>>(g, w->w2, (__nv_bfloat16*)((uint8_t*)ws + dynca_tc2_weight_bytes(g)));
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+int dynca_tc2_make_gmaps(const DyncaGeom& g, const float* gfine, const float* gcoarse, DyncaTc2Maps* m) {
+    int rc = t2_make_map((CUtensorMap*)m->x, gfine, 1, (size_t)g.B * g.C * g.H * g.W, g.B, g.C, g.H, g.W, T2_TH, T2_TW);
+    if (rc) return rc;
+    if (g.ns == 2) rc = t2_make_map((CUtensorMap*)m->xc, gcoarse, 1, (size_t)g.B * g.C * (g.H / 2) * (g.W / 2), g.B, g.C, g.H / 2, g.W / 2, 4, 8);
+    else memcpy(m->xc, m->x, sizeof(m->x));
+    return rc;
+}
+
+int dynca_tc2_add_coarse(const DyncaGeom& g, const float* gc, float* gx, cudaStream_t s) {
+    const size_t n = (size_t)g.B * g.C * g.H * g.W;
+    const int grid = (int)((n + 255) / 256 < (size_t)t2_num_sms() * 8 ? (n + 255) / 256 : (size_t)t2_num_sms() * 8);
+    dynca_tc2_add_coarse_kernel<<<grid, 256, 0, s>>>(g.B * g.C, g.H, g.W, gc, gx);
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const DyncaTc2Maps* xm, int slot_in, const float* x_in,
+                            int cslot_in, const float* xc_in, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
+                            int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out,
+                            const float* cond, const FireMask& fm, cudaStream_t s) {
+    T2BwdArgs a;
+    int rc = dynca_bf16_geom(g, &a.bg);
+    if (rc) return rc;
+    a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.slot_in = slot_in; a.cslot_in = cslot_in;
+    a.g_in = g_in; a.gc_in = gc_in; a.zero_in = zero_in; a.zero_cin = zero_cin;
+    a.g_tap = g_tap; a.tap_c = tap_c; a.tap_scale = tap_scale; a.g_out = g_out; a.gc_out = gc_out;
+    a.B1 = (const __nv_bfloat16*)ws;
+    a.U = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes + 64);
+    a.B2d = (const __nv_bfloat16*)((const uint8_t*)ws + dynca_tc2_weight_bytes(g));
+    a.gW1p = wsG; a.gW2p = a.gW1p + (size_t)g.Ppad * g.FCpad; a.gb2p = a.gW2p + (size_t)g.FCpad * g.CP;
+    a.fm = fm;
+    a.tiles_x = (g.W + T2_TW - 1) / T2_TW; a.tiles_y = (g.H + T2_TH - 1) / T2_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
+    const size_t smem = tb_smem(g, a.bg).total;
+    int grid = t2_num_sms();
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    const CUtensorMap* tx = (const CUtensorMap*)xm->x;
+    const CUtensorMap* txc = (const CUtensorMap*)xm->xc;
+    const CUtensorMap* tg = (const CUtensorMap*)gm->x;
+    const CUtensorMap* tgc = (const CUtensorMap*)gm->xc;
+    if (g.ns == 2) {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_bwd_tc2_kernel<2><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, a);
+    } else {
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dynca_bwd_tc2_kernel<1><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, a);
+    }
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}

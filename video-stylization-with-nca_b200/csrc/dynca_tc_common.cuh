@@ -77,6 +77,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {   // both operands MN-major
+    return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

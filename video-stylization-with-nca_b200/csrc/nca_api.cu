@@ -56,7 +56,7 @@ static int check_common(const NcaDyncaDesc* d, DyncaGeom* g, const float* cond, 
 // kernel variant of a description: 0 fp32, 1 tcgen05 (4x32 tiles, cp.async), 2 tcgen05 (8x16 tiles, TMA)
 static int dynca_variant(const NcaDyncaDesc* d, const DyncaGeom& g, int backward) {
     if (d->precision != NCA_PREC_BF16) return 0;
-    if (backward) return dynca_bf16_bwd_supported(g) ? 1 : 0;
+    if (backward) return dynca_tc2_bwd_supported(g) ? 2 : (dynca_bf16_bwd_supported(g) ? 1 : 0);
     return dynca_tc2_supported(g) ? 2 : 1;
 }
 int nca_dynca_kernel_variant(const NcaDyncaDesc* d, int32_t backward) {
@@ -77,8 +77,9 @@ size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward) {
     if (d->precision == NCA_PREC_BF16) {
         size_t b = backward ? dynca_bf16_bwd_weight_bytes(g) : dynca_bf16_weight_bytes(g);
         if (b == 0) return 0;
-        const size_t b2 = dynca_tc2_weight_bytes(g);
-        bytes += (b > b2 ? b : b2) + 2 * dynca_bf16_coarse_floats(g) * sizeof(float);
+        const size_t b2 = backward ? dynca_tc2_bwd_weight_bytes(g) : dynca_tc2_weight_bytes(g);
+        // coarse slots: forward 2 (ping-pong states); backward 3 (coarse state of the step + 2 coarse-gradient buffers)
+        bytes += (b > b2 ? b : b2) + (backward ? 3 : 2) * dynca_bf16_coarse_floats(g) * sizeof(float);
     }
     return bytes;
 }
@@ -185,16 +186,20 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         nca_set_error("workspace too small: %zu < %zu", workspace_bytes, nca_dynca_workspace_bytes(d, 1));
         return NCA_ERR_WORKSPACE;
     }
-    // NCA_PREC_BF16: tcgen05 BPTT kernel when the shape is supported (fc % 32 == 0, fc <= 128), else the fp32 kernel
-    const bool bf16 = dynca_variant(d, g, 1) != 0;
+    // NCA_PREC_BF16: tcgen05 BPTT kernels when the shape is supported (variant 2: 8x16 tiles + TMA, variant 1: 4x32 tiles),
+    // else the fp32 kernel
+    const int variant = dynca_variant(d, g, 1);
+    const bool bf16 = variant != 0;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)g.B * g.C * g.H * g.W, nb = n * sizeof(float);
     float* wsW = (float*)workspace;
     float* wsG = wsW + dynca_f32_weight_floats(g);
     float* gbuf[2] = {wsG + dynca_f32_grad_floats(g), wsG + dynca_f32_grad_floats(g) + nca_align_up(n, 64)};
     void* wsB = (void*)(gbuf[1] + nca_align_up(n, 64));
-    float* wsXc = (float*)((uint8_t*)wsB + dynca_bf16_bwd_weight_bytes(g));
-    rc = bf16 ? dynca_bf16_prep_bwd_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s);
+    const size_t imgb = dynca_bf16_bwd_weight_bytes(g) > dynca_tc2_bwd_weight_bytes(g) ? dynca_bf16_bwd_weight_bytes(g) : dynca_tc2_bwd_weight_bytes(g);
+    float* wsXc = (float*)((uint8_t*)wsB + imgb);
+    const size_t nc = dynca_bf16_coarse_floats(g), ncx = (size_t)g.B * g.C * (g.H / 2) * (g.W / 2);
+    rc = variant == 2 ? dynca_tc2_prep_bwd_weights(g, w, wsB, s) : (variant == 1 ? dynca_bf16_prep_bwd_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s));
     if (rc) return rc;
     NCA_CUDA_OK(cudaMemsetAsync(wsG, 0, dynca_f32_grad_floats(g) * sizeof(float), s));
     int ti = n_taps - 1;   // taps are consumed from the last step backwards
@@ -202,6 +207,44 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         // gx0 = g_final + tap at states[0] is not defined (taps are for t = 1..T): plain copy
         if (g_final) NCA_CUDA_OK(cudaMemcpyAsync(gx0, g_final, nb, cudaMemcpyDeviceToDevice, s));
         else NCA_CUDA_OK(cudaMemsetAsync(gx0, 0, nb, s));
+    }
+    if (variant == 2 && T > 0) {
+        // ping-pong gradient buffers F[p] (fine) / G[p] (coarse part); each launch zeroes the tile of its input it consumed,
+        // so only the initial state needs memsets
+        float* F[2] = {gbuf[0], gbuf[1]};
+        float* G[2] = {wsXc + nc, wsXc + 2 * nc};
+        NCA_CUDA_OK(cudaMemsetAsync(F[0], 0, nb, s));
+        NCA_CUDA_OK(cudaMemsetAsync(F[1], 0, nb, s));
+        NCA_CUDA_OK(cudaMemsetAsync(gx0, 0, nb, s));
+        if (g.ns == 2) NCA_CUDA_OK(cudaMemsetAsync(G[0], 0, 2 * nc * sizeof(float), s));
+        const bool chist = coarse_hist != nullptr && g.ns == 2;
+        DyncaTc2Maps xm, gm_final, gm[2];
+        rc = dynca_tc2_make_maps(g, states, T + 1, chist ? coarse_hist : wsXc, chist ? T + 1 : 1, ncx, &xm);
+        if (rc) return rc;
+        for (int p = 0; p < 2; ++p) { rc = dynca_tc2_make_gmaps(g, F[p], G[p], &gm[p]); if (rc) return rc; }
+        if (g_final) { rc = dynca_tc2_make_gmaps(g, g_final, G[1], &gm_final); if (rc) return rc; }
+        int p_in = 1;          // buffer index feeding the current step (step T-1 reads g_final or the zero buffer F[1], and G[1])
+        for (int t = T - 1; t >= 0; --t) {
+            FireMask fm = make_mask(d, g, masks, seed, t);
+            fm.t = (uint32_t)(t0 + t);
+            const bool from_final = (t == T - 1) && g_final != nullptr;
+            const int p_out = 1 - p_in;
+            float* gout = t == 0 ? gx0 : F[p_out];
+            const float* tap = nullptr;
+            if (ti >= 0 && tap_steps[ti] == t + 1) tap = g_taps[ti--];
+            const float* xc_t = nullptr;
+            if (g.ns == 2) {
+                if (chist) xc_t = coarse_hist + (size_t)t * ncx;
+                else { rc = dynca_bf16_coarsen(g, states + (size_t)t * n, wsXc, s); if (rc) return rc; xc_t = wsXc; }
+            }
+            rc = dynca_tc2_backward_step(g, wsB, wsG, &xm, t, states + (size_t)t * n, chist ? t : 0, xc_t,
+                                         from_final ? &gm_final : &gm[p_in], from_final ? const_cast<float*>(g_final) : F[p_in], G[p_in],
+                                         from_final ? 0 : 1, 1, tap, tap_c, tap_scale, gout, G[p_out], cond, fm, s);
+            if (rc) return rc;
+            p_in = p_out;
+        }
+        if (g.ns == 2) { rc = dynca_tc2_add_coarse(g, G[p_in], gx0, s); if (rc) return rc; }
+        return dynca_f32_unpack_grads(g, wsG, gw, s);
     }
     const float* gnext = g_final;   // NULL = zeros
     for (int t = T - 1; t >= 0; --t) {
