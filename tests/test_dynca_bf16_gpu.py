@@ -156,3 +156,39 @@ def test_bf16_backward_full_size_properties():
     for i in range(5):
         assert float(z[i].abs().max()) == 0.0                       # zero in -> exactly zero out
         assert float((a[i] - f[i]).norm() / f[i].norm()) < FP32_GRAD_RMS_TOL, i
+
+
+EMU_SHAPES = [  # B, C, fc, H, W, T, pad, scales, cond  (all dispatch to the 8x16-tile TMA kernels: W % 8 == 0)
+    (1, 16, 128, 18, 40, 2, "replicate", (0, 1), "cpe"),
+    (2, 12, 96, 26, 48, 2, "circular", (0, 1), None),
+    (1, 16, 128, 16, 32, 3, "reflect", (0, 1), "cpe"),
+    (1, 13, 96, 12, 24, 2, "constant", (0, 1), "tensor"),
+    (1, 14, 64, 20, 24, 2, "circular", (0,), "tensor"),
+]
+
+
+@pytest.mark.parametrize("case", EMU_SHAPES, ids=lambda c: "B%d_C%d_fc%d_%dx%d_T%d_%s_s%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], len(c[7]), c[8]))
+def test_tc2_ragged_shapes_vs_emulated_oracle(case):
+    """forward + BPTT of the 8x16-tile kernels on shapes with partial tiles / coarse rings leaving the image"""
+    B, C, fc, H, W, T, pad, scales, cond = case
+    g = torch.Generator().manual_seed(77)
+    cc = {"cpe": 2, None: 0, "tensor": 3}[cond]
+    w1 = torch.randn(fc, 4 * C + cc, generator=g) * 0.15
+    b1 = torch.randn(fc, generator=g) * 0.1
+    w2 = torch.randn(C, fc, generator=g) * 0.1
+    b2 = torch.randn(C, generator=g) * 0.02
+    x0 = torch.rand(B, C, H, W, generator=g) - 0.5
+    masks = (torch.rand(T, B, 1, H, W, generator=g) + 0.5).floor()
+    cf = torch.randn(B, C, H, W, generator=g)
+    cond_t = O.cpe2d(B, H, W) if cond == "cpe" else (torch.randn(B, 3, H, W, generator=g) if cond == "tensor" else None)
+    kind = {"cpe": _lib.NCA_COND_CPE, None: _lib.NCA_COND_NONE, "tensor": _lib.NCA_COND_TENSOR}[cond]
+    cfg = Fn.DyncaConfig(C, fc, pad, list(scales), kind, cc, precision="bf16")
+    fv, bv = (Fn.dynca_kernel_variant(cfg, B, H, W, backward=bw) for bw in (False, True))
+    assert (fv, bv) == (2, 2)
+    fe, ge, _ = O.dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, pad, cond_t, cf, {}, fv, bv)
+    pg = [p.clone().to(DEV).requires_grad_(True) for p in (x0, w1, b1, w2, b2)]
+    fg, _ = Fn.dynca_rollout(cfg, *pg, T, 0.5, cond=cond_t.to(DEV) if cond == "tensor" else None, masks=masks.to(DEV))
+    (fg * cf.to(DEV)).sum().backward()
+    assert rel_err(fg.detach().cpu(), fe) < EMU_STATE_TOL
+    for a, n in zip(pg, ("x0", "w1", "b1", "w2", "b2")):
+        assert float((a.grad.cpu() - ge[n]).norm() / (ge[n].norm() + 1e-30)) < EMU_GRAD_RMS_TOL, n

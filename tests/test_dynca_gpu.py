@@ -114,6 +114,9 @@ ORACLE_CASES = [
     (1, 12, 96, 10, 6, 2, "constant", (0, 1), "tensor"),
     (1, 8, 32, 4, 4, 2, "circular", (0, 1), None),             # tiny
     (1, 12, 96, 2, 66, 2, "replicate", (0, 1), "cpe"),         # one coarse row
+    (1, 16, 128, 18, 40, 2, "replicate", (0, 1), "cpe"),       # 8x16 tiles: coarse ring leaves the image on a non-edge tile
+    (2, 12, 96, 26, 48, 2, "circular", (0, 1), None),
+    (1, 14, 64, 20, 24, 2, "reflect", (0,), "tensor"),
 ]
 
 

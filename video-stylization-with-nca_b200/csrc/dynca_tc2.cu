@@ -27,7 +27,7 @@ struct T2FwdArgs {
     int slot_in, cslot_in;  // slot coordinates of x_in / xc_in in the tensor maps
     const __nv_bfloat16* B1; const __nv_bfloat16* B2; const float* b2p; const __nv_bfloat16* U;
     FireMask fm;
-    int tiles_x, tiles_y, n_tiles;
+    T2Tiles tl;
     int dbg;
     long long* tdbg;   // optional phase timestamps of CTA 0 (debug)
 };
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     const size_t plane = (size_t)H * W;
     const uint32_t stage_bytes = (uint32_t)C * T2_XR * T2_XS * 4u + (NS == 2 ? (uint32_t)C * T2_CR * T2_CS * 4u : 0u);
     const uint32_t tmem_cols = NS == 2 ? 256u : 128u;
-    const int n_tiles = a.n_tiles, tiles_per_b = a.tiles_x * a.tiles_y;
+    const int n_tiles = a.tl.n_tiles;
 
     // ---- one-time setup ----
     for (uint32_t i = tid; i < bg.b1_bytes / 16; i += T2_NTHREADS)
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
 #define T2_ISSUE_TMA(tile_)                                                                                              \
     do {                                                                                                                 \
         const int tt_ = (tile_);                                                                                         \
-        const int tb_ = tt_ / tiles_per_b, ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
+        int tb_, ty_, tx_;                                                                                               \
+        t2_tile_decode(a.tl, tt_, tb_, ty_, tx_);                                                                        \
         mbar_expect_tx(barT, stage_bytes);                                                                               \
         tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
         if (NS == 2) tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                 \
@@ -201,7 +202,8 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     do {                                                                                                                 \
         if (g.cond_kind == NCA_COND_CPE && warp == 7 && lane < T2_TH + T2_TW) {                                          \
             const int tt_ = (tile_);                                                                                     \
-            const int ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW;                    \
+            int tb_, ty_, tx_;                                                                                           \
+            t2_tile_decode(a.tl, tt_, tb_, ty_, tx_);                                                                    \
             const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow); \
             const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_)); \
             sCpe2[(buf_) * 24 + lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16); \
@@ -212,11 +214,14 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
 #define T2_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
-            const int b = tile / tiles_per_b;
-            const int y0 = ((tile / a.tiles_x) % a.tiles_y) * T2_TH, x0 = (tile % a.tiles_x) * T2_TW;
+            int b, y0, x0;
+            t2_tile_decode(a.tl, tile, b, y0, x0);
             const int gy = y0 + py, gx = x0 + px;
             const bool inimg = gy < H && gx < W;
-            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W;
+            // border tile: some staged position (fine ring, or the coarse tile whose ring reaches 4 fine cells further) lies
+            // outside the image
+            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
+                                (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
             float* sFire = sFire2 + (iter & 1) * 128;
             const uint32_t* sCpe = sCpe2 + (iter & 1) * 24;
             T2_STAMP(0);
@@ -472,14 +477,14 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     const bool timing = getenv("NCA_T2_TDBG") != nullptr;
     if (timing && !tdbg) { cudaMalloc(&tdbg, 256 * sizeof(long long)); }
     a.tdbg = timing ? tdbg : nullptr;
-    a.tiles_x = (g.W + T2_TW - 1) / T2_TW; a.tiles_y = (g.H + T2_TH - 1) / T2_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
+    a.tl = t2_make_tiles(g.B, g.H, g.W);
     const size_t smem = t2_smem(g, a.bg).total;
     const uint32_t tcols = g.ns == 2 ? 256u : 128u;
     int occ = (int)((227 * 1024) / (smem + 1024));
     if (occ > (int)(512u / tcols)) occ = (int)(512u / tcols);
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;
-    if (grid > a.n_tiles) grid = a.n_tiles;
+    if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
     const CUtensorMap* tx = (const CUtensorMap*)m->x;
     const CUtensorMap* txc = (const CUtensorMap*)m->xc;
     if (g.ns == 2) {

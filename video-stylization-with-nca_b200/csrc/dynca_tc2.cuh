@@ -8,6 +8,7 @@
 
 #define T2_TH 8
 #define T2_TW 16
+
 // TMA (fp32, no swizzle) needs the innermost box coordinate to be a multiple of 4 elements (16 bytes; measured: any
 // other start raises an illegal-instruction fault), so the boxes start 4 columns left of the tile: fine box columns
 // x0-4 .. x0+19 (ring column x0-1 at index T2_XO), coarse box columns x0/2-4 .. x0/2+11 (footprint column x0/2-2 at T2_CO)
@@ -21,6 +22,27 @@
 #define T2_QW 10
 #define T2_THREADS 256
 #define T2_HDR 1536u
+
+// tile index -> (sample, y0, x0) without runtime integer division: q = floor(n / d) = umul64hi(n, ceil(2^64 / d))
+struct T2Tiles {
+    int tiles_x, tiles_y, n_tiles, per_b;
+    unsigned long long mx, mb;      // ceil(2^64 / tiles_x), ceil(2^64 / per_b); 0 when the divisor is 1
+};
+static inline T2Tiles t2_make_tiles(int B, int H, int W) {
+    T2Tiles t;
+    t.tiles_x = (W + T2_TW - 1) / T2_TW; t.tiles_y = (H + T2_TH - 1) / T2_TH;
+    t.per_b = t.tiles_x * t.tiles_y; t.n_tiles = B * t.per_b;
+    t.mx = t.tiles_x == 1 ? 0ull : ~0ull / (unsigned long long)t.tiles_x + 1ull;
+    t.mb = t.per_b == 1 ? 0ull : ~0ull / (unsigned long long)t.per_b + 1ull;
+    return t;
+}
+__device__ __forceinline__ void t2_tile_decode(const T2Tiles& t, int tile, int& b, int& y0, int& x0) {
+    const unsigned q1 = t.mx ? (unsigned)__umul64hi((unsigned long long)tile, t.mx) : (unsigned)tile;      // tile / tiles_x
+    const unsigned bb = t.mb ? (unsigned)__umul64hi((unsigned long long)tile, t.mb) : (unsigned)tile;      // tile / per_b
+    b = (int)bb;
+    x0 = (tile - (int)q1 * t.tiles_x) * T2_TW;
+    y0 = ((int)q1 - (int)bb * t.tiles_y) * T2_TH;
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -52,7 +52,7 @@ struct T2BwdArgs {
     const __nv_bfloat16* B1; const __nv_bfloat16* B2d; const __nv_bfloat16* U;
     float* gW1p; float* gW2p; float* gb2p;            // fp32 accumulators, padded fp32-path layout (red.add)
     FireMask fm;
-    int tiles_x, tiles_y, n_tiles;
+    T2Tiles tl;
 };
 
 struct TBSmem {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
     const size_t plane = (size_t)H * W;
-    const int n_tiles = a.n_tiles, tiles_per_b = a.tiles_x * a.tiles_y;
+    const int n_tiles = a.tl.n_tiles;
     const int N6 = 16 * ((bg.npairs + 1) / 2);                 // perception columns of g_z, padded to the MMA granularity
     const uint32_t stage_bytes = (uint32_t)C * (T2_XR * T2_XS + T2_TH * T2_TW) * 4u +
                                  (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u);
@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 #define TB_ISSUE_TMA(tile_)                                                                                              \
     do {                                                                                                                 \
         const int tt_ = (tile_);                                                                                         \
-        const int tb_ = tt_ / tiles_per_b, ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
+        int tb_, ty_, tx_;                                                                                               \
+        t2_tile_decode(a.tl, tt_, tb_, ty_, tx_);                                                                        \
         mbar_expect_tx(barT, stage_bytes);                                                                               \
         tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
         tma_load_5d(sGn, ptm_g, barT, tx_, ty_, 0, tb_, 0);                                                              \
@@ -311,10 +312,25 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const int py = r >> 4, px = r & 15;
         uint32_t phM = 0, phT = 0;
         float b2acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // zero ring of the fine planes (rows 0,1,10,11 as float4; columns 0,1,18,19 of rows 2..9 as float2 pairs):
+        // 3*C planes x 28 items over 512 threads = at most 3 items per thread, offsets (in floats) fixed for the launch
+        int zoff[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int i = tid + q * TB_NCOMP;
+            int o = -1;
+            if (i < 3 * C * 28) {
+                const int k = i % 28, pl = i / 28;
+                if (k < 20) { const int row = k / 5 < 2 ? k / 5 : 8 + k / 5; o = pl * TB_PP + row * TB_PS + 4 * (k % 5); }
+                else o = (pl * TB_PP + (2 + (k - 20)) * TB_PS) | (1 << 30);      // flag: column pairs
+            }
+            zoff[q] = o;
+        }
 #define TB_TABLES(tile_, buf_)                                                                                           \
     do {                                                                                                                 \
         const int tt_ = (tile_);                                                                                         \
-        const int tb_ = tt_ / tiles_per_b, ty_ = ((tt_ / a.tiles_x) % a.tiles_y) * T2_TH, tx_ = (tt_ % a.tiles_x) * T2_TW; \
+        int tb_, ty_, tx_;                                                                                               \
+        t2_tile_decode(a.tl, tt_, tb_, ty_, tx_);                                                                        \
         if (g.cond_kind == NCA_COND_CPE && warp == 15 && lane < T2_TH + T2_TW) {                                         \
             const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow); \
             const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_)); \
@@ -326,11 +342,14 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         bar_sync_n(1, TB_NCOMP);
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
-            const int b = tile / tiles_per_b;
-            const int y0 = ((tile / a.tiles_x) % a.tiles_y) * T2_TH, x0 = (tile % a.tiles_x) * T2_TW;
+            int b, y0, x0;
+            t2_tile_decode(a.tl, tile, b, y0, x0);
             const int gy = y0 + py, gx = x0 + px;
             const bool inimg = gy < H && gx < W;
-            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W;
+            // border tile: some staged position (fine ring, or the coarse tile whose ring reaches 4 fine cells further) lies
+            // outside the image
+            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
+                                (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
             const float* sFire = sFire2 + (iter & 1) * 128;
             const uint32_t* sCpe = sCpe2 + (iter & 1) * 24;
             mbar_wait(barT, phT);
@@ -360,21 +379,27 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             float gn[4];
             {
                 const float fire = a.fm.supplied ? (inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f) : sFire[r];
-                float gyv[4];
+                const int nch = min(4, C - 4 * qtr);          // warp-uniform
+                const float* gp = sGn + (4 * qtr * T2_TH + py) * T2_TW + px;
+                const float* gcp = sGcn + (4 * qtr * 4 + (py >> 1)) * 8 + (px >> 1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int c = 4 * qtr + i;
                     float v = 0.0f;
-                    if (c < C) {
-                        v = sGn[(c * T2_TH + py) * T2_TW + px];
-                        if (NS == 2) v = fmaf(0.25f, sGcn[(c * 4 + (py >> 1)) * 8 + (px >> 1)], v);
-                        if (a.g_tap != nullptr && c < a.tap_c && inimg)
-                            v = fmaf(a.tap_scale, __ldg(a.g_tap + ((size_t)b * a.tap_c + c) * plane + (size_t)gy * W + gx), v);
+                    if (i < nch) {
+                        v = gp[i * T2_TH * T2_TW];
+                        if (NS == 2) v = fmaf(0.25f, gcp[i * 32], v);
                     }
                     gn[i] = v;
-                    gyv[i] = fire * v;
-                    b2acc[i] += gyv[i];
                 }
+                if (a.g_tap != nullptr && inimg) {            // rgb tap at states[t+1]: rare steps only
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (4 * qtr + i < a.tap_c)
+                            gn[i] = fmaf(a.tap_scale, __ldg(a.g_tap + ((size_t)b * a.tap_c + 4 * qtr + i) * plane + (size_t)gy * W + gx), gn[i]);
+                }
+                float gyv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { gyv[i] = fire * gn[i]; b2acc[i] += gyv[i]; }
                 uint2 pk;
                 pk.x = pack_bf16(gyv[0], gyv[1]); pk.y = pack_bf16(gyv[2], gyv[3]);
                 *reinterpret_cast<uint2*>(sGy + (uint32_t)(qtr >> 1) * 2048u + row_off + (uint32_t)(qtr & 1) * 8u) = pk;
@@ -458,17 +483,17 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             // ---- E2: D6 -> fp32 planes (overlay the operand region) ----
             {
-                // zero ring of the fine planes: rows 0,1,10,11 and columns 0,1,18,19 of rows 2..9
-                for (int i = tid; i < 3 * C * 28; i += TB_NCOMP) {
-                    float* pl = sPX + (i / 28) * TB_PP;
-                    const int k = i % 28;
-                    if (k < 20) {            // 4 full rows, as float4
-                        const int row = k / 5 < 2 ? k / 5 : 8 + k / 5;
-                        *reinterpret_cast<float4*>(pl + row * TB_PS + 4 * (k % 5)) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else {                 // rows 2..9: columns 0,1 and 18,19
-                        const int row = 2 + (k - 20);
-                        *reinterpret_cast<float2*>(pl + row * TB_PS) = make_float2(0.f, 0.f);
-                        *reinterpret_cast<float2*>(pl + row * TB_PS + 18) = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int o = zoff[q];
+                    if (o >= 0) {
+                        if (o & (1 << 30)) {
+                            float* pr = sPX + (o & ~(1 << 30));
+                            *reinterpret_cast<float2*>(pr) = make_float2(0.f, 0.f);
+                            *reinterpret_cast<float2*>(pr + 18) = make_float2(0.f, 0.f);
+                        } else {
+                            *reinterpret_cast<float4*>(sPX + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                 }
                 if (16 * qtr < N6) {
@@ -514,15 +539,22 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         const int vb = lane >> 4, ox = (lane & 15) + 1;      // ring column of the interior cell
                         float out[5];
                         tb_stencil_t<5, TB_PS>(X, Y, Lp, 5 * vb, ox, out);
-                        const int xx = x0 + ox - 1;
-                        const int tx = tb_fold(xx, W, g.pad);
 #pragma unroll
                         for (int k = 0; k < 5; ++k) {
-                            const int oy = 5 * vb + k, yy = y0 - 1 + oy;
-                            float v = out[k];
-                            if (oy >= 1 && oy <= T2_TH) v += sCtr[(c * T2_TH + oy - 1) * T2_TW + ox - 1];
-                            const int ty = tb_fold(yy, H, g.pad);
-                            if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, v);
+                            const int oy = 5 * vb + k;
+                            if (oy >= 1 && oy <= T2_TH) out[k] += sCtr[(c * T2_TH + oy - 1) * T2_TW + ox - 1];
+                        }
+                        if (!border) {       // every position is inside the image: coalesced rows, no folding
+                            float* p = gob + (size_t)(y0 - 1 + 5 * vb) * W + x0 + ox - 1;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) { atomicAdd(p, out[k]); p += W; }
+                        } else {
+                            const int tx = tb_fold(x0 + ox - 1, W, g.pad);
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                const int ty = tb_fold(y0 - 1 + 5 * vb + k, H, g.pad);
+                                if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[k]);
+                            }
                         }
                     }
                     if (lane < 20) {     // the two ring columns: 10 rows x 2 sides
@@ -530,8 +562,12 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         float out[1];
                         tb_stencil_t<1, TB_PS>(X, Y, Lp, oy, ox, out);
                         const int yy = y0 - 1 + oy, xx = x0 - 1 + ox;
-                        const int ty = tb_fold(yy, H, g.pad), tx = tb_fold(xx, W, g.pad);
-                        if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[0]);
+                        if (!border) {
+                            atomicAdd(gob + (size_t)yy * W + xx, out[0]);
+                        } else {
+                            const int ty = tb_fold(yy, H, g.pad), tx = tb_fold(xx, W, g.pad);
+                            if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[0]);
+                        }
                     }
                 }
             }
@@ -604,15 +640,22 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         float out[4];
                         tb_stencil_t<4, TB_CPS>(X, Y, Lp, 4 * vb, ox, out);
                         float* gcb = a.gc_out + ((size_t)b * C + c) * (plane >> 2);
-                        const int xx = cx0 - 1 + ox;
-                        const int tx = tb_fold(xx, Wc, g.pad);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const int oy = 4 * vb + k, yy = cy0 - 1 + oy;
-                            float v = out[k];
-                            if (oy >= 1 && oy <= T2_QH && ox >= 1 && ox <= T2_QW) v += sCCtr[(c * T2_QH + oy - 1) * T2_QW + ox - 1];
-                            const int ty = tb_fold(yy, Hc, g.pad);
-                            if (ty >= 0 && tx >= 0) atomicAdd(gcb + (size_t)ty * Wc + tx, v);
+                            const int oy = 4 * vb + k;
+                            if (oy >= 1 && oy <= T2_QH && ox >= 1 && ox <= T2_QW) out[k] += sCCtr[(c * T2_QH + oy - 1) * T2_QW + ox - 1];
+                        }
+                        if (!border) {
+                            float* p = gcb + (size_t)(cy0 - 1 + 4 * vb) * Wc + cx0 - 1 + ox;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { atomicAdd(p, out[k]); p += Wc; }
+                        } else {
+                            const int tx = tb_fold(cx0 - 1 + ox, Wc, g.pad);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int ty = tb_fold(cy0 - 1 + 4 * vb + k, Hc, g.pad);
+                                if (ty >= 0 && tx >= 0) atomicAdd(gcb + (size_t)ty * Wc + tx, out[k]);
+                            }
                         }
                     }
                 }
@@ -737,10 +780,10 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     a.B2d = (const __nv_bfloat16*)((const uint8_t*)ws + dynca_tc2_weight_bytes(g));
     a.gW1p = wsG; a.gW2p = a.gW1p + (size_t)g.Ppad * g.FCpad; a.gb2p = a.gW2p + (size_t)g.FCpad * g.CP;
     a.fm = fm;
-    a.tiles_x = (g.W + T2_TW - 1) / T2_TW; a.tiles_y = (g.H + T2_TH - 1) / T2_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
+    a.tl = t2_make_tiles(g.B, g.H, g.W);
     const size_t smem = tb_smem(g, a.bg).total;
     int grid = t2_num_sms();
-    if (grid > a.n_tiles) grid = a.n_tiles;
+    if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
     const CUtensorMap* tx = (const CUtensorMap*)xm->x;
     const CUtensorMap* txc = (const CUtensorMap*)xm->xc;
     const CUtensorMap* tg = (const CUtensorMap*)gm->x;
