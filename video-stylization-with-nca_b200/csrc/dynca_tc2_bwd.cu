@@ -53,6 +53,7 @@ struct T2BwdArgs {
     float* gW1p; float* gW2p; float* gb2p;            // fp32 accumulators, padded fp32-path layout (red.add)
     FireMask fm;
     T2Tiles tl;
+    long long* tdbg;
 };
 
 struct TBSmem {
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     } while (0)
         if ((int)blockIdx.x < n_tiles) TB_TABLES(blockIdx.x, 0);
         bar_sync_n(1, TB_NCOMP);
+#define TB_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
             int b, y0, x0;
@@ -352,8 +354,10 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                                 (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
             const float* sFire = sFire2 + (iter & 1) * 128;
             const uint32_t* sCpe = sCpe2 + (iter & 1) * 24;
+            TB_STAMP(0);
             mbar_wait(barT, phT);
             phT ^= 1u;
+            TB_STAMP(1);
             if (border && g.pad != NCA_PAD_CONSTANT) {
                 t2_patch_border<NS, TB_NCOMP>(g, a.x_in, a.xc_in, b, y0, x0, sX, sXc);
                 bar_sync_n(1, TB_NCOMP);
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
             }
             if (NS == 2) t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
+            TB_STAMP(2);
             // ---- g = dL/dx_{t+1} of this thread's 4 channels (+ coarse part, + tap) ; g_y = fire * g -> Gy ----
             float gn[4];
             {
@@ -405,6 +410,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 *reinterpret_cast<uint2*>(sGy + (uint32_t)(qtr >> 1) * 2048u + row_off + (uint32_t)(qtr & 1) * 8u) = pk;
             }
             if (tile + (int)gridDim.x < n_tiles) TB_TABLES(tile + gridDim.x, (iter + 1) & 1);
+            TB_STAMP(3);
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barA);
@@ -412,6 +418,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 mbar_wait(barM, phM);
                 phM ^= 1u;
                 tc_fence_after();
+                TB_STAMP(4);
                 // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
                 if ((warp & 3) < 2 && 32 * qtr < fc) {
                     uint32_t v[32];
@@ -431,9 +438,11 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 tc_fence_before();
                 mbar_arrive(barB);
             }
+            TB_STAMP(5);
             mbar_wait(barM, phM);
             phM ^= 1u;
             tc_fence_after();
+            TB_STAMP(6);
             // ---- E1: h = relu(D1), g_a = D3 * [D1 > 0] -> bf16 operands; thread -> hidden units 32q .. 32q+31 ----
             if (32 * qtr < fc) {
                 uint32_t av[32], gv[32];
@@ -457,10 +466,12 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             fence_proxy_async();
             tc_fence_before();
+            TB_STAMP(7);
             mbar_arrive(barC);
             mbar_wait(barM, phM);                              // D4, D5 (fine), D6, GaU complete; operand region is free
             phM ^= 1u;
             tc_fence_after();
+            TB_STAMP(8);
             if (NS == 2) {
                 // ---- GaU (rows 0..63) -> bf16 -> [(j/8)*1024 + q*16]: K-major A of D7, MN-major A of the gW1 coarse part ----
                 if ((warp & 3) < 2 && 32 * qtr < fc) {
@@ -526,17 +537,21 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     *reinterpret_cast<float4*>(a.gc_in + ((size_t)b * C + c) * (plane >> 2) + (size_t)((y0 >> 1) + rr) * (W >> 1) + (x0 >> 1) + x4) =
                         make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            TB_STAMP(9);
             bar_sync_n(1, TB_NCOMP);
-            // ---- P5: transposed fine perception -> red.add into dL/dx_t.  warp = channel, lane = (5-row block, column) ----
+            TB_STAMP(10);
+            // ---- P5: transposed fine perception -> red.add into dL/dx_t.  warp = (channel pair, 5-row block), lane =
+            //      (channel of the pair, column): channel planes are 240 floats = 16 banks apart -> conflict-free reads ----
             {
-                const int c = warp;
+                const int cp = warp >> 1, vb = warp & 1, hc = lane >> 4;
+                const int c = 2 * cp + hc;
                 if (c < C) {
                     const float* X = sPX + c * TB_PP;
                     const float* Y = X + C * TB_PP;
                     const float* Lp = Y + C * TB_PP;
                     float* gob = a.g_out + ((size_t)b * C + c) * plane;
                     {
-                        const int vb = lane >> 4, ox = (lane & 15) + 1;      // ring column of the interior cell
+                        const int ox = (lane & 15) + 1;      // ring column of the interior cell
                         float out[5];
                         tb_stencil_t<5, TB_PS>(X, Y, Lp, 5 * vb, ox, out);
 #pragma unroll
@@ -557,8 +572,16 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                             }
                         }
                     }
-                    if (lane < 20) {     // the two ring columns: 10 rows x 2 sides
-                        const int oy = lane >> 1, ox = (lane & 1) ? T2_TW + 1 : 0;
+                }
+                if (lane < 20) {     // the two ring columns: 2 channels x 5 rows x 2 sides
+                    const int hc2 = lane / 10, rem = lane % 10;
+                    const int c2 = 2 * cp + hc2;
+                    if (c2 < C) {
+                        const float* X = sPX + c2 * TB_PP;
+                        const float* Y = X + C * TB_PP;
+                        const float* Lp = Y + C * TB_PP;
+                        float* gob = a.g_out + ((size_t)b * C + c2) * plane;
+                        const int oy = 5 * vb + (rem >> 1), ox = (rem & 1) ? T2_TW + 1 : 0;
                         float out[1];
                         tb_stencil_t<1, TB_PS>(X, Y, Lp, oy, ox, out);
                         const int yy = y0 - 1 + oy, xx = x0 - 1 + ox;
@@ -571,10 +594,12 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
                 }
             }
+            TB_STAMP(11);
             if (NS == 2) {
                 mbar_wait(barM, phM);                          // D5 coarse part, D7 complete
                 phM ^= 1u;
                 tc_fence_after();
+                TB_STAMP(12);
                 // ---- D7 -> coarse planes (zero padded [10][14], footprint cell (qy,qx) at [qy+2][qx+2]) ----
                 for (int i = tid; i < 3 * C * TB_CPP / 2; i += TB_NCOMP) reinterpret_cast<float2*>(sCPX)[i] = make_float2(0.f, 0.f);
                 bar_sync_n(1, TB_NCOMP);
@@ -628,12 +653,15 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
                     bar_sync_n(1, TB_NCOMP);
                 }
+                TB_STAMP(13);
                 // ---- P6: transposed coarse perception -> red.add into the coarse gradient buffer.
                 //      warp = channel, lane = (4-row block, column of the 8 x 12 coarse ring) ----
                 {
-                    const int c = warp;
+                    // warp = (channel pair, 4-row block), lane = (channel of the pair, column of the 8 x 12 coarse ring):
+                    // coarse channel planes are 140 floats = 12 banks apart -> conflict-free reads
+                    const int cp = warp >> 1, vb = warp & 1, hc = lane / 12, ox = lane % 12;
+                    const int c = 2 * cp + hc;
                     if (c < C && lane < 24) {
-                        const int vb = lane / 12, ox = lane % 12;
                         const float* X = sCPX + c * TB_CPP;
                         const float* Y = X + C * TB_CPP;
                         const float* Lp = Y + C * TB_CPP;
@@ -660,7 +688,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
                 }
             }
+            TB_STAMP(14);
             bar_sync_n(1, TB_NCOMP);     // the planes overlay the operand region the next tile's P1 writes
+            TB_STAMP(15);
         }
         // ---- flush: D4 [fc x 16] -> gW2p[j][c];  D5 [fc x K1] -> gW1p[k][j] (k' -> reference k, perception columns x s0) ----
         {
@@ -781,6 +811,10 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     a.gW1p = wsG; a.gW2p = a.gW1p + (size_t)g.Ppad * g.FCpad; a.gb2p = a.gW2p + (size_t)g.FCpad * g.CP;
     a.fm = fm;
     a.tl = t2_make_tiles(g.B, g.H, g.W);
+    static long long* tdbg = nullptr;
+    const bool timing = getenv("NCA_T2_TDBG") != nullptr;
+    if (timing && !tdbg) cudaMalloc(&tdbg, 128 * sizeof(long long));
+    a.tdbg = timing ? tdbg : nullptr;
     const size_t smem = tb_smem(g, a.bg).total;
     int grid = t2_num_sms();
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
@@ -796,5 +830,14 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
         dynca_bwd_tc2_kernel<1><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, a);
     }
     NCA_LAUNCH_OK();
+    if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps
+        long long h[128];
+        cudaMemcpy(h, tdbg, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int it = 0; it < 8; ++it) {
+            fprintf(stderr, "tc2 bwd timing iter %d:", it);
+            for (int k = 0; k < 16; ++k) fprintf(stderr, " %lld", h[it * 16 + k] - h[it * 16]);
+            fprintf(stderr, "  | since prev tile start %lld\n", it ? h[it * 16] - h[(it - 1) * 16] : 0);
+        }
+    }
     return NCA_OK;
 }
