@@ -255,10 +255,17 @@ def main():
         roof = {"bound": "tensor", "achieved": ach_tf, "peak": tens, "unit": "TFLOP/s", "frac": ach_tf / tens}
     else:
         roof = {"bound": "hbm", "achieved": ach_gb, "peak": hbm, "unit": "GB/s", "frac": ach_gb / hbm}
-    roof.update({"traffic": None, "kernel": f"dynca_bwd_{args.precision}_kernel<2>", "kernel_ms": ms_kernel,
+    variant = Fn.dynca_kernel_variant(cfg, B, H, W, backward=True)
+    kname = {0: "dynca_bwd_f32_kernel<2>", 1: "dynca_bwd_bf16_kernel<2>", 2: "dynca_bwd_tc2_kernel<2>"}[variant]
+    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(kname)
+    roof.update({"traffic": traffic, "kernel": kname, "kernel_ms": ms_kernel,
                  "peaks": which, "hbm_frac": ach_gb / hbm, "tensor_frac": ach_tf / tens,
-                 "note": "algorithmic flops 3*F_mlp+2*F_perc = %d, bytes 12C = %d per cell-update; kernel time = "
-                         "nca_dynca_backward call / T (includes the per-step memset)" % (FLOPS_BWD_KERNEL, BYTES_BWD_KERNEL)})
+                 "note": "algorithmic flops 3*F_mlp+2*F_perc = %d, bytes 12C = %d per cell-update, %d cells per launch; "
+                         "kernel time = nca_dynca_backward call / T, CUDA events on the launching stream"
+                         % (FLOPS_BWD_KERNEL, BYTES_BWD_KERNEL, B * H * W)})
 
     # ---- e2e: public module API with HOST buffers ----
     x_host = x0.cpu().pin_memory()
