@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 24);
     uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 32);
     uint64_t* barD = reinterpret_cast<uint64_t*>(smem + 40);
+    uint64_t* barG = reinterpret_cast<uint64_t*>(smem + 56);    // Gy written, stage consumed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48);
     float* sFire2 = reinterpret_cast<float*>(smem + 128);               // 2 x 128 floats
     uint32_t* sCpe2 = reinterpret_cast<uint32_t*>(smem + 128 + 1024);   // 2 x 24
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         mbar_init(barB, TB_NCOMP);
         mbar_init(barC, TB_NCOMP);
         mbar_init(barD, TB_NCOMP);
+        mbar_init(barG, TB_NCOMP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(tmem_slot, 512u);
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const CUtensorMap* const ptm_xc = &tm_xc;
         const CUtensorMap* const ptm_g = &tm_g;
         const CUtensorMap* const ptm_gc = &tm_gc;
-        uint32_t phA = 0, phB = 0, phC = 0, phD = 0;
+        uint32_t phA = 0, phB = 0, phC = 0, phD = 0, phG = 0;
         const bool leader = elect_one();
         bool first = true;
 #define TB_ISSUE_TMA(tile_)                                                                                              \
@@ -250,6 +252,11 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 #pragma unroll 5
                 for (int ks = 0; ks < k1steps; ++ks)
                     umma_ss(tmem_base + TB_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
+            }
+            mbar_wait(barG, phG);                              // g_y is computed while the recompute MMAs run
+            phG ^= 1u;
+            tc_fence_after();
+            if (leader) {
                 umma_ss(tmem_base + TB_D3, dGy, dB2d, id_fc, false);
                 if (NS == 1) umma_commit(barM);
                 if (tile + (int)gridDim.x < n_tiles) TB_ISSUE_TMA(tile + gridDim.x);     // the stage is free
@@ -379,6 +386,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
             }
             if (NS == 2) t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(barA);                                 // A1 / Zc complete: the recompute MMAs start
             TB_STAMP(2);
             // ---- g = dL/dx_{t+1} of this thread's 4 channels (+ coarse part, + tap) ; g_y = fire * g -> Gy ----
             float gn[4];
@@ -413,7 +423,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             TB_STAMP(3);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(barA);
+            mbar_arrive(barG);                                 // Gy complete, stage consumed
             if (NS == 2) {
                 mbar_wait(barM, phM);
                 phM ^= 1u;
