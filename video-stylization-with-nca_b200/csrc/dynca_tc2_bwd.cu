@@ -57,14 +57,17 @@ struct T2BwdArgs {
 };
 
 struct TBSmem {
-    uint32_t b1, b2d, u, x, xc, gn, gcn, zc, gau, a1, dcb, gy, h, ga, px, ctr, cpx, cctr, total;
+    uint32_t b1, b2d, u, x, xc, gn, gcn, zc, gau, a1, gy, h, ga, px, ctr, cpx, cctr, total;
 };
+// A1 / Zc / Gy are double buffered over tiles (the next tile's operands are produced while the gradient MMAs of the
+// current tile run); DcB shares its storage with GaU (DcB is dead once D1 is complete, GaU is written after that); the
+// fp32 planes overlay H | Ga (dead once the gradient MMAs are complete), the coarse planes reuse the fine planes.
 __host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16Geom& bg) {
     TBSmem s;
-    const uint32_t C = (uint32_t)g.C, fc8 = (uint32_t)(g.fc / 8);
+    const uint32_t C = (uint32_t)g.C;
     uint32_t o = TB_HDR;
     s.b1 = o; o += bg.b1_bytes;
-    s.b2d = o; o += fc8 * 256u;
+    s.b2d = o; o += (uint32_t)(g.fc / 8) * 256u;
     s.u = o; o += g.ns == 2 ? 16384u : 0u;
     o = (o + 127u) & ~127u;
     s.x = o; o += C * T2_XR * T2_XS * 4u;
@@ -75,22 +78,22 @@ __host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16G
     o = (o + 127u) & ~127u;
     s.gcn = o; o += g.ns == 2 ? C * 4u * 8u * 4u : 0u;
     o = (o + 127u) & ~127u;
-    s.zc = o; o += g.ns == 2 ? 8192u : 0u;
-    s.gau = o; o += g.ns == 2 ? 16u * 1024u : 0u;      // 16 chunks: the M = 128 views read all of them whatever fc is
+    s.zc = o; o += g.ns == 2 ? 2u * 8192u : 0u;          // 2 buffers; M = 128 reads of a 64-row chunk alias what follows
+    s.gau = o; o += g.ns == 2 ? 16u * 1024u : 0u;        // GaU | DcB, 16 chunks whatever fc is
+    s.a1 = o; o += 2u * bg.a1_bytes;
+    s.gy = o; o += 2u * 4096u;
     o = (o + 127u) & ~127u;
-    // ---- operand region, overlaid by the fp32 planes once the MMAs that read it are complete ----
-    const uint32_t base = o;
-    s.a1 = o; o += bg.a1_bytes;
-    s.dcb = o; o += g.ns == 2 ? fc8 * 1024u : 0u;
-    s.gy = o; o += 4096u;
     s.h = o; o += 16u * 2048u;
     s.ga = o; o += 16u * 2048u;
-    uint32_t p = base;
+    uint32_t p = s.h;
     s.px = p; p += 3u * C * TB_PP * 4u;
     s.ctr = p; p += C * T2_TH * T2_TW * 4u;
+    const uint32_t pf = p;
+    p = s.h;
     s.cpx = p; p += g.ns == 2 ? 3u * C * TB_CPP * 4u : 0u;
     s.cctr = p; p += g.ns == 2 ? C * T2_QH * T2_QW * 4u : 0u;
-    s.total = (o > p ? o : p) + 1024u;      // + slack: M = 128 reads of 64-row operands run past their end
+    const uint32_t pm = pf > p ? pf : p;
+    s.total = (o > pm ? o : pm) + 1024u;                 // + slack for the aliasing reads of the last buffer
     return s;
 }
 
@@ -134,14 +137,21 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
     const TBSmem L = tb_smem(g, bg);
-    uint64_t* barM = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);
-    uint64_t* barA = reinterpret_cast<uint64_t*>(smem + 16);
-    uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 24);
-    uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 32);
-    uint64_t* barD = reinterpret_cast<uint64_t*>(smem + 40);
-    uint64_t* barG = reinterpret_cast<uint64_t*>(smem + 56);    // Gy written, stage consumed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48);
+    // MMA-completion barriers (tcgen05.commit), one per batch of a tile, so that the MMA warp may run ahead into the next
+    // tile's recompute batch without a barrier ever being two phases ahead of its waiters
+    uint64_t* barM1 = reinterpret_cast<uint64_t*>(smem);          // Dc
+    uint64_t* barM2 = reinterpret_cast<uint64_t*>(smem + 8);      // D1, D3
+    uint64_t* barM3 = reinterpret_cast<uint64_t*>(smem + 16);     // D4, D5 (fine), D6, GaU
+    uint64_t* barM4 = reinterpret_cast<uint64_t*>(smem + 24);     // D5 (coarse), D7
+    uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 32);      // TMA
+    // compute -> MMA warp hand-offs (512 arrivals each)
+    uint64_t* barA = reinterpret_cast<uint64_t*>(smem + 40);      // A1 / Zc written
+    uint64_t* barG = reinterpret_cast<uint64_t*>(smem + 48);      // Gy written, stage consumed
+    uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 56);      // DcB written
+    uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 64);      // H, Ga written; D1 / D3 consumed
+    uint64_t* barD = reinterpret_cast<uint64_t*>(smem + 72);      // GaU (bf16) written
+    uint64_t* barE = reinterpret_cast<uint64_t*>(smem + 80);      // D6 / D7 read back (their TMEM columns are D3's)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 88);
     float* sFire2 = reinterpret_cast<float*>(smem + 128);               // 2 x 128 floats
     uint32_t* sCpe2 = reinterpret_cast<uint32_t*>(smem + 128 + 1024);   // 2 x 24
     uint8_t* sB1 = smem + L.b1;
@@ -151,16 +161,16 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     float* sXc = reinterpret_cast<float*>(smem + L.xc);
     float* sGn = reinterpret_cast<float*>(smem + L.gn);
     float* sGcn = reinterpret_cast<float*>(smem + L.gcn);
-    uint8_t* sZc = smem + L.zc;
-    uint8_t* sGaU = smem + L.gau;
-    uint8_t* sA1 = smem + L.a1;
-    uint8_t* sDcB = smem + L.dcb;
-    uint8_t* sGy = smem + L.gy;
+    uint8_t* sZc2 = smem + L.zc;          // 2 x 8192
+    uint8_t* sGaU = smem + L.gau;         // GaU, and DcB before it
+    uint8_t* sDcB = sGaU;
+    uint8_t* sA12 = smem + L.a1;          // 2 x a1_bytes
+    uint8_t* sGy2 = smem + L.gy;          // 2 x 4096
     uint8_t* sH = smem + L.h;
     uint8_t* sGa = smem + L.ga;
     float* sPX = reinterpret_cast<float*>(smem + L.px);       // [3][C][12][20]: X, Y, L planes
     float* sCtr = reinterpret_cast<float*>(smem + L.ctr);     // [C][8][16]: g + g_z(id) - 16 g_z(lap)
-    float* sCPX = reinterpret_cast<float*>(smem + L.cpx);     // [3][C][10][14]
+    float* sCPX = reinterpret_cast<float*>(smem + L.cpx);     // [3][C][10][14]   (reuses the fine planes after P5)
     float* sCCtr = reinterpret_cast<float*>(smem + L.cctr);   // [C][6][10]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
@@ -181,13 +191,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     // everything an MMA may read before the tile loop writes it must be finite: clear the dynamic area once
     for (uint32_t i = L.zc / 16 + tid; i < L.total / 16; i += TB_NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        mbar_init(barM, 1);
-        mbar_init(barT, 1);
-        mbar_init(barA, TB_NCOMP);
-        mbar_init(barB, TB_NCOMP);
-        mbar_init(barC, TB_NCOMP);
-        mbar_init(barD, TB_NCOMP);
-        mbar_init(barG, TB_NCOMP);
+        mbar_init(barM1, 1); mbar_init(barM2, 1); mbar_init(barM3, 1); mbar_init(barM4, 1); mbar_init(barT, 1);
+        mbar_init(barA, TB_NCOMP); mbar_init(barG, TB_NCOMP); mbar_init(barB, TB_NCOMP);
+        mbar_init(barC, TB_NCOMP); mbar_init(barD, TB_NCOMP); mbar_init(barE, TB_NCOMP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(tmem_slot, 512u);
@@ -203,25 +209,29 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const uint32_t id_fc = umma_idesc_bf16(128, fc), id_fc_bmn = id_fc | (1u << 16), id_fc_mn = umma_idesc_bf16_mn(128, fc);
         const uint32_t id_w2 = umma_idesc_bf16_mn(128, 16), id_w1 = umma_idesc_bf16_mn(128, bg.K1), id_w1c = umma_idesc_bf16_mn(128, N6);
         const uint32_t id_gz = umma_idesc_bf16(128, N6) | (1u << 16);
-        const uint64_t dA1 = umma_desc(smem_u32(sA1), 2048u, 128u), dB1 = umma_desc(smem_u32(sB1), lbo_b1, 128u);
-        const uint64_t dZc = umma_desc(smem_u32(sZc), 1024u, 128u), dU = umma_desc(smem_u32(sU), 2048u, 128u);
+        const uint64_t dB1 = umma_desc(smem_u32(sB1), lbo_b1, 128u);
+        const uint64_t dU = umma_desc(smem_u32(sU), 2048u, 128u);
         const uint64_t dDcB = umma_desc(smem_u32(sDcB), 128u, 1024u);
-        const uint64_t dGy = umma_desc(smem_u32(sGy), 2048u, 128u), dB2d = umma_desc(smem_u32(sB2d), lbo_b1, 128u);
+        const uint64_t dB2d = umma_desc(smem_u32(sB2d), lbo_b1, 128u);
         // MN-major views (cells / coarse cells / hidden units become K): LBO = 128 (K groups), SBO = group stride of MN
         const uint64_t dHt = umma_desc(smem_u32(sH), 128u, 2048u), dGat = umma_desc(smem_u32(sGa), 128u, 2048u);
-        const uint64_t dGyt = umma_desc(smem_u32(sGy), 128u, 2048u), dA1t = umma_desc(smem_u32(sA1), 128u, 2048u);
         const uint64_t dUt = umma_desc(smem_u32(sU), 128u, 2048u);
         const uint64_t dGa = umma_desc(smem_u32(sGa), 2048u, 128u);
         const uint64_t dB1t = umma_desc(smem_u32(sB1), 128u, lbo_b1);                 // B1 as [N = k'][K = hidden]
-        const uint64_t dGaUt = umma_desc(smem_u32(sGaU), 128u, 1024u), dZct = umma_desc(smem_u32(sZc), 128u, 1024u);
+        const uint64_t dGaUt = umma_desc(smem_u32(sGaU), 128u, 1024u);
         const uint64_t dGaU = umma_desc(smem_u32(sGaU), 1024u, 128u);
+        // double-buffered operands: descriptor of buffer 1 = descriptor of buffer 0 + (bytes >> 4)
+        const uint64_t dA1_0 = umma_desc(smem_u32(sA12), 2048u, 128u), dA1t_0 = umma_desc(smem_u32(sA12), 128u, 2048u);
+        const uint64_t dZc_0 = umma_desc(smem_u32(sZc2), 1024u, 128u), dZct_0 = umma_desc(smem_u32(sZc2), 128u, 1024u);
+        const uint64_t dGy_0 = umma_desc(smem_u32(sGy2), 2048u, 128u), dGyt_0 = umma_desc(smem_u32(sGy2), 128u, 2048u);
+        const uint64_t oA1 = (uint64_t)(bg.a1_bytes >> 4), oZc = (uint64_t)(8192u >> 4), oGy = (uint64_t)(4096u >> 4);
         const uint64_t sB1k = (uint64_t)((2u * lbo_b1) >> 4);
         const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, kfsteps = fc / 16;
         const CUtensorMap* const ptm_x = &tm_x;
         const CUtensorMap* const ptm_xc = &tm_xc;
         const CUtensorMap* const ptm_g = &tm_g;
         const CUtensorMap* const ptm_gc = &tm_gc;
-        uint32_t phA = 0, phB = 0, phC = 0, phD = 0, phG = 0;
+        uint32_t phA = 0, phB = 0, phC = 0, phD = 0, phG = 0, phE = 0;
         const bool leader = elect_one();
         bool first = true;
 #define TB_ISSUE_TMA(tile_)                                                                                              \
@@ -238,7 +248,13 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         }                                                                                                                \
     } while (0)
         if (leader && (int)blockIdx.x < n_tiles) TB_ISSUE_TMA(blockIdx.x);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint64_t par = (uint64_t)(it & 1);
+            const uint64_t dA1 = dA1_0 + par * oA1, dA1t = dA1t_0 + par * oA1;
+            const uint64_t dZc = dZc_0 + par * oZc, dZct = dZct_0 + par * oZc;
+            const uint64_t dGy = dGy_0 + par * oGy, dGyt = dGyt_0 + par * oGy;
+            // ---- recompute batch: the compute warps produced these operands while the previous tile's gradient MMAs ran ----
             mbar_wait(barA, phA);
             phA ^= 1u;
             tc_fence_after();
@@ -247,19 +263,23 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 #pragma unroll 4
                     for (int ks = 0; ks < kcsteps; ++ks)
                         umma_ss(tmem_base + TB_DC, dZc + (uint64_t)(ks * (2048 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
-                    umma_commit(barM);
+                    umma_commit(barM1);
                 }
 #pragma unroll 5
                 for (int ks = 0; ks < k1steps; ++ks)
                     umma_ss(tmem_base + TB_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
             }
-            mbar_wait(barG, phG);                              // g_y is computed while the recompute MMAs run
+            mbar_wait(barG, phG);                              // Gy written, stage consumed
             phG ^= 1u;
+            if (leader && tile + (int)gridDim.x < n_tiles) TB_ISSUE_TMA(tile + gridDim.x);
+            if (it > 0) {                                      // D3's columns held D6 / D7 of the previous tile
+                mbar_wait(barE, phE);
+                phE ^= 1u;
+            }
             tc_fence_after();
             if (leader) {
                 umma_ss(tmem_base + TB_D3, dGy, dB2d, id_fc, false);
-                if (NS == 1) umma_commit(barM);
-                if (tile + (int)gridDim.x < n_tiles) TB_ISSUE_TMA(tile + gridDim.x);     // the stage is free
+                if (NS == 1) umma_commit(barM2);
             }
             if (NS == 2) {
                 mbar_wait(barB, phB);
@@ -269,22 +289,17 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                         umma_ss(tmem_base + TB_D1, dU + (uint64_t)(ks * (4096 >> 4)), dDcB + (uint64_t)(ks * (256 >> 4)), id_fc_bmn, true);
-                    umma_commit(barM);
+                    umma_commit(barM2);
                 }
             }
-            mbar_wait(barC, phC);                              // H, Ga written; D1 / D3 / Dc consumed; stage consumed
+            mbar_wait(barC, phC);                              // H, Ga written; D1 / D3 consumed
             phC ^= 1u;
             tc_fence_after();
             if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {               // 16 cells per instruction
-                    const uint64_t o = (uint64_t)(ks * (256 >> 4));
-                    umma_ss(tmem_base + TB_D4, dHt + o, dGyt + o, id_w2, !(first && ks == 0));
-                    umma_ss(tmem_base + TB_D5, dGat + o, dA1t + o, id_w1, !(first && ks == 0));
-                }
+                // g_z first (the compute warps wait for it), weight gradients behind it in the same batch
 #pragma unroll 8
                 for (int ks = 0; ks < kfsteps; ++ks)           // D6 = Ga . W1h  (g_z of the fine scale)
-                    umma_ss(tmem_base + TB_D1, dGa + (uint64_t)(ks * (4096 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
+                    umma_ss(tmem_base + TB_D3, dGa + (uint64_t)(ks * (4096 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
                 if (NS == 2) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {           // GaU = U^T . Ga
@@ -292,7 +307,13 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         umma_ss(tmem_base + TB_DC, dUt + o, dGat + o, id_fc_mn, ks > 0);
                     }
                 }
-                umma_commit(barM);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {               // 16 cells per instruction
+                    const uint64_t o = (uint64_t)(ks * (256 >> 4));
+                    umma_ss(tmem_base + TB_D4, dHt + o, dGyt + o, id_w2, !(first && ks == 0));
+                    umma_ss(tmem_base + TB_D5, dGat + o, dA1t + o, id_w1, !(first && ks == 0));
+                }
+                umma_commit(barM3);
             }
             first = false;
             if (NS == 2) {
@@ -307,8 +328,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
 #pragma unroll 8
                     for (int ks = 0; ks < kfsteps; ++ks)       // D7 = GaU . W1h  (g_z on the coarse footprint)
-                        umma_ss(tmem_base + TB_D1 + 64u, dGaU + (uint64_t)(ks * (2048 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
-                    umma_commit(barM);
+                        umma_ss(tmem_base + TB_D3 + 64u, dGaU + (uint64_t)(ks * (2048 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
+                    umma_commit(barM4);
                 }
             }
         }
@@ -318,7 +339,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t row_off = (uint32_t)r * 16u;
         const int py = r >> 4, px = r & 15;
-        uint32_t phM = 0, phT = 0;
+        uint32_t phM1 = 0, phM2 = 0, phM3 = 0, phM4 = 0, phT = 0;
         float b2acc[4] = {0.f, 0.f, 0.f, 0.f};
         // zero ring of the fine planes (rows 0,1,10,11 as float4; columns 0,1,18,19 of rows 2..9 as float2 pairs):
         // 3*C planes x 28 items over 512 threads = at most 3 items per thread, offsets (in floats) fixed for the launch
@@ -334,42 +355,38 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             zoff[q] = o;
         }
-#define TB_TABLES(tile_, buf_)                                                                                           \
-    do {                                                                                                                 \
-        const int tt_ = (tile_);                                                                                         \
-        int tb_, ty_, tx_;                                                                                               \
-        t2_tile_decode(a.tl, tt_, tb_, ty_, tx_);                                                                        \
-        if (g.cond_kind == NCA_COND_CPE && warp == 15 && lane < T2_TH + T2_TW) {                                         \
-            const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow); \
-            const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_)); \
-            sCpe2[(buf_) * 24 + lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16); \
-        }                                                                                                                \
-        if (!a.fm.supplied && warp == 14) t2_fire_tile(a.fm, tb_, ty_, tx_, H, W, lane, sFire2 + (buf_) * 128);          \
-    } while (0)
-        if ((int)blockIdx.x < n_tiles) TB_TABLES(blockIdx.x, 0);
-        bar_sync_n(1, TB_NCOMP);
-#define TB_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
-        int iter = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        // CPE rows / columns (warp 15) and fire decisions (warp 14) of a tile, double buffered over tiles
+        auto tables = [&](int tile_, int buf_) {
+            int tb_, ty_, tx_;
+            t2_tile_decode(a.tl, tile_, tb_, ty_, tx_);
+            if (g.cond_kind == NCA_COND_CPE && warp == 15 && lane < T2_TH + T2_TW) {
+                const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow);
+                const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_));
+                sCpe2[buf_ * 24 + lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16);
+            }
+            if (!a.fm.supplied && warp == 14) t2_fire_tile(a.fm, tb_, ty_, tx_, H, W, lane, sFire2 + buf_ * 128);
+        };
+        // ---- P1 of a tile: perception operands A1 / Zc (-> barrier A), g = dL/dx_{t+1} and Gy (-> barrier G).
+        //      Runs for tile i+1 while the gradient MMAs of tile i are in flight.  itn = iteration index of that tile. ----
+        auto p1 = [&](int tile_, int itn, float (&gn)[4]) {
             int b, y0, x0;
-            t2_tile_decode(a.tl, tile, b, y0, x0);
+            t2_tile_decode(a.tl, tile_, b, y0, x0);
             const int gy = y0 + py, gx = x0 + px;
             const bool inimg = gy < H && gx < W;
-            // border tile: some staged position (fine ring, or the coarse tile whose ring reaches 4 fine cells further) lies
-            // outside the image
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
                                 (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
-            const float* sFire = sFire2 + (iter & 1) * 128;
-            const uint32_t* sCpe = sCpe2 + (iter & 1) * 24;
-            TB_STAMP(0);
+            const int par = itn & 1;
+            uint8_t* sA1 = sA12 + (uint32_t)par * bg.a1_bytes;
+            uint8_t* sZc = sZc2 + (uint32_t)par * 8192u;
+            uint8_t* sGy = sGy2 + (uint32_t)par * 4096u;
+            const float* sFire = sFire2 + par * 128;
+            const uint32_t* sCpe = sCpe2 + par * 24;
             mbar_wait(barT, phT);
             phT ^= 1u;
-            TB_STAMP(1);
             if (border && g.pad != NCA_PAD_CONSTANT) {
                 t2_patch_border<NS, TB_NCOMP>(g, a.x_in, a.xc_in, b, y0, x0, sX, sXc);
                 bar_sync_n(1, TB_NCOMP);
             }
-            // ---- P1: perception operands ----
             t2_fine_to_a1<16>(sX, sA1, C, bg.npairs, warp, lane);
             if (qtr == 0) {
                 uint4 cv;
@@ -388,10 +405,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             if (NS == 2) t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(barA);                                 // A1 / Zc complete: the recompute MMAs start
-            TB_STAMP(2);
-            // ---- g = dL/dx_{t+1} of this thread's 4 channels (+ coarse part, + tap) ; g_y = fire * g -> Gy ----
-            float gn[4];
+            mbar_arrive(barA);
+            // g of this thread's 4 channels (+ coarse part, + tap); g_y = fire * g -> Gy
             {
                 const float fire = a.fm.supplied ? (inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f) : sFire[r];
                 const int nch = min(4, C - 4 * qtr);          // warp-uniform
@@ -419,16 +434,41 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 pk.x = pack_bf16(gyv[0], gyv[1]); pk.y = pack_bf16(gyv[2], gyv[3]);
                 *reinterpret_cast<uint2*>(sGy + (uint32_t)(qtr >> 1) * 2048u + row_off + (uint32_t)(qtr & 1) * 8u) = pk;
             }
-            if (tile + (int)gridDim.x < n_tiles) TB_TABLES(tile + gridDim.x, (iter + 1) & 1);
-            TB_STAMP(3);
+            // zero the consumed tile of g_{t+1} in global memory (it is the output of the next launch)
+            if (a.zero_in) {
+                const int c = tid >> 5, rr = (tid >> 2) & 7, x4 = (tid & 3) * 4;
+                if (c < C && y0 + rr < H && x0 + x4 < W)
+                    *reinterpret_cast<float4*>(a.g_in + ((size_t)b * C + c) * plane + (size_t)(y0 + rr) * W + x0 + x4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (NS == 2 && a.zero_cin && tid < 128) {
+                const int c = tid >> 3, rr = (tid >> 1) & 3, x4 = (tid & 1) * 4;
+                if (c < C && (y0 >> 1) + rr < (H >> 1) && (x0 >> 1) + x4 < (W >> 1))
+                    *reinterpret_cast<float4*>(a.gc_in + ((size_t)b * C + c) * (plane >> 2) + (size_t)((y0 >> 1) + rr) * (W >> 1) + (x0 >> 1) + x4) =
+                        make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (tile_ + (int)gridDim.x < n_tiles) tables(tile_ + gridDim.x, (itn + 1) & 1);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(barG);                                 // Gy complete, stage consumed
+            mbar_arrive(barG);
+        };
+
+        float gn[4] = {0.f, 0.f, 0.f, 0.f}, gn_next[4] = {0.f, 0.f, 0.f, 0.f};
+        if ((int)blockIdx.x < n_tiles) tables(blockIdx.x, 0);
+        bar_sync_n(1, TB_NCOMP);
+        if ((int)blockIdx.x < n_tiles) p1(blockIdx.x, 0, gn);
+#define TB_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+            int b, y0, x0;
+            t2_tile_decode(a.tl, tile, b, y0, x0);
+            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
+                                (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
+            TB_STAMP(0);
             if (NS == 2) {
-                mbar_wait(barM, phM);
-                phM ^= 1u;
+                mbar_wait(barM1, phM1);
+                phM1 ^= 1u;
                 tc_fence_after();
-                TB_STAMP(4);
+                TB_STAMP(1);
                 // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
                 if ((warp & 3) < 2 && 32 * qtr < fc) {
                     uint32_t v[32];
@@ -448,11 +488,11 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 tc_fence_before();
                 mbar_arrive(barB);
             }
-            TB_STAMP(5);
-            mbar_wait(barM, phM);
-            phM ^= 1u;
+            TB_STAMP(2);
+            mbar_wait(barM2, phM2);
+            phM2 ^= 1u;
             tc_fence_after();
-            TB_STAMP(6);
+            TB_STAMP(3);
             // ---- E1: h = relu(D1), g_a = D3 * [D1 > 0] -> bf16 operands; thread -> hidden units 32q .. 32q+31 ----
             if (32 * qtr < fc) {
                 uint32_t av[32], gv[32];
@@ -476,12 +516,16 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             fence_proxy_async();
             tc_fence_before();
-            TB_STAMP(7);
             mbar_arrive(barC);
-            mbar_wait(barM, phM);                              // D4, D5 (fine), D6, GaU complete; operand region is free
-            phM ^= 1u;
+            TB_STAMP(4);
+            // ---- software pipeline: operands of the NEXT tile while the gradient MMAs of this one run ----
+            const int next = tile + (int)gridDim.x;
+            if (next < n_tiles) p1(next, iter + 1, gn_next);
+            TB_STAMP(5);
+            mbar_wait(barM3, phM3);                            // D6, GaU, D4, D5 (fine) complete; H | Ga are free
+            phM3 ^= 1u;
             tc_fence_after();
-            TB_STAMP(8);
+            TB_STAMP(6);
             if (NS == 2) {
                 // ---- GaU (rows 0..63) -> bf16 -> [(j/8)*1024 + q*16]: K-major A of D7, MN-major A of the gW1 coarse part ----
                 if ((warp & 3) < 2 && 32 * qtr < fc) {
@@ -502,7 +546,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 tc_fence_before();
                 mbar_arrive(barD);
             }
-            // ---- E2: D6 -> fp32 planes (overlay the operand region) ----
+            // ---- E2: D6 -> fp32 planes (overlay H | Ga) ----
             {
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
@@ -519,7 +563,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 }
                 if (16 * qtr < N6) {
                     uint32_t v[16];
-                    tmem_ld16(tmem_lane + TB_D1 + 16u * (uint32_t)qtr, v);
+                    tmem_ld16(tmem_lane + TB_D3 + 16u * (uint32_t)qtr, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -534,22 +578,11 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         }
                     }
                 }
+                if (NS == 1) { tc_fence_before(); mbar_arrive(barE); }      // D6 read: D3's columns are free again
             }
-            // ---- P7 (early): zero the consumed tile of g_{t+1} in global memory (it is the output of the next launch) ----
-            if (a.zero_in) {
-                const int c = tid >> 5, rr = (tid >> 2) & 7, x4 = (tid & 3) * 4;
-                if (c < C && y0 + rr < H && x0 + x4 < W)
-                    *reinterpret_cast<float4*>(a.g_in + ((size_t)b * C + c) * plane + (size_t)(y0 + rr) * W + x0 + x4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (NS == 2 && a.zero_cin && tid < 128) {
-                const int c = tid >> 3, rr = (tid >> 1) & 3, x4 = (tid & 1) * 4;
-                if (c < C && (y0 >> 1) + rr < (H >> 1) && (x0 >> 1) + x4 < (W >> 1))
-                    *reinterpret_cast<float4*>(a.gc_in + ((size_t)b * C + c) * (plane >> 2) + (size_t)((y0 >> 1) + rr) * (W >> 1) + (x0 >> 1) + x4) =
-                        make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            TB_STAMP(9);
+            TB_STAMP(7);
             bar_sync_n(1, TB_NCOMP);
-            TB_STAMP(10);
+            TB_STAMP(8);
             // ---- P5: transposed fine perception -> red.add into dL/dx_t.  warp = (channel pair, 5-row block), lane =
             //      (channel of the pair, column): channel planes are 240 floats = 16 banks apart -> conflict-free reads ----
             {
@@ -560,26 +593,24 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     const float* Y = X + C * TB_PP;
                     const float* Lp = Y + C * TB_PP;
                     float* gob = a.g_out + ((size_t)b * C + c) * plane;
-                    {
-                        const int ox = (lane & 15) + 1;      // ring column of the interior cell
-                        float out[5];
-                        tb_stencil_t<5, TB_PS>(X, Y, Lp, 5 * vb, ox, out);
+                    const int ox = (lane & 15) + 1;      // ring column of the interior cell
+                    float out[5];
+                    tb_stencil_t<5, TB_PS>(X, Y, Lp, 5 * vb, ox, out);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const int oy = 5 * vb + k;
+                        if (oy >= 1 && oy <= T2_TH) out[k] += sCtr[(c * T2_TH + oy - 1) * T2_TW + ox - 1];
+                    }
+                    if (!border) {       // every position is inside the image: coalesced rows, no folding
+                        float* p = gob + (size_t)(y0 - 1 + 5 * vb) * W + x0 + ox - 1;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) { atomicAdd(p, out[k]); p += W; }
+                    } else {
+                        const int tx = tb_fold(x0 + ox - 1, W, g.pad);
 #pragma unroll
                         for (int k = 0; k < 5; ++k) {
-                            const int oy = 5 * vb + k;
-                            if (oy >= 1 && oy <= T2_TH) out[k] += sCtr[(c * T2_TH + oy - 1) * T2_TW + ox - 1];
-                        }
-                        if (!border) {       // every position is inside the image: coalesced rows, no folding
-                            float* p = gob + (size_t)(y0 - 1 + 5 * vb) * W + x0 + ox - 1;
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) { atomicAdd(p, out[k]); p += W; }
-                        } else {
-                            const int tx = tb_fold(x0 + ox - 1, W, g.pad);
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) {
-                                const int ty = tb_fold(y0 - 1 + 5 * vb + k, H, g.pad);
-                                if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[k]);
-                            }
+                            const int ty = tb_fold(y0 - 1 + 5 * vb + k, H, g.pad);
+                            if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[k]);
                         }
                     }
                 }
@@ -604,19 +635,20 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
                 }
             }
-            TB_STAMP(11);
+            TB_STAMP(9);
             if (NS == 2) {
-                mbar_wait(barM, phM);                          // D5 coarse part, D7 complete
-                phM ^= 1u;
+                mbar_wait(barM4, phM4);                        // D5 coarse part, D7 complete
+                phM4 ^= 1u;
                 tc_fence_after();
-                TB_STAMP(12);
+                bar_sync_n(1, TB_NCOMP);                       // every P5 read of the fine planes is done: reuse them
+                TB_STAMP(10);
                 // ---- D7 -> coarse planes (zero padded [10][14], footprint cell (qy,qx) at [qy+2][qx+2]) ----
                 for (int i = tid; i < 3 * C * TB_CPP / 2; i += TB_NCOMP) reinterpret_cast<float2*>(sCPX)[i] = make_float2(0.f, 0.f);
                 bar_sync_n(1, TB_NCOMP);
                 if ((warp & 3) < 2 && 16 * qtr < N6) {      // warp-uniform: the TMEM load is .sync.aligned
                     uint32_t v[16];
                     const int qy = r / T2_QW, qx = r % T2_QW;
-                    tmem_ld16(tmem_lane + TB_D1 + 64u + 16u * (uint32_t)qtr, v);
+                    tmem_ld16(tmem_lane + TB_D3 + 64u + 16u * (uint32_t)qtr, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -631,44 +663,50 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(barE);                             // D7 read: D3's columns are free again
                 bar_sync_n(1, TB_NCOMP);
                 const int Hc = H >> 1, Wc = W >> 1;
                 const int cy0 = (y0 >> 1) - 1, cx0 = (x0 >> 1) - 1;          // coarse coordinates of footprint cell (0,0)
                 if (border) {
                     // transpose of the replicate extension: footprint cells outside the image fold into the clamped cell
-                    // (rows first, then columns; one thread per (array, channel, column / row) so nothing races)
-                    for (int i = tid; i < 4 * C * T2_QW; i += TB_NCOMP) {
-                        const int qx = i % T2_QW, c = (i / T2_QW) % C, arr = i / (T2_QW * C);
-                        float* base = arr < 3 ? sCPX + (arr * C + c) * TB_CPP + 2 * TB_CPS + qx + 2 : sCCtr + c * T2_QH * T2_QW + qx;
-                        const int S = arr < 3 ? TB_CPS : T2_QW;
-                        for (int qy = 0; qy < T2_QH; ++qy) {
-                            const int Qy = cy0 + qy;
-                            if (Qy >= 0 && Qy < Hc) continue;
-                            const int ty = min(max(Qy, 0), Hc - 1) - cy0;
-                            if (ty >= 0 && ty < T2_QH) base[ty * S] += base[qy * S];
-                            base[qy * S] = 0.0f;
+                    // (rows, then columns; one thread per (array, channel, column / row) so nothing races); a pass is skipped
+                    // when the footprint does not leave the image in that direction
+                    if (cy0 < 0 || cy0 + T2_QH > Hc) {
+                        for (int i = tid; i < 4 * C * T2_QW; i += TB_NCOMP) {
+                            const int qx = i % T2_QW, c = (i / T2_QW) % C, arr = i / (T2_QW * C);
+                            float* base = arr < 3 ? sCPX + (arr * C + c) * TB_CPP + 2 * TB_CPS + qx + 2 : sCCtr + c * T2_QH * T2_QW + qx;
+                            const int S = arr < 3 ? TB_CPS : T2_QW;
+                            for (int qy = 0; qy < T2_QH; ++qy) {
+                                const int Qy = cy0 + qy;
+                                if (Qy >= 0 && Qy < Hc) continue;
+                                const int ty = min(max(Qy, 0), Hc - 1) - cy0;
+                                if (ty >= 0 && ty < T2_QH) base[ty * S] += base[qy * S];
+                                base[qy * S] = 0.0f;
+                            }
                         }
+                        bar_sync_n(1, TB_NCOMP);
                     }
-                    bar_sync_n(1, TB_NCOMP);
-                    for (int i = tid; i < 4 * C * T2_QH; i += TB_NCOMP) {
-                        const int qy = i % T2_QH, c = (i / T2_QH) % C, arr = i / (T2_QH * C);
-                        float* base = arr < 3 ? sCPX + (arr * C + c) * TB_CPP + (qy + 2) * TB_CPS + 2 : sCCtr + (c * T2_QH + qy) * T2_QW;
-                        for (int qx = 0; qx < T2_QW; ++qx) {
-                            const int Qx = cx0 + qx;
-                            if (Qx >= 0 && Qx < Wc) continue;
-                            const int tx = min(max(Qx, 0), Wc - 1) - cx0;
-                            if (tx >= 0 && tx < T2_QW) base[tx] += base[qx];
-                            base[qx] = 0.0f;
+                    if (cx0 < 0 || cx0 + T2_QW > Wc) {
+                        for (int i = tid; i < 4 * C * T2_QH; i += TB_NCOMP) {
+                            const int qy = i % T2_QH, c = (i / T2_QH) % C, arr = i / (T2_QH * C);
+                            float* base = arr < 3 ? sCPX + (arr * C + c) * TB_CPP + (qy + 2) * TB_CPS + 2 : sCCtr + (c * T2_QH + qy) * T2_QW;
+                            for (int qx = 0; qx < T2_QW; ++qx) {
+                                const int Qx = cx0 + qx;
+                                if (Qx >= 0 && Qx < Wc) continue;
+                                const int tx = min(max(Qx, 0), Wc - 1) - cx0;
+                                if (tx >= 0 && tx < T2_QW) base[tx] += base[qx];
+                                base[qx] = 0.0f;
+                            }
                         }
+                        bar_sync_n(1, TB_NCOMP);
                     }
-                    bar_sync_n(1, TB_NCOMP);
                 }
-                TB_STAMP(13);
+                TB_STAMP(11);
                 // ---- P6: transposed coarse perception -> red.add into the coarse gradient buffer.
-                //      warp = channel, lane = (4-row block, column of the 8 x 12 coarse ring) ----
+                //      warp = (channel pair, 4-row block), lane = (channel of the pair, column of the 8 x 12 coarse ring):
+                //      coarse channel planes are 140 floats = 12 banks apart -> conflict-free reads ----
                 {
-                    // warp = (channel pair, 4-row block), lane = (channel of the pair, column of the 8 x 12 coarse ring):
-                    // coarse channel planes are 140 floats = 12 banks apart -> conflict-free reads
                     const int cp = warp >> 1, vb = warp & 1, hc = lane / 12, ox = lane % 12;
                     const int c = 2 * cp + hc;
                     if (c < C && lane < 24) {
@@ -698,9 +736,11 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
                 }
             }
-            TB_STAMP(14);
-            bar_sync_n(1, TB_NCOMP);     // the planes overlay the operand region the next tile's P1 writes
-            TB_STAMP(15);
+            TB_STAMP(12);
+            bar_sync_n(1, TB_NCOMP);     // the planes overlay H | Ga, which the next tile's E1 writes
+            TB_STAMP(13);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gn[i] = gn_next[i];
         }
         // ---- flush: D4 [fc x 16] -> gW2p[j][c];  D5 [fc x K1] -> gW1p[k][j] (k' -> reference k, perception columns x s0) ----
         {
