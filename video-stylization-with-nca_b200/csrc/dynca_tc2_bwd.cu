@@ -368,19 +368,16 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         };
         // ---- P1 of a tile: perception operands A1 / Zc (-> barrier A), g = dL/dx_{t+1} and Gy (-> barrier G).
         //      Runs for tile i+1 while the gradient MMAs of tile i are in flight.  itn = iteration index of that tile. ----
-        auto p1 = [&](int tile_, int itn, float (&gn)[4]) {
+        // p1a: stage wait, border patch, fine perception -> A1, cond chunk.   p1b: coarse perception -> Zc (-> A), Gy (-> G).
+        auto p1a = [&](int tile_, int itn) {
             int b, y0, x0;
             t2_tile_decode(a.tl, tile_, b, y0, x0);
             const int gy = y0 + py, gx = x0 + px;
             const bool inimg = gy < H && gx < W;
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
                                 (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
-            const int par = itn & 1;
-            uint8_t* sA1 = sA12 + (uint32_t)par * bg.a1_bytes;
-            uint8_t* sZc = sZc2 + (uint32_t)par * 8192u;
-            uint8_t* sGy = sGy2 + (uint32_t)par * 4096u;
-            const float* sFire = sFire2 + par * 128;
-            const uint32_t* sCpe = sCpe2 + par * 24;
+            uint8_t* sA1 = sA12 + (uint32_t)(itn & 1) * bg.a1_bytes;
+            const uint32_t* sCpe = sCpe2 + (itn & 1) * 24;
             mbar_wait(barT, phT);
             phT ^= 1u;
             if (border && g.pad != NCA_PAD_CONSTANT) {
@@ -402,6 +399,18 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
                     *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
             }
+        };
+        auto p1b = [&](int tile_, int itn, float (&gn)[4]) {
+            int b, y0, x0;
+            t2_tile_decode(a.tl, tile_, b, y0, x0);
+            const int gy = y0 + py, gx = x0 + px;
+            const bool inimg = gy < H && gx < W;
+            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
+                                (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
+            const int par = itn & 1;
+            uint8_t* sZc = sZc2 + (uint32_t)par * 8192u;
+            uint8_t* sGy = sGy2 + (uint32_t)par * 4096u;
+            const float* sFire = sFire2 + par * 128;
             if (NS == 2) t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
             fence_proxy_async();
             tc_fence_before();
@@ -455,7 +464,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         float gn[4] = {0.f, 0.f, 0.f, 0.f}, gn_next[4] = {0.f, 0.f, 0.f, 0.f};
         if ((int)blockIdx.x < n_tiles) tables(blockIdx.x, 0);
         bar_sync_n(1, TB_NCOMP);
-        if ((int)blockIdx.x < n_tiles) p1(blockIdx.x, 0, gn);
+        if ((int)blockIdx.x < n_tiles) { p1a(blockIdx.x, 0); p1b(blockIdx.x, 0, gn); }
 #define TB_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
@@ -489,6 +498,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 mbar_arrive(barB);
             }
             TB_STAMP(2);
+            const int next = tile + (int)gridDim.x;
+            if (next < n_tiles) p1a(next, iter + 1);          // software pipeline, part 1: in the shadow of D1 / D3
             mbar_wait(barM2, phM2);
             phM2 ^= 1u;
             tc_fence_after();
@@ -518,9 +529,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             tc_fence_before();
             mbar_arrive(barC);
             TB_STAMP(4);
-            // ---- software pipeline: operands of the NEXT tile while the gradient MMAs of this one run ----
-            const int next = tile + (int)gridDim.x;
-            if (next < n_tiles) p1(next, iter + 1, gn_next);
+            // ---- software pipeline, part 2: rest of the NEXT tile's operands while the gradient MMAs of this one run ----
+            if (next < n_tiles) p1b(next, iter + 1, gn_next);
             TB_STAMP(5);
             mbar_wait(barM3, phM3);                            // D6, GaU, D4, D5 (fine) complete; H | Ga are free
             phM3 ^= 1u;
