@@ -192,3 +192,31 @@ def test_tc2_ragged_shapes_vs_emulated_oracle(case):
     assert rel_err(fg.detach().cpu(), fe) < EMU_STATE_TOL
     for a, n in zip(pg, ("x0", "w1", "b1", "w2", "b2")):
         assert float((a.grad.cpu() - ge[n]).norm() / (ge[n].norm() + 1e-30)) < EMU_GRAD_RMS_TOL, n
+
+
+def test_tc2_c5_frame_properties():
+    """config-5 frame size (1920x1080, EC flavour C=13, circular): never-firing cells keep their value bit-exactly,
+    Philox == supplied mask, bf16 close to fp32, and the rollout is translation-equivariant under circular padding
+    (a size-independent property of the step: shifting the input and the mask by whole tiles shifts the output)."""
+    torch.manual_seed(4)
+    B, C, fc, H, W, T = 1, 13, 96, 1080, 1920, 3
+    kw = dict(fc_dim=fc, padding_mode="circular", pos_emb=None, device=torch.device(DEV))
+    mb = nca_b200.DyNCA_EC(C, 3, precision="bf16", **kw)
+    mf = nca_b200.DyNCA_EC(C, 3, precision="fp32", **kw)
+    mf.load_state_dict(mb.state_dict())
+    cfg = mb._cfg(_lib.NCA_COND_NONE, 0)
+    assert Fn.dynca_kernel_variant(cfg, B, H, W) == 2
+    x0 = torch.rand(B, C, H, W, device=DEV) - 0.5
+    with torch.no_grad():
+        s, _ = mb.forward_nsteps(x0, T, masks=torch.zeros(T, B, 1, H, W, device=DEV))
+        assert torch.equal(s, x0)
+        masks = Fn.philox_mask(B, H, W, 0.5, 9, T)
+        a, _ = mb.forward_nsteps(x0, T, seed=9)
+        b, _ = mb.forward_nsteps(x0, T, masks=masks)
+        assert torch.equal(a, b)
+        f, _ = mf.forward_nsteps(x0, T, masks=masks)
+        assert rel_err((a - x0).cpu(), (f - x0).cpu()) < ROLLOUT_TOL
+        dy, dx = 13, 7      # not multiples of the 8x16 tile: every cell lands in a different tile row / lane
+        xs, ms = torch.roll(x0, (dy, dx), (2, 3)), torch.roll(masks, (dy, dx), (3, 4))
+        c, _ = mb.forward_nsteps(xs.contiguous(), T, masks=ms.contiguous())
+        assert torch.equal(torch.roll(a, (dy, dx), (2, 3)), c)
