@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NCA_B200_ABI_VERSION 2
+#define NCA_B200_ABI_VERSION 3
 
 enum { NCA_OK = 0, NCA_ERR_ARG = -1, NCA_ERR_UNSUPPORTED = -2, NCA_ERR_CUDA = -3, NCA_ERR_WORKSPACE = -4 };
 
@@ -133,6 +133,8 @@ typedef struct NcaEncDesc {
     float   alive_thr;        /* 0.1 (nca.py:163)                                             */
     float   fire_rate;        /* cell_fire_rate (nca.py:67)                                   */
     float   clamp;            /* 10.0 (nca.py:194)                                            */
+    int32_t precision;        /* NCA_PREC_*: BF16 runs the forward update MLP on tcgen05 (W % 4 == 0,
+                                 alive_thr >= 0; other shapes and the BPTT use the fp32 kernels)      */
 } NcaEncDesc;
 
 /* wp [3C,1,3,3] perception_net.weight; wa [hid,3C], ba [hid]; wb [hid,hid], bb [hid]; wc [C,hid]. */

@@ -30,13 +30,13 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_workspace(lib):
-    assert lib.nca_abi_version() == 2
+    assert lib.nca_abi_version() == 3
     d = _lib.DyncaDesc(8, 16, 256, 256, 128, _lib.NCA_COND_CPE, 2, 1, 2, 0, _lib.NCA_MASK_PHILOX, 0.5)
     fwd = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
     bwd = lib.nca_dynca_workspace_bytes(C.byref(d), 1)
     assert 0 < fwd < bwd
     assert bwd >= 2 * 8 * 16 * 256 * 256 * 4
-    e = _lib.EncDesc(4, 20, 64, 64, 64, 3, _lib.NCA_MASK_PHILOX, 0.1, 0.5, 10.0)
+    e = _lib.EncDesc(4, 20, 64, 64, 64, 3, _lib.NCA_MASK_PHILOX, 0.1, 0.5, 10.0, 0)
     assert 0 < lib.nca_enc_workspace_bytes(C.byref(e), 0) < lib.nca_enc_workspace_bytes(C.byref(e), 1)
     e.hid = 32
     assert lib.nca_enc_workspace_bytes(C.byref(e), 0) == 0

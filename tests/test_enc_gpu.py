@@ -128,3 +128,60 @@ def test_enc_module_grow_with_encoder_gradient():
         y, _ = nca((x, ge.to(DEV)), masks=masks[:1])
     assert rel_err(y.cpu(), O.enc_step(x.cpu(), ge, wp, *mlp, masks[0].cpu(), 3, 0.1)) < STATE_TOL
     assert nca.alive(out).dtype == torch.bool
+
+
+# ---- tcgen05 forward path (NCA_PREC_BF16): update MLP with bf16 operands, fp32 accumulate -----------------------
+BF16_STEP_TOL = 1e-2
+
+
+def _life_agree(got, want):
+    """cells whose alive / clamp decision agrees between the two results (a bf16-sized change of the living channel
+    next to the 0.1 threshold may flip a cell; such cells are excluded and must be rare)"""
+    dead_g = got.abs().sum(1, keepdim=True) == 0
+    dead_w = want.abs().sum(1, keepdim=True) == 0
+    return dead_g == dead_w
+
+
+@pytest.mark.parametrize("name", ENC_CASES)
+def test_enc_bf16_single_steps(name):
+    t, m = load_case(name)
+    cfg = Fn.EncConfig(m["C"], m["living_dim"], m["thr"], m["rate"], precision="bf16")
+    ws = [t[k].to(DEV) for k in NAMES]
+    with torch.no_grad():
+        x = t["x0"]
+        for s in range(min(3, m["T"])):
+            want = O.enc_step(x, t["goal_enc"], *[t[k] for k in NAMES], t["fires"][s], m["living_dim"], m["thr"])
+            got = Fn.enc_rollout(cfg, x.to(DEV), t["goal_enc"].to(DEV), *ws, 1, masks=t["fires"][s:s + 1].to(DEV)).cpu()
+            ok = _life_agree(got, want)
+            assert float(ok.float().mean()) > 0.99
+            upd_g, upd_w = (got - x) * ok, (want - x) * ok
+            assert rel_err(upd_g, upd_w) < BF16_STEP_TOL
+            x = want
+
+
+def test_enc_bf16_c4_frame_properties():
+    """c4 frame size, batch 32: never-firing cells with a full-alive state keep their value bit-exactly; Philox ==
+    supplied mask; bf16 update close to the fp32 kernels; gradients flow (fp32 BPTT kernels)"""
+    torch.manual_seed(2)
+    B, H = 32, 64
+    nb = nca_b200.ConditionedNCA(target_shape=(3, H, H), num_hidden_channels=16, living_channel_dim=3, precision="bf16").to(DEV)
+    nf = nca_b200.ConditionedNCA(target_shape=(3, H, H), num_hidden_channels=16, living_channel_dim=3).to(DEV)
+    nf.load_state_dict(nb.state_dict())
+    x = 0.3 * torch.randn(B, 20, H, H, device=DEV)
+    x[:, 3] = 0.5 + 0.2 * torch.rand(B, H, H, device=DEV)          # everything alive, far from the threshold
+    goal = torch.rand(B, 3, H, H, device=DEV)
+    with torch.no_grad():
+        ge = nb._pad_goal(nb.encoder(goal))
+        cfgb, cfgf = nb._cfg(), nf._cfg()
+        w = [p.detach() for p in nb._w()]
+        same = Fn.enc_rollout(cfgb, x, ge, *w, 2, masks=torch.zeros(2, B, 1, H, H, device=DEV))
+        assert torch.equal(same, x)
+        a = Fn.enc_rollout(cfgb, x, ge, *w, 3, seed=21)
+        b = Fn.enc_rollout(cfgb, x, ge, *w, 3, masks=Fn.philox_mask(B, H, H, 0.5, 21, 3, enc=True))
+        assert torch.equal(a, b)
+        f = Fn.enc_rollout(cfgf, x, ge, *w, 1, seed=21)
+        a1 = Fn.enc_rollout(cfgb, x, ge, *w, 1, seed=21)
+        assert rel_err((a1 - x).cpu(), (f - x).cpu()) < BF16_STEP_TOL
+    out = nb.grow(x, 4, goal, seed=5)
+    out.square().mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in nb.parameters() if p.requires_grad)

@@ -32,7 +32,7 @@ class DyncaWeights(C.Structure):
 class EncDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("hid", C.c_int32),
                 ("living_dim", C.c_int32), ("mask_mode", C.c_int32), ("alive_thr", C.c_float),
-                ("fire_rate", C.c_float), ("clamp", C.c_float)]
+                ("fire_rate", C.c_float), ("clamp", C.c_float), ("precision", C.c_int32)]
 
 
 class EncWeights(C.Structure):
@@ -80,7 +80,7 @@ def load_library():
     lib.nca_enc_forward.argtypes = [C.POINTER(EncDesc), C.POINTER(EncWeights), P, P, U64, I, I, I, P, P, P, SZ, P]
     lib.nca_enc_backward.argtypes = [C.POINTER(EncDesc), C.POINTER(EncWeights), P, P, U64, I, I, P, P, P, P, P,
                                      C.POINTER(EncWeights), P, SZ, P]
-    if lib.nca_abi_version() != 2:
+    if lib.nca_abi_version() != 3:
         raise NcaError("libnca_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -265,14 +265,14 @@ __device__ __forceinline__ void t2_coarse_to_zc(const DyncaGeom& g, const float*
     }
 }
 // fire decisions of one 8x16 tile by ONE warp: 32 lanes = 32 quads of 4 consecutive pixels -> sFire[128]
-__device__ __forceinline__ void t2_fire_tile(const FireMask& fm, int b, int y0, int x0, int H, int W, int lane, float* __restrict__ sFire) {
+__device__ __forceinline__ void t2_fire_tile(const FireMask& fm, int b, int y0, int x0, int H, int W, int lane, float* __restrict__ sFire, int enc = 0) {
     const int fy = y0 + (lane >> 2), fx = x0 + 4 * (lane & 3);
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
     if (fy < H && fx < W) {
         const uint32_t p = (uint32_t)(fy * W + fx);
         const uint4 rr = nca_philox4x32_10(p >> 2, (uint32_t)b, fm.t, NCA_PHILOX_STREAM, fm.k0, fm.k1);
-        f.x = nca_fire(rr.x, fm.thr, 0); f.y = nca_fire(rr.y, fm.thr, 0);
-        f.z = nca_fire(rr.z, fm.thr, 0); f.w = nca_fire(rr.w, fm.thr, 0);
+        f.x = nca_fire(rr.x, fm.thr, enc); f.y = nca_fire(rr.y, fm.thr, enc);
+        f.z = nca_fire(rr.z, fm.thr, enc); f.w = nca_fire(rr.w, fm.thr, enc);
     }
     *reinterpret_cast<float4*>(sFire + (lane >> 2) * 16 + 4 * (lane & 3)) = f;
 }
@@ -292,12 +292,12 @@ static inline T2EncodeFn t2_encode_fn() {
     return fn;
 }
 // 5-D map over [slots][B][C][Hh][Ww] fp32 with box [1][1][C][bh][bw]
-static inline int t2_make_map(CUtensorMap* tm, const float* base, int slots, size_t slot_floats, int B, int C, int Hh, int Ww, int bh, int bw) {
+static inline int t2_make_map(CUtensorMap* tm, const float* base, int slots, size_t slot_floats, int B, int C, int Hh, int Ww, int bh, int bw, int bc = 0) {
     T2EncodeFn fn = t2_encode_fn();
     if (!fn) { nca_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NCA_ERR_CUDA; }
     cuuint64_t dims[5] = {(cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)C, (cuuint64_t)B, (cuuint64_t)slots};
     cuuint64_t strides[4] = {(cuuint64_t)Ww * 4, (cuuint64_t)Hh * Ww * 4, (cuuint64_t)C * Hh * Ww * 4, (cuuint64_t)slot_floats * 4};
-    cuuint32_t box[5] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)C, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)(bc > 0 ? bc : C), 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

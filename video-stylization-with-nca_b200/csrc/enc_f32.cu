@@ -467,6 +467,7 @@ static int enc_make_geom(const NcaEncDesc* d, EncGeom* g) {
     NCA_CHECK_ARG(d->hid == ENC_HID, "ConditionedNCA: hidden width must be 64 (nca.py:40-46), got %d", d->hid);
     NCA_CHECK_ARG(d->living_dim < d->C, "living_dim=%d out of range", d->living_dim);
     NCA_CHECK_ARG(d->mask_mode == NCA_MASK_SUPPLIED || d->mask_mode == NCA_MASK_PHILOX, "bad mask_mode");
+    NCA_CHECK_ARG(d->precision == NCA_PREC_FP32 || d->precision == NCA_PREC_BF16, "bad precision %d", d->precision);
     NCA_CHECK_ARG((long long)d->H * d->W < (1ll << 31), "H*W too large");
     g->B = d->B; g->C = d->C; g->H = d->H; g->W = d->W; g->liv = d->living_dim < 0 ? -1 : d->living_dim;
     g->thr = d->alive_thr; g->clampv = d->clamp;
@@ -505,7 +506,8 @@ size_t nca_enc_workspace_bytes(const NcaEncDesc* d, int32_t backward) {
     EncGeom g;
     if (enc_make_geom(d, &g)) return 0;
     const size_t n = nca_align_up((size_t)g.B * g.C * g.H * g.W, 64);
-    return (nca_align_up(ENC_BWD_WFLOATS, 64) + (backward ? 2 * n : n)) * sizeof(float);
+    // [padded fp32 weights | x1 (forward) or 2 state-gradient buffers (backward) | tcgen05 operand images (forward, bf16)]
+    return (nca_align_up(ENC_BWD_WFLOATS, 64) + (backward ? 2 * n : n)) * sizeof(float) + (backward ? 0 : enc_tc_weight_bytes(d));
 }
 
 int nca_enc_forward(const NcaEncDesc* d, const NcaEncWeights* w, const float* goal, const float* masks, uint64_t seed,
@@ -527,6 +529,26 @@ int nca_enc_forward(const NcaEncDesc* d, const NcaEncWeights* w, const float* go
     cudaStream_t s = (cudaStream_t)stream;
     float* wsW = (float*)workspace;
     float* x1 = wsW + nca_align_up(ENC_BWD_WFLOATS, 64);
+    const size_t n = (size_t)g.B * g.C * g.H * g.W, cells = (size_t)g.B * g.H * g.W;
+    const int lgrid = (int)((cells + 255) / 256 < (size_t)enc_num_sms() * 8 ? (cells + 255) / 256 : (size_t)enc_num_sms() * 8);
+    if (enc_tc_supported(d) && T > 0) {
+        // tcgen05 path: x1 by enc_fwd_tc_kernel, then the life / clamp pass
+        void* wsT = (void*)(x1 + nca_align_up(n, 64));
+        rc = enc_tc_prep_weights(d, w, wsT, s);
+        if (rc) return rc;
+        EncTcMaps maps;
+        rc = enc_tc_make_maps(d, states, keep_history ? T + 1 : 2, goal, &maps);
+        if (rc) return rc;
+        for (int t = 0; t < T; ++t) {
+            const int si = keep_history ? t : (t & 1), so = keep_history ? t + 1 : ((t + 1) & 1);
+            rc = enc_tc_forward_step(d, w, wsT, &maps, si, x1, enc_mask(d, g, masks, seed, t0, t), s);
+            if (rc) return rc;
+            enc_life_kernel<<<lgrid, 256, 0, s>>>(g, states + (size_t)si * n, x1, states + (size_t)so * n,
+                                                  keep_history ? life_hist + (size_t)t * cells : nullptr);
+            NCA_LAUNCH_OK();
+        }
+        return NCA_OK;
+    }
     enc_prep_weights_kernel<<<32, 256, 0, s>>>(g.C, w->wp, w->wa, w->ba, w->wb, w->bb, w->wc, wsW);
     NCA_LAUNCH_OK();
     const size_t smem = enc_smem_floats(false) * sizeof(float);
@@ -535,8 +557,6 @@ int nca_enc_forward(const NcaEncDesc* d, const NcaEncWeights* w, const float* go
     a.g = g; a.goal = goal; a.wsW = wsW; a.x1 = x1;
     a.tiles_x = (g.W + ET_TW - 1) / ET_TW; a.tiles_y = (g.H + ET_TH - 1) / ET_TH; a.n_tiles = g.B * a.tiles_x * a.tiles_y;
     const int grid = a.n_tiles < enc_num_sms() ? a.n_tiles : enc_num_sms();
-    const size_t n = (size_t)g.B * g.C * g.H * g.W, cells = (size_t)g.B * g.H * g.W;
-    const int lgrid = (int)((cells + 255) / 256 < (size_t)enc_num_sms() * 8 ? (cells + 255) / 256 : (size_t)enc_num_sms() * 8);
     for (int t = 0; t < T; ++t) {
         const float* xin = keep_history ? states + (size_t)t * n : states + (size_t)(t & 1) * n;
         float* xout = keep_history ? states + (size_t)(t + 1) * n : states + (size_t)((t + 1) & 1) * n;

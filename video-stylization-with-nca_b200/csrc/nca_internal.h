@@ -49,3 +49,12 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
                             int cslot_in, const float* xc_in, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
                             int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out,
                             const float* cond, const FireMask& fm, cudaStream_t s);
+
+// enc_tc.cu (ConditionedNCA forward on tcgen05)
+struct EncTcMaps { alignas(64) unsigned char x[128]; alignas(64) unsigned char l[128]; alignas(64) unsigned char g[128]; };
+bool enc_tc_supported(const NcaEncDesc* d);
+size_t enc_tc_weight_bytes(const NcaEncDesc* d);
+int enc_tc_prep_weights(const NcaEncDesc* d, const NcaEncWeights* w, void* ws, cudaStream_t s);
+int enc_tc_make_maps(const NcaEncDesc* d, const float* states, int slots, const float* goal, EncTcMaps* m);
+int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void* ws, const EncTcMaps* m, int slot_in, float* x1,
+                        const FireMask& fm, cudaStream_t s);

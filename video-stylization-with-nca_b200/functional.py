@@ -252,13 +252,14 @@ def dynca_rollout(cfg, x0, w1, b1, w2, b2, T, rate=0.5, cond=None, masks=None, s
 class EncConfig:
     """Static description of a ConditionedNCA (ctor arguments of nca.py:62-74)."""
 
-    def __init__(self, C_, living_dim, alive_thr=0.1, fire_rate=0.5, hid=64, clamp=10.0):
+    def __init__(self, C_, living_dim, alive_thr=0.1, fire_rate=0.5, hid=64, clamp=10.0, precision="fp32"):
         self.C, self.living_dim, self.alive_thr, self.fire_rate, self.hid, self.clamp = C_, living_dim, alive_thr, fire_rate, hid, clamp
+        self.precision = _lib.NCA_PREC[precision]
 
     def desc(self, B, H, W, supplied):
         return _lib.EncDesc(B, self.C, H, W, self.hid, self.living_dim,
                             _lib.NCA_MASK_SUPPLIED if supplied else _lib.NCA_MASK_PHILOX,
-                            float(self.alive_thr), float(self.fire_rate), float(self.clamp))
+                            float(self.alive_thr), float(self.fire_rate), float(self.clamp), self.precision)
 
 
 def _enc_weights_struct(ws):

@@ -69,8 +69,9 @@ class UpdateNet(nn.Module):
 class ConditionedNCA(nn.Module):
     def __init__(self, encoder: nn.Module = None, target_shape: Tuple[int] = (3, 64, 64), num_hidden_channels=16,
                  use_living_channel: bool = True, living_channel_dim: Optional[int] = None,
-                 alpha_living_threshold: float = 0.1, cell_fire_rate: float = 0.5, zero_bias=True):
+                 alpha_living_threshold: float = 0.1, cell_fire_rate: float = 0.5, zero_bias=True, *, precision='fp32'):
         super().__init__()
+        self.precision = precision
         self.target_shape = target_shape
         self.num_target_channels = target_shape[0]
         self.image_size = target_shape[-1]
@@ -89,7 +90,7 @@ class ConditionedNCA(nn.Module):
     # -- CUDA path plumbing ----------------------------------------------------------------------------
     def _cfg(self):
         return Fn.EncConfig(self.num_channels, self.living_channel_dim if self.use_living_channel else -1,
-                            self.alpha_living_threshold, self.cell_fire_rate)
+                            self.alpha_living_threshold, self.cell_fire_rate, precision=self.precision)
 
     def _w(self):
         o = self.update_net.out
