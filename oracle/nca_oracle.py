@@ -409,3 +409,57 @@ def enc_rollout(x, goal, wp, wa, ba, wb, bb, wc, fires, living_dim=3, thr=0.1, k
         if keep:
             hist.append(x)
     return (x, hist) if keep else x
+
+
+# --------------------------------------------------------------------------------------
+# BF16-operand emulation of the ConditionedNCA step and its BPTT (checker for csrc/enc_tc.cu).
+# Rounding points: p -> bf16, Wa / Wb / Wc -> bf16, ba as bf16 hi + lo, h1 / h2 -> bf16 (bb added in fp32 before the relu);
+# backward: g_o = fire * g1 -> bf16, g_a2 / g_a1 -> bf16; gbb / gba sum the ROUNDED g_a2 / g_a1 (they ride the weight-gradient
+# MMAs); g_p, the transposed depthwise conv, gwp and the pass-through stay fp32.
+# --------------------------------------------------------------------------------------
+def enc_bf16emu_rollout_grads(x0, goal, wp, wa, ba, wb, bb, wc, fires, g_final, living_dim=3, thr=0.1, clampv=10.0):
+    T = fires.shape[0]
+    waq, wbq, wcq, baq = bf16r(wa), bf16r(wb), bf16r(wc), _hilo(ba)
+    xs, saved = [x0], []
+    x = x0
+    for t in range(T):
+        pre = enc_alive(x, living_dim, thr).to(x.dtype) if living_dim >= 0 else torch.ones_like(x[:, :1])
+        xin = (x + goal * pre).detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            p = enc_perception_fast(xin, wp)
+        pq = bf16r(p.detach())
+        a1 = torch.einsum("jk,bkhw->bjhw", waq, pq) + baq[None, :, None, None]
+        h1 = bf16r(torch.relu(a1))
+        a2 = torch.einsum("jk,bkhw->bjhw", wbq, h1) + bb[None, :, None, None]
+        h2 = bf16r(torch.relu(a2))
+        out = torch.einsum("cj,bjhw->bchw", wcq, h2)
+        x1 = x + fires[t] * out
+        post = enc_alive(x1, living_dim, thr).to(x.dtype) if living_dim >= 0 else torch.ones_like(pre)
+        life = pre * post
+        v = x1 * life
+        saved.append((xin, p, pq, h1, h2, pre, life, (v >= -clampv) & (v <= clampv)))
+        x = torch.clamp(v, -clampv, clampv)
+        xs.append(x)
+    g = g_final.clone()
+    G = {k: torch.zeros_like(t_) for k, t_ in dict(wp=wp, wa=wa, ba=ba, wb=wb, bb=bb, wc=wc, goal=goal).items()}
+    for t in range(T - 1, -1, -1):
+        xin, p, pq, h1, h2, pre, life, cm = saved[t]
+        g1 = g * cm.to(g.dtype) * life
+        go = bf16r(fires[t] * g1)
+        G["wc"] += torch.einsum("bchw,bjhw->cj", go, h2)
+        ga2 = bf16r(torch.einsum("bchw,cj->bjhw", go, wcq) * (h2 > 0).to(g.dtype))
+        G["wb"] += torch.einsum("bjhw,bkhw->jk", ga2, h1)
+        G["bb"] += ga2.sum(dim=(0, 2, 3))
+        ga1 = bf16r(torch.einsum("bjhw,jk->bkhw", ga2, wbq) * (h1 > 0).to(g.dtype))
+        G["wa"] += torch.einsum("bjhw,bkhw->jk", ga1, pq)
+        G["ba"] += ga1.sum(dim=(0, 2, 3))
+        gp = torch.einsum("bjhw,jk->bkhw", ga1, waq)
+        wpl = wp.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            p2 = enc_perception_fast(xin, wpl)
+        gxin, gwp = torch.autograd.grad(p2, [xin, wpl], gp)
+        G["wp"] += gwp
+        G["goal"] += gxin * pre
+        g = g1 + gxin
+    G["x0"] = g
+    return xs[-1], G

@@ -185,3 +185,28 @@ def test_enc_bf16_c4_frame_properties():
     out = nb.grow(x, 4, goal, seed=5)
     out.square().mean().backward()
     assert all(torch.isfinite(p.grad).all() for p in nb.parameters() if p.requires_grad)
+
+
+def _enc_bf16_vs_emu(t, m, T):
+    cfg = Fn.EncConfig(m["C"], m["living_dim"], m["thr"], m["rate"], precision="bf16")
+    ps = [t[k].to(DEV).requires_grad_(True) for k in NAMES]
+    x0 = t["x0"].to(DEV).requires_grad_(True)
+    goal = t["goal_enc"].to(DEV).requires_grad_(True)
+    final = Fn.enc_rollout(cfg, x0, goal, *ps, T, masks=t["fires"][:T].to(DEV))
+    (final * t["coef_final"].to(DEV)).sum().backward()
+    fe, ge = O.enc_bf16emu_rollout_grads(t["x0"], t["goal_enc"], *[t[k] for k in NAMES], t["fires"][:T], t["coef_final"],
+                                         m["living_dim"], m["thr"])
+    errs = {"state": rel_err(final.detach().cpu(), fe)}
+    for p, k in zip(ps + [x0, goal], list(NAMES) + ["x0", "goal"]):
+        errs[k] = float((p.grad.cpu() - ge[k]).norm() / (ge[k].norm() + 1e-30))
+    return errs
+
+
+@pytest.mark.parametrize("name", ENC_CASES)
+def test_enc_bf16_bptt_vs_emulated_oracle(name):
+    """tcgen05 forward + BPTT against the oracle that rounds the GEMM operands to bf16 at the same points"""
+    t, m = load_case(name)
+    errs = _enc_bf16_vs_emu(t, m, min(m["T"], 4))
+    print(name, {k: "%.1e" % v for k, v in errs.items()})
+    assert errs["state"] < 3e-3, errs
+    assert max(v for k, v in errs.items() if k != "state") < 1e-2, errs

@@ -506,8 +506,8 @@ size_t nca_enc_workspace_bytes(const NcaEncDesc* d, int32_t backward) {
     EncGeom g;
     if (enc_make_geom(d, &g)) return 0;
     const size_t n = nca_align_up((size_t)g.B * g.C * g.H * g.W, 64);
-    // [padded fp32 weights | x1 (forward) or 2 state-gradient buffers (backward) | tcgen05 operand images (forward, bf16)]
-    return (nca_align_up(ENC_BWD_WFLOATS, 64) + (backward ? 2 * n : n)) * sizeof(float) + (backward ? 0 : enc_tc_weight_bytes(d));
+    // [padded fp32 weights | x1 (forward) or 2 state-gradient buffers (backward) | tcgen05 operand images (bf16)]
+    return (nca_align_up(ENC_BWD_WFLOATS, 64) + (backward ? 2 * n : n)) * sizeof(float) + enc_tc_weight_bytes(d);
 }
 
 int nca_enc_forward(const NcaEncDesc* d, const NcaEncWeights* w, const float* goal, const float* masks, uint64_t seed,
@@ -602,6 +602,32 @@ int nca_enc_backward(const NcaEncDesc* d, const NcaEncWeights* w, const float* g
     if (T == 0) {
         if (g_final) NCA_CUDA_OK(cudaMemcpyAsync(gx0, g_final, nb, cudaMemcpyDeviceToDevice, s));
         else NCA_CUDA_OK(cudaMemsetAsync(gx0, 0, nb, s));
+        return NCA_OK;
+    }
+    if (enc_tc_bwd_supported(d)) {
+        // tcgen05 BPTT: one fused kernel per step; weight gradients go straight to the caller's buffers (zeroed above)
+        void* wsT = (void*)(gbuf[1] + nca_align_up(n, 64));
+        rc = enc_tc_prep_weights(d, w, wsT, s);
+        if (rc) return rc;
+        EncTcMaps maps, gm_final, gm[2];
+        rc = enc_tc_make_maps(d, states, T + 1, goal, &maps);
+        if (rc) return rc;
+        for (int p = 0; p < 2; ++p) { rc = enc_tc_make_gmap(d, gbuf[p], &gm[p]); if (rc) return rc; }
+        if (g_final) {
+            NCA_CHECK_ARG((((uintptr_t)g_final) & 15u) == 0, "g_final must be 16-byte aligned");
+            rc = enc_tc_make_gmap(d, g_final, &gm_final);
+            if (rc) return rc;
+        } else {
+            NCA_CUDA_OK(cudaMemsetAsync(gbuf[T & 1], 0, nb, s));      // zeros stand in for dL/d states[T]
+        }
+        for (int t = T - 1; t >= 0; --t) {
+            float* gout = t == 0 ? gx0 : gbuf[t & 1];
+            NCA_CUDA_OK(cudaMemsetAsync(gout, 0, nb, s));
+            const EncTcMaps* gmap = (t == T - 1) ? (g_final ? &gm_final : &gm[T & 1]) : &gm[(t + 1) & 1];
+            rc = enc_tc_backward_step(d, w, wsT, &maps, gmap, t, life_hist + (size_t)t * cells, gout, g_goal, gw,
+                                      enc_mask(d, g, masks, seed, t0, t), s);
+            if (rc) return rc;
+        }
         return NCA_OK;
     }
     const size_t smem = enc_smem_floats(true) * sizeof(float);

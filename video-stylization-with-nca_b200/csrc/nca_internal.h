@@ -58,3 +58,8 @@ int enc_tc_prep_weights(const NcaEncDesc* d, const NcaEncWeights* w, void* ws, c
 int enc_tc_make_maps(const NcaEncDesc* d, const float* states, int slots, const float* goal, EncTcMaps* m);
 int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void* ws, const EncTcMaps* m, int slot_in, float* x1,
                         const FireMask& fm, cudaStream_t s);
+bool enc_tc_bwd_supported(const NcaEncDesc* d);
+int enc_tc_make_gmap(const NcaEncDesc* d, const float* gnext, EncTcMaps* m);
+int enc_tc_backward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void* ws, const EncTcMaps* m, const EncTcMaps* gm,
+                         int slot_in, const uint8_t* life, float* g_out, float* g_goal, const NcaEncWeightGrads* gw,
+                         const FireMask& fm, cudaStream_t s);
