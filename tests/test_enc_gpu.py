@@ -210,3 +210,31 @@ def test_enc_bf16_bptt_vs_emulated_oracle(name):
     print(name, {k: "%.1e" % v for k, v in errs.items()})
     assert errs["state"] < 3e-3, errs
     assert max(v for k, v in errs.items() if k != "state") < 1e-2, errs
+
+
+TC_CASES = [  # B, C, H, W, T, living_dim  (W % 4 == 0: tcgen05 kernels)
+    (2, 20, 9, 36, 3, 3),        # ragged: partial tiles in both directions
+    (1, 20, 20, 24, 3, 3),
+    (1, 13, 16, 16, 2, 3),       # odd channel count: half-empty perception chunk
+    (1, 20, 16, 32, 2, -1),      # use_living_channel=False
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B%d_C%d_%dx%d_T%d_l%d" % c)
+def test_enc_bf16_ragged_shapes_vs_emulated_oracle(case):
+    B, C, H, W, T, liv = case
+    g = torch.Generator().manual_seed(41)
+    K = 3 * C
+    t = dict(wp=torch.randn(K, 1, 3, 3, generator=g) * 0.3, wa=torch.randn(64, K, generator=g) * 0.2,
+             ba=torch.randn(64, generator=g) * 0.1, wb=torch.randn(64, 64, generator=g) * 0.15,
+             bb=torch.randn(64, generator=g) * 0.1, wc=torch.randn(C, 64, generator=g) * 0.1)
+    x0 = torch.randn(B, C, H, W, generator=g) * 0.4
+    if liv >= 0:
+        x0[:, liv] = torch.rand(B, H, W, generator=g) * 0.5 - 0.15
+    x0[:, 0] *= 30.0                                              # some cells hit the +-10 clamp
+    t.update(x0=x0, goal_enc=torch.rand(B, C, H, W, generator=g), fires=(torch.rand(T, B, 1, H, W, generator=g) < 0.5).float(),
+             coef_final=torch.randn(B, C, H, W, generator=g))
+    m = dict(C=C, living_dim=liv, thr=0.1, rate=0.5)
+    errs = _enc_bf16_vs_emu(t, m, T)
+    assert errs["state"] < 3e-3, errs
+    assert max(v for k, v in errs.items() if k != "state") < 1e-2, errs
