@@ -506,23 +506,28 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             TB_STAMP(3);
             // ---- E1: h = relu(D1), g_a = D3 * [D1 > 0] -> bf16 operands; thread -> hidden units 32q .. 32q+31 ----
             if (32 * qtr < fc) {
-                uint32_t av[32], gv[32];
-                tmem_ld32(tmem_lane + TB_D1 + 32u * (uint32_t)qtr, av);
-                tmem_ld32(tmem_lane + TB_D3 + 32u * (uint32_t)qtr, gv);
-                tmem_ld_wait();
+                // two passes of 16 columns: D1 and D3 values of a pass are live together (32 registers), so the relu mask
+                // is consumed as it is produced instead of being parked in predicate bits
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    uint4 o, p;
-                    o.x = pack_bf16_relu(__uint_as_float(av[qq * 8 + 0]), __uint_as_float(av[qq * 8 + 1]));
-                    o.y = pack_bf16_relu(__uint_as_float(av[qq * 8 + 2]), __uint_as_float(av[qq * 8 + 3]));
-                    o.z = pack_bf16_relu(__uint_as_float(av[qq * 8 + 4]), __uint_as_float(av[qq * 8 + 5]));
-                    o.w = pack_bf16_relu(__uint_as_float(av[qq * 8 + 6]), __uint_as_float(av[qq * 8 + 7]));
-                    float ga[8];
+                for (int hp = 0; hp < 2; ++hp) {
+                    uint32_t av[16], gv[16];
+                    tmem_ld16(tmem_lane + TB_D1 + 32u * (uint32_t)qtr + 16u * (uint32_t)hp, av);
+                    tmem_ld16(tmem_lane + TB_D3 + 32u * (uint32_t)qtr + 16u * (uint32_t)hp, gv);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) ga[i] = __uint_as_float(av[qq * 8 + i]) > 0.0f ? __uint_as_float(gv[qq * 8 + i]) : 0.0f;
-                    p.x = pack_bf16(ga[0], ga[1]); p.y = pack_bf16(ga[2], ga[3]); p.z = pack_bf16(ga[4], ga[5]); p.w = pack_bf16(ga[6], ga[7]);
-                    *reinterpret_cast<uint4*>(sH + (uint32_t)(4 * qtr + qq) * 2048u + row_off) = o;
-                    *reinterpret_cast<uint4*>(sGa + (uint32_t)(4 * qtr + qq) * 2048u + row_off) = p;
+                    for (int qq = 0; qq < 2; ++qq) {
+                        uint4 o, p;
+                        o.x = pack_bf16_relu(__uint_as_float(av[qq * 8 + 0]), __uint_as_float(av[qq * 8 + 1]));
+                        o.y = pack_bf16_relu(__uint_as_float(av[qq * 8 + 2]), __uint_as_float(av[qq * 8 + 3]));
+                        o.z = pack_bf16_relu(__uint_as_float(av[qq * 8 + 4]), __uint_as_float(av[qq * 8 + 5]));
+                        o.w = pack_bf16_relu(__uint_as_float(av[qq * 8 + 6]), __uint_as_float(av[qq * 8 + 7]));
+                        float ga[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ga[i] = __uint_as_float(av[qq * 8 + i]) > 0.0f ? __uint_as_float(gv[qq * 8 + i]) : 0.0f;
+                        p.x = pack_bf16(ga[0], ga[1]); p.y = pack_bf16(ga[2], ga[3]); p.z = pack_bf16(ga[4], ga[5]); p.w = pack_bf16(ga[6], ga[7]);
+                        *reinterpret_cast<uint4*>(sH + (uint32_t)(4 * qtr + 2 * hp + qq) * 2048u + row_off) = o;
+                        *reinterpret_cast<uint4*>(sGa + (uint32_t)(4 * qtr + 2 * hp + qq) * 2048u + row_off) = p;
+                    }
                 }
             }
             fence_proxy_async();
