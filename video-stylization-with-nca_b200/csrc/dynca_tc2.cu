@@ -33,7 +33,7 @@ struct T2FwdArgs {
 };
 
 struct T2Smem {
-    uint32_t b1, b2w, u, x, xc, uni, a1, zc, dcb, total;
+    uint32_t b1, b2w, u, x, xc, cond, uni, a1, zc, dcb, total;
 };
 __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16Geom& bg) {
     T2Smem s;
@@ -45,6 +45,8 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
     s.x = o; o += (uint32_t)g.C * T2_XR * T2_XS * 4u;
     o = (o + 127u) & ~127u;
     s.xc = o; o += g.ns == 2 ? (uint32_t)g.C * T2_CR * T2_CS * 4u : 0u;
+    o = (o + 127u) & ~127u;
+    s.cond = o; o += g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u;
     o = (o + 127u) & ~127u;
     s.uni = o;
     s.a1 = o;
@@ -60,7 +62,8 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
 
 template <int NS>
 __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
-                                                                     const __grid_constant__ CUtensorMap tm_xc, const T2FwdArgs a) {
+                                                                     const __grid_constant__ CUtensorMap tm_xc,
+                                                                     const __grid_constant__ CUtensorMap tm_c, const T2FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     uint8_t* sU = smem + L.u;
     float* sX = reinterpret_cast<float*>(smem + L.x);
     float* sXc = reinterpret_cast<float*>(smem + L.xc);
+    float* sCond = reinterpret_cast<float*>(smem + L.cond);
     uint8_t* sA1 = smem + L.a1;
     uint8_t* sZc = smem + L.zc;
     uint8_t* sDcB = smem + L.dcb;
@@ -86,7 +90,8 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
     const size_t plane = (size_t)H * W;
-    const uint32_t stage_bytes = (uint32_t)C * T2_XR * T2_XS * 4u + (NS == 2 ? (uint32_t)C * T2_CR * T2_CS * 4u : 0u);
+    const uint32_t stage_bytes = (uint32_t)C * T2_XR * T2_XS * 4u + (NS == 2 ? (uint32_t)C * T2_CR * T2_CS * 4u : 0u) +
+                                 (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
     const uint32_t tmem_cols = NS == 2 ? 256u : 128u;
     const int n_tiles = a.tl.n_tiles;
 
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
         const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, k2steps = fc / 16;
         const CUtensorMap* const ptm_x = &tm_x;
         const CUtensorMap* const ptm_xc = &tm_xc;
+        const CUtensorMap* const ptm_c = &tm_c;
         uint32_t phA = 0, phB = 0, phC = 0;
         const bool leader = elect_one();
 #define T2_ISSUE_TMA(tile_)                                                                                              \
@@ -139,6 +145,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
         mbar_expect_tx(barT, stage_bytes);                                                                               \
         tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
         if (NS == 2) tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                 \
+        if (g.cond_kind == NCA_COND_TENSOR) tma_load_5d(sCond, ptm_c, barT, tx_, ty_, 0, tb_, 0);                        \
     } while (0)
         if (leader && (int)blockIdx.x < n_tiles) T2_ISSUE_TMA(blockIdx.x);
 #define T2_MSTAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && leader && miter < 8) a.tdbg[128 + miter * 8 + (k_)] = clock64(); } while (0)
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
                     const uint32_t ry = sCpe[py], cx = sCpe[T2_TH + px];
                     cv = make_uint4((ry & 0xffffu) | (cx << 16), 0x3F803F80u, (ry >> 16) | (cx & 0xffff0000u), 0u);
                 } else {
-                    cv = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
+                    cv = g.cond_kind == NCA_COND_TENSOR ? t2_cond_chunk_smem(g, sCond, r, inimg) : dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
                 }
                 *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = cv;
             } else {
@@ -451,12 +458,17 @@ int dynca_tc2_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* w
 }
 
 // tensor maps of one rollout: states [slots][B][C][H][W] and (two scales) coarse states [cslots][B][C][H/2][W/2]
-int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, const float* coarse, int cslots, size_t cslot_floats, DyncaTc2Maps* m) {
+int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, const float* coarse, int cslots, size_t cslot_floats,
+                        const float* cond, DyncaTc2Maps* m) {
     static_assert(sizeof(CUtensorMap) == sizeof(m->x), "tensor map size");
     int rc = t2_make_map((CUtensorMap*)m->x, states, slots, (size_t)g.B * g.C * g.H * g.W, g.B, g.C, g.H, g.W, T2_XR, T2_XS);
     if (rc) return rc;
     if (g.ns == 2) rc = t2_make_map((CUtensorMap*)m->xc, coarse, cslots, cslot_floats, g.B, g.C, g.H / 2, g.W / 2, T2_CR, T2_CS);
     else memcpy(m->xc, m->x, sizeof(m->x));
+    if (rc) return rc;
+    if (g.cond_kind == NCA_COND_TENSOR)
+        rc = t2_make_map((CUtensorMap*)m->cond, cond, 1, (size_t)g.B * g.cc * g.H * g.W, g.B, g.cc, g.H, g.W, T2_TH, T2_TW);
+    else memcpy(m->cond, m->x, sizeof(m->x));
     return rc;
 }
 
@@ -487,12 +499,13 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
     const CUtensorMap* tx = (const CUtensorMap*)m->x;
     const CUtensorMap* txc = (const CUtensorMap*)m->xc;
+    const CUtensorMap* tcn = (const CUtensorMap*)m->cond;
     if (g.ns == 2) {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_fwd_tc2_kernel<2><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, a);
+        dynca_fwd_tc2_kernel<2><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, *tcn, a);
     } else {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_fwd_tc2_kernel<1><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, a);
+        dynca_fwd_tc2_kernel<1><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, *tcn, a);
     }
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps (cycles since the tile's first stamp)

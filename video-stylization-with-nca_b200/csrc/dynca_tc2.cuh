@@ -264,6 +264,25 @@ __device__ __forceinline__ void t2_coarse_to_zc(const DyncaGeom& g, const float*
         }
     }
 }
+// cond chunk of A1 (see dynca_cond_chunk) from the TMA-staged cond tile sCond [cc][8][16] (NCA_COND_TENSOR)
+__device__ __forceinline__ uint4 t2_cond_chunk_smem(const DyncaGeom& g, const float* __restrict__ sCond, int r, bool inimg) {
+    float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (inimg) {
+        const bool split = dynca_cond_split(g.cc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int src = i < g.cc ? i : ((split && i >= g.cc + 2 && i < 2 * g.cc + 2) ? i - g.cc - 2 : -1);
+            if (src >= 0) {
+                const float raw = sCond[src * (T2_TH * T2_TW) + r];
+                const float hi = __bfloat162float(__float2bfloat16_rn(raw));
+                cv[i] = i < g.cc ? hi : raw - hi;
+            } else if (i == g.cc || i == g.cc + 1) cv[i] = 1.0f;
+        }
+    }
+    uint4 v;
+    v.x = pack_bf16(cv[0], cv[1]); v.y = pack_bf16(cv[2], cv[3]); v.z = pack_bf16(cv[4], cv[5]); v.w = pack_bf16(cv[6], cv[7]);
+    return v;
+}
 // fire decisions of one 8x16 tile by ONE warp: 32 lanes = 32 quads of 4 consecutive pixels -> sFire[128]
 __device__ __forceinline__ void t2_fire_tile(const FireMask& fm, int b, int y0, int x0, int H, int W, int lane, float* __restrict__ sFire, int enc = 0) {
     const int fy = y0 + (lane >> 2), fx = x0 + 4 * (lane & 3);

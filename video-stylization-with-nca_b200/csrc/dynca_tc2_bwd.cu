@@ -57,7 +57,7 @@ struct T2BwdArgs {
 };
 
 struct TBSmem {
-    uint32_t b1, b2d, u, x, xc, gn, gcn, zc, gau, a1, gy, h, ga, px, ctr, cpx, cctr, total;
+    uint32_t b1, b2d, u, x, xc, gn, gcn, cond, zc, gau, a1, gy, h, ga, px, ctr, cpx, cctr, total;
 };
 // A1 / Zc / Gy are double buffered over tiles (the next tile's operands are produced while the gradient MMAs of the
 // current tile run); DcB shares its storage with GaU (DcB is dead once D1 is complete, GaU is written after that); the
@@ -77,6 +77,8 @@ __host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16G
     s.gn = o; o += C * T2_TH * T2_TW * 4u;
     o = (o + 127u) & ~127u;
     s.gcn = o; o += g.ns == 2 ? C * 4u * 8u * 4u : 0u;
+    o = (o + 127u) & ~127u;
+    s.cond = o; o += g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u;
     o = (o + 127u) & ~127u;
     s.zc = o; o += g.ns == 2 ? 2u * 8192u : 0u;          // 2 buffers; M = 128 reads of a 64-row chunk alias what follows
     s.gau = o; o += g.ns == 2 ? 16u * 1024u : 0u;        // GaU | DcB, 16 chunks whatever fc is
@@ -132,7 +134,8 @@ template <int NS>
 __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                         const __grid_constant__ CUtensorMap tm_xc,
                                                                         const __grid_constant__ CUtensorMap tm_g,
-                                                                        const __grid_constant__ CUtensorMap tm_gc, const T2BwdArgs a) {
+                                                                        const __grid_constant__ CUtensorMap tm_gc,
+                                                                        const __grid_constant__ CUtensorMap tm_c, const T2BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     float* sXc = reinterpret_cast<float*>(smem + L.xc);
     float* sGn = reinterpret_cast<float*>(smem + L.gn);
     float* sGcn = reinterpret_cast<float*>(smem + L.gcn);
+    float* sCond = reinterpret_cast<float*>(smem + L.cond);
     uint8_t* sZc2 = smem + L.zc;          // 2 x 8192
     uint8_t* sGaU = smem + L.gau;         // GaU, and DcB before it
     uint8_t* sDcB = sGaU;
@@ -178,7 +182,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     const int n_tiles = a.tl.n_tiles;
     const int N6 = 16 * ((bg.npairs + 1) / 2);                 // perception columns of g_z, padded to the MMA granularity
     const uint32_t stage_bytes = (uint32_t)C * (T2_XR * T2_XS + T2_TH * T2_TW) * 4u +
-                                 (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u);
+                                 (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u) +
+                                 (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
 
     // ---- one-time setup ----
     for (uint32_t i = tid; i < bg.b1_bytes / 16; i += TB_NTHREADS)
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const CUtensorMap* const ptm_xc = &tm_xc;
         const CUtensorMap* const ptm_g = &tm_g;
         const CUtensorMap* const ptm_gc = &tm_gc;
+        const CUtensorMap* const ptm_c = &tm_c;
         uint32_t phA = 0, phB = 0, phC = 0, phD = 0, phG = 0, phE = 0;
         const bool leader = elect_one();
         bool first = true;
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         mbar_expect_tx(barT, stage_bytes);                                                                               \
         tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
         tma_load_5d(sGn, ptm_g, barT, tx_, ty_, 0, tb_, 0);                                                              \
+        if (g.cond_kind == NCA_COND_TENSOR) tma_load_5d(sCond, ptm_c, barT, tx_, ty_, 0, tb_, 0);                        \
         if (NS == 2) {                                                                                                   \
             tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                          \
             tma_load_5d(sGcn, ptm_gc, barT, tx_ >> 1, ty_ >> 1, 0, tb_, 0);                                              \
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     cv = make_uint4((ry & 0xffffu) | (cx << 16), 0x3F803F80u, (ry >> 16) | (cx & 0xffff0000u), 0u);
                     if (!inimg) cv = make_uint4(0, 0, 0, 0);      // rows of A1 are summed over cells by the weight-gradient MMA
                 } else {
-                    cv = dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
+                    cv = g.cond_kind == NCA_COND_TENSOR ? t2_cond_chunk_smem(g, sCond, r, inimg) : dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
                 }
                 *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = cv;
             } else if (qtr == 1) {
@@ -887,12 +894,13 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     const CUtensorMap* txc = (const CUtensorMap*)xm->xc;
     const CUtensorMap* tg = (const CUtensorMap*)gm->x;
     const CUtensorMap* tgc = (const CUtensorMap*)gm->xc;
+    const CUtensorMap* tcn = (const CUtensorMap*)xm->cond;
     if (g.ns == 2) {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_bwd_tc2_kernel<2><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, a);
+        dynca_bwd_tc2_kernel<2><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, *tcn, a);
     } else {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_bwd_tc2_kernel<1><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, a);
+        dynca_bwd_tc2_kernel<1><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, *tcn, a);
     }
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps

@@ -139,7 +139,8 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
     const size_t cstride = chist ? (size_t)g.B * g.C * (g.H / 2) * (g.W / 2) : nc;
     DyncaTc2Maps maps;
     if (variant == 2) {
-        rc = dynca_tc2_make_maps(g, states, keep_history ? T + 1 : 2, cbase, chist ? T + 1 : 2, cstride, &maps);
+        NCA_CHECK_ARG(NCA_ALIGNED16(cond), "cond must be 16-byte aligned");
+        rc = dynca_tc2_make_maps(g, states, keep_history ? T + 1 : 2, cbase, chist ? T + 1 : 2, cstride, cond, &maps);
         if (rc) return rc;
     }
     for (int t = 0; t < T; ++t) {
@@ -219,7 +220,8 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         if (g.ns == 2) NCA_CUDA_OK(cudaMemsetAsync(G[0], 0, 2 * nc * sizeof(float), s));
         const bool chist = coarse_hist != nullptr && g.ns == 2;
         DyncaTc2Maps xm, gm_final, gm[2];
-        rc = dynca_tc2_make_maps(g, states, T + 1, chist ? coarse_hist : wsXc, chist ? T + 1 : 1, ncx, &xm);
+        NCA_CHECK_ARG(NCA_ALIGNED16(cond) && NCA_ALIGNED16(g_final), "cond / g_final must be 16-byte aligned");
+        rc = dynca_tc2_make_maps(g, states, T + 1, chist ? coarse_hist : wsXc, chist ? T + 1 : 1, ncx, cond, &xm);
         if (rc) return rc;
         for (int p = 0; p < 2; ++p) { rc = dynca_tc2_make_gmaps(g, F[p], G[p], &gm[p]); if (rc) return rc; }
         if (g_final) { rc = dynca_tc2_make_gmaps(g, g_final, G[1], &gm_final); if (rc) return rc; }

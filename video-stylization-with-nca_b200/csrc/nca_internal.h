@@ -30,11 +30,12 @@ int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* xc, cons
                              const FireMask& fm, cudaStream_t s);
 
 // dynca_tc2.cu (tcgen05 path, 8x16 tiles + TMA; shapes with W % 4 == 0, fc % 32 == 0)
-struct DyncaTc2Maps { alignas(64) unsigned char x[128]; alignas(64) unsigned char xc[128]; };   // two CUtensorMap
+struct DyncaTc2Maps { alignas(64) unsigned char x[128]; alignas(64) unsigned char xc[128]; alignas(64) unsigned char cond[128]; };   // CUtensorMaps
 bool dynca_tc2_supported(const DyncaGeom& g);
 size_t dynca_tc2_weight_bytes(const DyncaGeom& g);
 int dynca_tc2_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s);
-int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, const float* coarse, int cslots, size_t cslot_floats, DyncaTc2Maps* m);
+int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, const float* coarse, int cslots, size_t cslot_floats,
+                        const float* cond, DyncaTc2Maps* m);
 int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Maps* m, int slot_in, const float* x_in, float* x_out,
                            int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s);
 int dynca_bf16_coarsen(const DyncaGeom& g, const float* x, float* xc, cudaStream_t s);
