@@ -148,7 +148,11 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
         if (g.cond_kind == NCA_COND_TENSOR) tma_load_5d(sCond, ptm_c, barT, tx_, ty_, 0, tb_, 0);                        \
     } while (0)
         if (leader && (int)blockIdx.x < n_tiles) T2_ISSUE_TMA(blockIdx.x);
+#ifdef NCA_T2_TIMING
 #define T2_MSTAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && leader && miter < 8) a.tdbg[128 + miter * 8 + (k_)] = clock64(); } while (0)
+#else
+#define T2_MSTAMP(k_) do { } while (0)
+#endif
         int miter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++miter) {
             T2_MSTAMP(0);
@@ -218,7 +222,11 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     } while (0)
         if ((int)blockIdx.x < n_tiles) T2_CPE_TABLE(blockIdx.x, 0);
         bar_sync_n(1, 256);
+#ifdef NCA_T2_TIMING
 #define T2_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
+#else
+#define T2_STAMP(k_) do { } while (0)
+#endif
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
             int b, y0, x0;
@@ -365,10 +373,9 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
                     const bool cst = inimg && (lane & 17) == 0;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float a01 = __shfl_xor_sync(0xffffffffu, xn[i], 1);
-                        const float a10 = __shfl_xor_sync(0xffffffffu, xn[i], 16);
-                        const float a11 = __shfl_xor_sync(0xffffffffu, xn[i], 17);
-                        if (cst && i < nch) *co = 0.25f * (((xn[i] + a01) + a10) + a11);
+                        const float h2 = xn[i] + __shfl_xor_sync(0xffffffffu, xn[i], 1);          // row pair sums
+                        const float s4 = h2 + __shfl_xor_sync(0xffffffffu, h2, 16);
+                        if (cst && i < nch) *co = 0.25f * s4;
                         co += cpl;
                     }
                 }

@@ -66,6 +66,13 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
     return d;
 }
 
+// 0xffff in each half whose bf16 value is non-zero (relu mask of a packed hidden pair: h != 0 <=> pre-activation > 0)
+__device__ __forceinline__ uint32_t bf16x2_nz_mask(uint32_t h) {
+    uint32_t m;
+    asm("set.ne.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(0u));
+    return m;
+}
+
 // perception of 4 vertically adjacent cells (rows r0 .. r0+3 of the tile) of one channel; col = stage column of the
 // left neighbour.  Separable: s = [1 2 1]^T, d = [-1 0 1]^T over rows.
 __device__ __forceinline__ void t2_percept4(const float* __restrict__ ch, int r0, int col, float id[4], float sx[4], float sy[4], float lp[4]) {

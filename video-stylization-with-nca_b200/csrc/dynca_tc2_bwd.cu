@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         }
         // CPE rows / columns (warp 15) and fire decisions (warp 14) of a tile, double buffered over tiles
         auto tables = [&](int tile_, int buf_) {
+            if (warp < 14) return;
             int tb_, ty_, tx_;
             t2_tile_decode(a.tl, tile_, tb_, ty_, tx_);
             if (g.cond_kind == NCA_COND_CPE && warp == 15 && lane < T2_TH + T2_TW) {
@@ -376,9 +377,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         // ---- P1 of a tile: perception operands A1 / Zc (-> barrier A), g = dL/dx_{t+1} and Gy (-> barrier G).
         //      Runs for tile i+1 while the gradient MMAs of tile i are in flight.  itn = iteration index of that tile. ----
         // p1a: stage wait, border patch, fine perception -> A1, cond chunk.   p1b: coarse perception -> Zc (-> A), Gy (-> G).
-        auto p1a = [&](int tile_, int itn) {
-            int b, y0, x0;
-            t2_tile_decode(a.tl, tile_, b, y0, x0);
+        auto p1a = [&](int b, int y0, int x0, int itn) {
             const int gy = y0 + py, gx = x0 + px;
             const bool inimg = gy < H && gx < W;
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
@@ -407,9 +406,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
             }
         };
-        auto p1b = [&](int tile_, int itn, float (&gn)[4]) {
-            int b, y0, x0;
-            t2_tile_decode(a.tl, tile_, b, y0, x0);
+        auto p1b = [&](int tile_, int b, int y0, int x0, int itn, float (&gn)[4]) {
             const int gy = y0 + py, gx = x0 + px;
             const bool inimg = gy < H && gx < W;
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
@@ -471,12 +468,20 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         float gn[4] = {0.f, 0.f, 0.f, 0.f}, gn_next[4] = {0.f, 0.f, 0.f, 0.f};
         if ((int)blockIdx.x < n_tiles) tables(blockIdx.x, 0);
         bar_sync_n(1, TB_NCOMP);
-        if ((int)blockIdx.x < n_tiles) { p1a(blockIdx.x, 0); p1b(blockIdx.x, 0, gn); }
+        int nb = 0, ny0 = 0, nx0 = 0;      // coordinates of the tile whose operands are produced ahead
+        if ((int)blockIdx.x < n_tiles) {
+            t2_tile_decode(a.tl, blockIdx.x, nb, ny0, nx0);
+            p1a(nb, ny0, nx0, 0);
+            p1b(blockIdx.x, nb, ny0, nx0, 0, gn);
+        }
+#ifdef NCA_T2_TIMING
 #define TB_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
+#else
+#define TB_STAMP(k_) do { } while (0)
+#endif
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
-            int b, y0, x0;
-            t2_tile_decode(a.tl, tile, b, y0, x0);
+            const int b = nb, y0 = ny0, x0 = nx0;
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
                                 (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
             TB_STAMP(0);
@@ -506,7 +511,10 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             TB_STAMP(2);
             const int next = tile + (int)gridDim.x;
-            if (next < n_tiles) p1a(next, iter + 1);          // software pipeline, part 1: in the shadow of D1 / D3
+            if (next < n_tiles) {                              // software pipeline, part 1: in the shadow of D1 / D3
+                t2_tile_decode(a.tl, next, nb, ny0, nx0);
+                p1a(nb, ny0, nx0, iter + 1);
+            }
             mbar_wait(barM2, phM2);
             phM2 ^= 1u;
             tc_fence_after();
@@ -528,10 +536,10 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         o.y = pack_bf16_relu(__uint_as_float(av[qq * 8 + 2]), __uint_as_float(av[qq * 8 + 3]));
                         o.z = pack_bf16_relu(__uint_as_float(av[qq * 8 + 4]), __uint_as_float(av[qq * 8 + 5]));
                         o.w = pack_bf16_relu(__uint_as_float(av[qq * 8 + 6]), __uint_as_float(av[qq * 8 + 7]));
-                        float ga[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) ga[i] = __uint_as_float(av[qq * 8 + i]) > 0.0f ? __uint_as_float(gv[qq * 8 + i]) : 0.0f;
-                        p.x = pack_bf16(ga[0], ga[1]); p.y = pack_bf16(ga[2], ga[3]); p.z = pack_bf16(ga[4], ga[5]); p.w = pack_bf16(ga[6], ga[7]);
+                        p.x = pack_bf16(__uint_as_float(gv[qq * 8 + 0]), __uint_as_float(gv[qq * 8 + 1])) & bf16x2_nz_mask(o.x);
+                        p.y = pack_bf16(__uint_as_float(gv[qq * 8 + 2]), __uint_as_float(gv[qq * 8 + 3])) & bf16x2_nz_mask(o.y);
+                        p.z = pack_bf16(__uint_as_float(gv[qq * 8 + 4]), __uint_as_float(gv[qq * 8 + 5])) & bf16x2_nz_mask(o.z);
+                        p.w = pack_bf16(__uint_as_float(gv[qq * 8 + 6]), __uint_as_float(gv[qq * 8 + 7])) & bf16x2_nz_mask(o.w);
                         *reinterpret_cast<uint4*>(sH + (uint32_t)(4 * qtr + 2 * hp + qq) * 2048u + row_off) = o;
                         *reinterpret_cast<uint4*>(sGa + (uint32_t)(4 * qtr + 2 * hp + qq) * 2048u + row_off) = p;
                     }
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             mbar_arrive(barC);
             TB_STAMP(4);
             // ---- software pipeline, part 2: rest of the NEXT tile's operands while the gradient MMAs of this one run ----
-            if (next < n_tiles) p1b(next, iter + 1, gn_next);
+            if (next < n_tiles) p1b(next, nb, ny0, nx0, iter + 1, gn_next);
             TB_STAMP(5);
             mbar_wait(barM3, phM3);                            // D6, GaU, D4, D5 (fine) complete; H | Ga are free
             phM3 ^= 1u;
