@@ -52,8 +52,7 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
     s.a1 = o;
     s.zc = s.a1 + bg.a1_bytes;
     s.dcb = s.zc + (g.ns == 2 ? 8192u : 0u);
-    uint32_t first = bg.a1_bytes + (g.ns == 2 ? 8192u + (uint32_t)(g.fc / 8) * 1024u : 0u);
-    o += first > bg.a2_bytes ? first : bg.a2_bytes;
+    o += bg.a1_bytes + (g.ns == 2 ? 8192u + (uint32_t)(g.fc / 8) * 1024u : 0u);       // the hidden layer (A2) lives in tensor memory
     s.total = o;
     return s;
 }
@@ -86,13 +85,12 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     uint8_t* sA1 = smem + L.a1;
     uint8_t* sZc = smem + L.zc;
     uint8_t* sDcB = smem + L.dcb;
-    uint8_t* sA2 = smem + L.uni;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
     const size_t plane = (size_t)H * W;
     const uint32_t stage_bytes = (uint32_t)C * T2_XR * T2_XS * 4u + (NS == 2 ? (uint32_t)C * T2_CR * T2_CS * 4u : 0u) +
                                  (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
-    const uint32_t tmem_cols = NS == 2 ? 256u : 128u;
+    const uint32_t tmem_cols = 256u;
     const int n_tiles = a.tl.n_tiles;
 
     // ---- one-time setup ----
@@ -118,7 +116,9 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = 0u;
+    // columns: Dc 0..127 (two scales), D1 128..255 / 0..127; D2 and the bf16 hidden layer A2 (fc / 2 columns) reuse Dc's
+    // columns (dead once DcB is written) or, with one scale, the free upper half
+    const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = NS == 2 ? 0u : 192u, TM_A2 = NS == 2 ? 64u : 128u;
 
     if (warp == 8) {
         // =========================== MMA / TMA warp ===========================
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
         const uint64_t dA1 = umma_desc(smem_u32(sA1), 2048u, 128u), dB1 = umma_desc(smem_u32(sB1), lbo_b1, 128u);
         const uint64_t dZc = umma_desc(smem_u32(sZc), 1024u, 128u), dU = umma_desc(smem_u32(sU), 2048u, 128u);
         const uint64_t dDcB = umma_desc(smem_u32(sDcB), 128u, 1024u);
-        const uint64_t dA2 = umma_desc(smem_u32(sA2), 2048u, 128u), dB2 = umma_desc(smem_u32(sB2w), 256u, 128u);
+        const uint64_t dB2 = umma_desc(smem_u32(sB2w), 256u, 128u);
         const uint64_t sB1k = (uint64_t)((2u * lbo_b1) >> 4);
         const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, k2steps = fc / 16;
         const CUtensorMap* const ptm_x = &tm_x;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
             if (leader) {
 #pragma unroll 8
                 for (int ks = 0; ks < k2steps; ++ks)
-                    umma_ss(tmem_base + TM_D2, dA2 + (uint64_t)(ks * (4096 >> 4)), dB2 + (uint64_t)(ks * (512 >> 4)), idesc2, ks > 0);
+                    umma_ts(tmem_base + TM_D2, tmem_base + TM_A2 + 8u * (uint32_t)ks, dB2 + (uint64_t)(ks * (512 >> 4)), idesc2, ks > 0);
                 umma_commit(barM);
             }
             T2_MSTAMP(6);
@@ -320,28 +320,22 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
             phM ^= 1u;
             tc_fence_after();
             T2_STAMP(9);
-            // ---- E1: relu(D1) -> bf16 -> A2 ----
+            // ---- E1: relu(D1) -> bf16 -> A2 in tensor memory (the A operand of GEMM 2) ----
 #pragma unroll 1
             for (int blk = 0; blk < 2; ++blk) {
                 const int j0 = 64 * half + 32 * blk;
                 if (j0 < fc) {
-                    uint32_t v[32];
+                    uint32_t v[32], o[16];
                     tmem_ld32(tmem_lane + TM_D1 + (uint32_t)j0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        uint4 o;
-                        o.x = pack_bf16_relu(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                        o.y = pack_bf16_relu(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                        o.z = pack_bf16_relu(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                        o.w = pack_bf16_relu(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                        *reinterpret_cast<uint4*>(sA2 + (uint32_t)(j0 / 8 + qq) * 2048u + row_off) = o;
-                    }
+                    for (int i = 0; i < 16; ++i) o[i] = pack_bf16_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                    tmem_st16(tmem_lane + TM_A2 + (uint32_t)(j0 >> 1), o);
                 }
             }
+            tmem_st_wait();
             T2_STAMP(10);
             if (tile + (int)gridDim.x < n_tiles) T2_CPE_TABLE(tile + gridDim.x, (iter + 1) & 1);   // published by the arrive below
-            fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barC);                                 // ---- C: A2 complete ----
             T2_STAMP(12);
@@ -498,7 +492,7 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     a.tdbg = timing ? tdbg : nullptr;
     a.tl = t2_make_tiles(g.B, g.H, g.W);
     const size_t smem = t2_smem(g, a.bg).total;
-    const uint32_t tcols = g.ns == 2 ? 256u : 128u;
+    const uint32_t tcols = 256u;
     int occ = (int)((227 * 1024) / (smem + 1024));
     if (occ > (int)(512u / tcols)) occ = (int)(512u / tcols);
     if (occ < 1) occ = 1;

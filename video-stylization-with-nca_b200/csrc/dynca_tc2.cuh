@@ -59,6 +59,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // two floats -> bf16x2 with relu fused (lo in the low half)
 __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
     uint32_t d;
@@ -206,12 +214,22 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t d
 }
 
 
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (M = 128 rows = lanes, two bf16 K elements per 32-bit column) comes from
+// tensor memory, so it costs no shared-memory bandwidth
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+
 // ---- perception phases shared by the forward and the BPTT kernel (NW = number of compute warps, 8 or 16) ----
-// fine perception -> A1: item = (channel pair, vertical block of 4 rows); lane = (column px, channel of the pair).
-// Channel planes are T2_XR * T2_XS = 240 floats apart = 16 banks, so the two half-warps never collide.
+// fine perception -> A1: item = (channel pair, vertical block of 4 rows); lane = (column px, channel of the pair), channel
+// in the low bit: channel planes are T2_XR * T2_XS = 240 floats apart = 16 banks, so the loads of a warp cover all 32 banks,
+// and the 8-byte stores of a half warp (8 columns x 2 channels) are 128 contiguous bytes.
 template <int NW>
 __device__ __forceinline__ void t2_fine_to_a1(const float* __restrict__ sX, uint8_t* __restrict__ sA1, int C, int npairs, int warp, int lane) {
-    const int hc = lane >> 4, pxx = lane & 15;
+    const int hc = lane & 1, pxx = lane >> 1;
     for (int item = warp; item < 2 * npairs; item += NW) {
         const int cp = item >> 1, vb = item & 1, c = 2 * cp + hc;
         float id[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f};

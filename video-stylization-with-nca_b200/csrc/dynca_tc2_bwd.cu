@@ -31,9 +31,12 @@
 #define TB_D3 256u
 #define TB_D4 384u
 #define TB_D5 400u
-// fp32 plane geometry (zero padded): fine cell (py,px) at [py+2][px+2] of [12][20]; coarse cell (qy,qx) at [qy+2][qx+2] of [10][14]
-#define TB_PR 12
-#define TB_PS 20
+// fp32 plane geometry (zero padded): fine cell (py,px) at [py+1][px+5] of [10][24] (ring position (oy,ox) reads rows
+// oy-1..oy+1, columns ox+3..ox+5: the 4 interior outputs ox = 1+4j.. of a thread start at the 16-byte aligned column
+// 4j+4; channel planes are 240 floats = 60 16-byte units apart, = 4 mod 8, so the float4 loads of a (4 column groups x
+// 2 channels) quarter warp are conflict free); coarse cell (qy,qx) at [qy+2][qx+2] of [10][14]
+#define TB_PR 10
+#define TB_PS 24
 #define TB_PP (TB_PR * TB_PS)
 #define TB_CPR 10
 #define TB_CPS 14
@@ -119,6 +122,34 @@ __device__ __forceinline__ void tb_stencil_t(const float* __restrict__ X, const 
 #pragma unroll
     for (int k = 0; k < NR; ++k)      // output oy0+k reads input rows (oy0+k) - a, a = 0,1,2 -> hx[k+2], hx[k+1], hx[k]
         out[k] = fmaf(2.0f, hx[k + 1], hx[k] + hx[k + 2]) + (hy[k] - hy[k + 2]);
+}
+
+// horizontal pass of the transposed stencils over one plane row: p = X plane at the thread's aligned column 4j+4, the Y and
+// L planes follow at +ps, +2ps.  hx / hy = the 4 interior outputs of the group, ex / ey = the ring column (0 for j = 0,
+// 17 for j = 3), which sees only cell column 0 (x[1]) / 15 (x[4]).
+__device__ __forceinline__ void tb_hrow(const float* __restrict__ p, int ps, int j, float hx[4], float hy[4], float& ex, float& ey) {
+    const float4 xa = *reinterpret_cast<const float4*>(p);
+    const float2 xb = *reinterpret_cast<const float2*>(p + 4);
+    const float4 ya = *reinterpret_cast<const float4*>(p + ps);
+    const float2 yb = *reinterpret_cast<const float2*>(p + ps + 4);
+    const float4 la = *reinterpret_cast<const float4*>(p + 2 * ps);
+    const float2 lb = *reinterpret_cast<const float2*>(p + 2 * ps + 4);
+    const float x[6] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y};
+    const float y[6] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y};
+    const float l[6] = {la.x, la.y, la.z, la.w, lb.x, lb.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hx[i] = (x[i] - x[i + 2]) + fmaf(2.0f, l[i + 1], l[i] + l[i + 2]);
+        hy[i] = fmaf(2.0f, y[i + 1], y[i] + y[i + 2]);
+    }
+    ex = j == 0 ? l[1] - x[1] : x[4] + l[4];
+    ey = j == 0 ? y[1] : y[4];
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {      // p 16-byte aligned
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {                        // p 8-byte aligned
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
 // image index that padded coordinate r of an axis of n cells folds back to under the TRANSPOSED padding (-1 = dropped)
@@ -348,17 +379,17 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const int py = r >> 4, px = r & 15;
         uint32_t phM1 = 0, phM2 = 0, phM3 = 0, phM4 = 0, phT = 0;
         float b2acc[4] = {0.f, 0.f, 0.f, 0.f};
-        // zero ring of the fine planes (rows 0,1,10,11 as float4; columns 0,1,18,19 of rows 2..9 as float2 pairs):
-        // 3*C planes x 28 items over 512 threads = at most 3 items per thread, offsets (in floats) fixed for the launch
-        int zoff[3];
+        // zero pads of the fine planes: rows 0 and 9 (columns 4..23 as float4) and columns 4 / 21 of rows 1..8 (a scalar
+        // pair): 3*C planes x 18 items over 512 threads = at most 2 items per thread, offsets (in floats) fixed for the launch
+        int zoff[2];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < 2; ++q) {
             const int i = tid + q * TB_NCOMP;
             int o = -1;
-            if (i < 3 * C * 28) {
-                const int k = i % 28, pl = i / 28;
-                if (k < 20) { const int row = k / 5 < 2 ? k / 5 : 8 + k / 5; o = pl * TB_PP + row * TB_PS + 4 * (k % 5); }
-                else o = (pl * TB_PP + (2 + (k - 20)) * TB_PS) | (1 << 30);      // flag: column pairs
+            if (i < 3 * C * 18) {
+                const int k = i % 18, pl = i / 18;
+                if (k < 10) o = pl * TB_PP + (k < 5 ? 0 : 9) * TB_PS + 4 + 4 * (k % 5);
+                else o = (pl * TB_PP + (1 + (k - 10)) * TB_PS + 4) | (1 << 30);      // flag: column pair
             }
             zoff[q] = o;
         }
@@ -579,13 +610,13 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             // ---- E2: D6 -> fp32 planes (overlay H | Ga) ----
             {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     const int o = zoff[q];
                     if (o >= 0) {
                         if (o & (1 << 30)) {
                             float* pr = sPX + (o & ~(1 << 30));
-                            *reinterpret_cast<float2*>(pr) = make_float2(0.f, 0.f);
-                            *reinterpret_cast<float2*>(pr + 18) = make_float2(0.f, 0.f);
+                            pr[0] = 0.0f;
+                            pr[17] = 0.0f;
                         } else {
                             *reinterpret_cast<float4*>(sPX + o) = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
@@ -599,7 +630,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     for (int i = 0; i < 4; ++i) {
                         const int c = 4 * qtr + i;
                         if (c < C) {
-                            const int o = (c * TB_PR + py + 2) * TB_PS + px + 2;
+                            const int o = (c * TB_PR + py + 1) * TB_PS + px + 5;
                             const float lp = __uint_as_float(v[4 * i + 3]);
                             sPX[o] = __uint_as_float(v[4 * i + 1]);
                             sPX[C * TB_PP + o] = __uint_as_float(v[4 * i + 2]);
@@ -613,54 +644,98 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             TB_STAMP(7);
             bar_sync_n(1, TB_NCOMP);
             TB_STAMP(8);
-            // ---- P5: transposed fine perception -> red.add into dL/dx_t.  warp = (channel pair, 5-row block), lane =
-            //      (channel of the pair, column): channel planes are 240 floats = 16 banks apart -> conflict-free reads ----
+            // ---- P5: transposed fine perception -> red.add into dL/dx_t.  A thread owns 4 consecutive columns (one
+            //      aligned float4 of the image row): warps 0..7 = channel pair x 4 row pairs x 4 column groups (tile rows
+            //      1..8 of the ring, plus the ring columns 0 / 17 from the same registers), warps 8..11 = the ring rows 0 / 9.
+            //      Interior positions are cells of this tile: unless the tile is ragged they need no folding and go out as
+            //      one vector reduction per row. ----
             {
-                const int cp = warp >> 1, vb = warp & 1, hc = lane >> 4;
-                const int c = 2 * cp + hc;
-                if (c < C) {
-                    const float* X = sPX + c * TB_PP;
-                    const float* Y = X + C * TB_PP;
-                    const float* Lp = Y + C * TB_PP;
-                    float* gob = a.g_out + ((size_t)b * C + c) * plane;
-                    const int ox = (lane & 15) + 1;      // ring column of the interior cell
-                    float out[5];
-                    tb_stencil_t<5, TB_PS>(X, Y, Lp, 5 * vb, ox, out);
+                const bool ragged = y0 + T2_TH > H || x0 + T2_TW > W;
+                if (warp < 12) {
+                    const int j = lane & 3;
+                    int c, row0, side = 0;
+                    if (warp < 8) { c = 2 * warp + ((lane >> 2) & 1); row0 = 2 * (lane >> 3); }
+                    else { const int t = tid - 256; c = ((t >> 2) & 1) + 2 * (t >> 4); side = (t >> 3) & 1; row0 = side ? 8 : 1; }
+                    if (c < C) {
+                        const float* X = sPX + c * TB_PP + row0 * TB_PS + 4 * j + 4;
+                        float* gob = a.g_out + ((size_t)b * C + c) * plane;
+                        const int gx0 = x0 + 4 * j;                     // image column of the group's first output
+                        const int gxe = j == 0 ? x0 - 1 : x0 + T2_TW;   // image column of the ring output (j = 0 / 3 only)
+                        if (warp < 8) {
+                            // output row kk = 0 / 1 reads plane rows kk .. kk+2: stream the 4 rows through the accumulators
+                            float o0[4], o1[4], e0, e1;
+                            {
+                                float hx[4], hy[4], ex, ey;
+                                tb_hrow(X, C * TB_PP, j, hx, hy, ex, ey);
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const int oy = 5 * vb + k;
-                        if (oy >= 1 && oy <= T2_TH) out[k] += sCtr[(c * T2_TH + oy - 1) * T2_TW + ox - 1];
-                    }
-                    if (!border) {       // every position is inside the image: coalesced rows, no folding
-                        float* p = gob + (size_t)(y0 - 1 + 5 * vb) * W + x0 + ox - 1;
+                                for (int i = 0; i < 4; ++i) o0[i] = hx[i] + hy[i];
+                                e0 = ex + ey;
+                                tb_hrow(X + TB_PS, C * TB_PP, j, hx, hy, ex, ey);
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) { atomicAdd(p, out[k]); p += W; }
-                    } else {
-                        const int tx = tb_fold(x0 + ox - 1, W, g.pad);
+                                for (int i = 0; i < 4; ++i) { o0[i] = fmaf(2.0f, hx[i], o0[i]); o1[i] = hx[i] + hy[i]; }
+                                e0 = fmaf(2.0f, ex, e0); e1 = ex + ey;
+                                tb_hrow(X + 2 * TB_PS, C * TB_PP, j, hx, hy, ex, ey);
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) {
-                            const int ty = tb_fold(y0 - 1 + 5 * vb + k, H, g.pad);
-                            if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[k]);
-                        }
-                    }
-                }
-                if (lane < 20) {     // the two ring columns: 2 channels x 5 rows x 2 sides
-                    const int hc2 = lane / 10, rem = lane % 10;
-                    const int c2 = 2 * cp + hc2;
-                    if (c2 < C) {
-                        const float* X = sPX + c2 * TB_PP;
-                        const float* Y = X + C * TB_PP;
-                        const float* Lp = Y + C * TB_PP;
-                        float* gob = a.g_out + ((size_t)b * C + c2) * plane;
-                        const int oy = 5 * vb + (rem >> 1), ox = (rem & 1) ? T2_TW + 1 : 0;
-                        float out[1];
-                        tb_stencil_t<1, TB_PS>(X, Y, Lp, oy, ox, out);
-                        const int yy = y0 - 1 + oy, xx = x0 - 1 + ox;
-                        if (!border) {
-                            atomicAdd(gob + (size_t)yy * W + xx, out[0]);
+                                for (int i = 0; i < 4; ++i) { o0[i] += hx[i] - hy[i]; o1[i] = fmaf(2.0f, hx[i], o1[i]); }
+                                e0 += ex - ey; e1 = fmaf(2.0f, ex, e1);
+                                tb_hrow(X + 3 * TB_PS, C * TB_PP, j, hx, hy, ex, ey);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) o1[i] += hx[i] - hy[i];
+                                e1 += ex - ey;
+                            }
+                            const float* ctr = sCtr + (c * T2_TH + row0) * T2_TW + 4 * j;
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) {
+                                const float4 cv = *reinterpret_cast<const float4*>(ctr + kk * T2_TW);
+                                float out[4];
+                                out[0] = (kk ? o1[0] : o0[0]) + cv.x; out[1] = (kk ? o1[1] : o0[1]) + cv.y;
+                                out[2] = (kk ? o1[2] : o0[2]) + cv.z; out[3] = (kk ? o1[3] : o0[3]) + cv.w;
+                                const float eo = kk ? e1 : e0;
+                                const int gy = y0 + row0 + kk;
+                                if (!ragged) {
+                                    red_add_v4(gob + (size_t)gy * W + gx0, out[0], out[1], out[2], out[3]);
+                                } else {
+                                    const int ty = tb_fold(gy, H, g.pad);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int tx = tb_fold(gx0 + i, W, g.pad);
+                                        if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[i]);
+                                    }
+                                }
+                                if (j == 0 || j == 3) {
+                                    if (!border) {
+                                        atomicAdd(gob + (size_t)gy * W + gxe, eo);
+                                    } else {
+                                        const int ty = tb_fold(gy, H, g.pad), tx = tb_fold(gxe, W, g.pad);
+                                        if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, eo);
+                                    }
+                                }
+                            }
                         } else {
-                            const int ty = tb_fold(yy, H, g.pad), tx = tb_fold(xx, W, g.pad);
-                            if (ty >= 0 && tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[0]);
+                            // ring row 0 sees only cell row 0 (taps a = 2), ring row 9 only cell row 7 (taps a = 0)
+                            float hx[4], hy[4], ex, ey, out[4];
+                            tb_hrow(X, C * TB_PP, j, hx, hy, ex, ey);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) out[i] = side ? hx[i] + hy[i] : hx[i] - hy[i];
+                            const float eo = side ? ex + ey : ex - ey;
+                            const int gy = side ? y0 + T2_TH : y0 - 1;
+                            if (!border) {
+                                red_add_v4(gob + (size_t)gy * W + gx0, out[0], out[1], out[2], out[3]);
+                                if (j == 0 || j == 3) atomicAdd(gob + (size_t)gy * W + gxe, eo);
+                            } else {
+                                const int ty = tb_fold(gy, H, g.pad);
+                                if (ty >= 0) {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int tx = tb_fold(gx0 + i, W, g.pad);
+                                        if (tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, out[i]);
+                                    }
+                                    if (j == 0 || j == 3) {
+                                        const int tx = tb_fold(gxe, W, g.pad);
+                                        if (tx >= 0) atomicAdd(gob + (size_t)ty * W + tx, eo);
+                                    }
+                                }
+                            }
                         }
                     }
                 }
