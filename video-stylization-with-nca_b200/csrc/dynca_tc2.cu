@@ -29,6 +29,7 @@ struct T2FwdArgs {
     FireMask fm;
     T2Tiles tl;
     int dbg;
+    int pdl;           // launch with the programmatic-serialization attribute (not the first step of a call)
     long long* tdbg;   // optional phase timestamps of CTA 0 (debug)
 };
 
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     const uint32_t tmem_cols = 256u;
     const int n_tiles = a.tl.n_tiles;
 
-    // ---- one-time setup ----
+    griddep_launch();
+    // ---- one-time setup (independent of the previous step's output: may overlap its tail) ----
     for (uint32_t i = tid; i < bg.b1_bytes / 16; i += T2_NTHREADS)
         reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
     for (uint32_t i = tid; i < bg.b2_bytes / 16; i += T2_NTHREADS)
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();          // the previous step's state (and coarse state) is complete and visible from here on
     // columns: Dc 0..127 (two scales), D1 128..255 / 0..127; D2 and the bf16 hidden layer A2 (fc / 2 columns) reuse Dc's
     // columns (dead once DcB is written) or, with one scale, the free upper half
     const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = NS == 2 ? 0u : 192u, TM_A2 = NS == 2 ? 64u : 128u;
@@ -474,8 +477,9 @@ int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, cons
 }
 
 int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Maps* m, int slot_in, const float* x_in, float* x_out,
-                           int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s) {
+                           int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s, int pdl) {
     T2FwdArgs a;
+    a.pdl = pdl;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
     a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.x_out = x_out; a.xc_out = xc_out;
@@ -503,10 +507,10 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     const CUtensorMap* tcn = (const CUtensorMap*)m->cond;
     if (g.ns == 2) {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_fwd_tc2_kernel<2><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, *tcn, a);
+        NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<2>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
     } else {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_fwd_tc2_kernel<1><<<grid, T2_NTHREADS, smem, s>>>(*tx, *txc, *tcn, a);
+        NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<1>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
     }
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps (cycles since the tile's first stamp)

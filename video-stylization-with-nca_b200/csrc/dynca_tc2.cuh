@@ -195,6 +195,24 @@ __device__ __forceinline__ void t2_patch_border(const DyncaGeom& g, const float*
     }
 }
 
+// ---- programmatic dependent launch: the step kernels of a rollout are launched back to back on one stream; a launch with
+// the programmatic-serialization attribute may become resident as soon as every CTA of its predecessor has executed
+// griddep_launch (first instruction of the kernel) or exited, runs its prologue (operand images -> shared memory, barrier
+// init, tensor-memory allocation) in the shadow of the predecessor's tail, and blocks in griddep_wait until the
+// predecessor grid has completed and its memory is visible.  Without the attribute both are no-ops. ----
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t t2_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- synchronisation helpers: compute threads -> MMA warp hand-offs are mbarriers, not CTA barriers ----
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

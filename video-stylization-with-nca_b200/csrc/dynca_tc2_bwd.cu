@@ -56,6 +56,7 @@ struct T2BwdArgs {
     float* gW1p; float* gW2p; float* gb2p;            // fp32 accumulators, padded fp32-path layout (red.add)
     FireMask fm;
     T2Tiles tl;
+    int pdl;           // launch with the programmatic-serialization attribute (not the first step of a call)
     long long* tdbg;
 };
 
@@ -171,6 +172,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
     const TBSmem L = tb_smem(g, bg);
+#ifdef NCA_T2_TIMING
+    if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) a.tdbg[128] = clock64();
+#endif
     // MMA-completion barriers (tcgen05.commit), one per batch of a tile, so that the MMA warp may run ahead into the next
     // tile's recompute batch without a barrier ever being two phases ahead of its waiters
     uint64_t* barM1 = reinterpret_cast<uint64_t*>(smem);          // Dc
@@ -216,7 +220,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                                  (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u) +
                                  (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
 
-    // ---- one-time setup ----
+    griddep_launch();
+    // ---- one-time setup (independent of the previous launch's output: may overlap its tail) ----
     for (uint32_t i = tid; i < bg.b1_bytes / 16; i += TB_NTHREADS)
         reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
     for (uint32_t i = tid; i < (uint32_t)(fc / 8) * 256u / 16; i += TB_NTHREADS)
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();          // dL/dx_{t+1} (and the weight-gradient accumulators) of the previous launch are complete from here on
 
     if (warp == 16) {
         // =========================== MMA / TMA warp ===========================
@@ -511,6 +517,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 #define TB_STAMP(k_) do { } while (0)
 #endif
         int iter = 0;
+#ifdef NCA_T2_TIMING
+        if (a.tdbg && blockIdx.x == 0 && tid == 0) a.tdbg[129] = clock64();
+#endif
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
             const int b = nb, y0 = ny0, x0 = nx0;
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
@@ -847,6 +856,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 4; ++i) gn[i] = gn_next[i];
         }
+#ifdef NCA_T2_TIMING
+        if (a.tdbg && blockIdx.x == 0 && tid == 0) { a.tdbg[130] = clock64(); a.tdbg[132] = iter; }
+#endif
         // ---- flush: D4 [fc x 16] -> gW2p[j][c];  D5 [fc x K1] -> gW1p[k][j] (k' -> reference k, perception columns x s0) ----
         {
             const int j = (warp & 3) * 32 + lane;
@@ -890,6 +902,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         tc_fence_before();
     }
     __syncthreads();
+#ifdef NCA_T2_TIMING
+    if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) a.tdbg[131] = clock64();
+#endif
     if (warp == 16) tmem_dealloc(tmem_base, 512u);
 }
 
@@ -953,8 +968,9 @@ int dynca_tc2_add_coarse(const DyncaGeom& g, const float* gc, float* gx, cudaStr
 int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const DyncaTc2Maps* xm, int slot_in, const float* x_in,
                             int cslot_in, const float* xc_in, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
                             int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out,
-                            const float* cond, const FireMask& fm, cudaStream_t s) {
+                            const float* cond, const FireMask& fm, cudaStream_t s, int pdl) {
     T2BwdArgs a;
+    a.pdl = pdl;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
     a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.slot_in = slot_in; a.cslot_in = cslot_in;
@@ -968,7 +984,7 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     a.tl = t2_make_tiles(g.B, g.H, g.W);
     static long long* tdbg = nullptr;
     const bool timing = getenv("NCA_T2_TDBG") != nullptr;
-    if (timing && !tdbg) cudaMalloc(&tdbg, 128 * sizeof(long long));
+    if (timing && !tdbg) cudaMalloc(&tdbg, 160 * sizeof(long long));
     a.tdbg = timing ? tdbg : nullptr;
     const size_t smem = tb_smem(g, a.bg).total;
     int grid = t2_num_sms();
@@ -980,15 +996,16 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     const CUtensorMap* tcn = (const CUtensorMap*)xm->cond;
     if (g.ns == 2) {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_bwd_tc2_kernel<2><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, *tcn, a);
+        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<2>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a));
     } else {
         NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dynca_bwd_tc2_kernel<1><<<grid, TB_NTHREADS, smem, s>>>(*tx, *txc, *tg, *tgc, *tcn, a);
+        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<1>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a));
     }
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps
-        long long h[128];
+        long long h[160];
         cudaMemcpy(h, tdbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "tc2 bwd CTA 0: setup %lld, tile loop %lld (%lld tiles), flush %lld cycles\n", h[129] - h[128], h[130] - h[129], h[132], h[131] - h[130]);
         for (int it = 0; it < 8; ++it) {
             fprintf(stderr, "tc2 bwd timing iter %d:", it);
             for (int k = 0; k < 16; ++k) fprintf(stderr, " %lld", h[it * 16 + k] - h[it * 16]);

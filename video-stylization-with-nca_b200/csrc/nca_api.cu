@@ -154,7 +154,7 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
             if (g.ns == 2 && t == 0) { rc = dynca_bf16_coarsen(g, xin, cbase + (size_t)ci * cstride, s); if (rc) return rc; }
             const bool need_next = g.ns == 2 && (t + 1 < T || chist);
             rc = dynca_tc2_forward_step(g, wsB, &maps, si, xin, xout, ci, g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr,
-                                        need_next ? cbase + (size_t)co * cstride : nullptr, cond, fm, s);
+                                        need_next ? cbase + (size_t)co * cstride : nullptr, cond, fm, s, t > 0);
         } else if (variant == 1) {
             float* xc = g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr;
             rc = dynca_bf16_forward_step(g, wsB, xc, xin, xout, cond, fm, s);
@@ -241,7 +241,8 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
             }
             rc = dynca_tc2_backward_step(g, wsB, wsG, &xm, t, states + (size_t)t * n, chist ? t : 0, xc_t,
                                          from_final ? &gm_final : &gm[p_in], from_final ? const_cast<float*>(g_final) : F[p_in], G[p_in],
-                                         from_final ? 0 : 1, 1, tap, tap_c, tap_scale, gout, G[p_out], cond, fm, s);
+                                         from_final ? 0 : 1, 1, tap, tap_c, tap_scale, gout, G[p_out], cond, fm, s,
+                                         t < T - 1 && (chist || g.ns != 2));      // no coarsen launch in between
             if (rc) return rc;
             p_in = p_out;
         }
