@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     const size_t plane = (size_t)H * W;
     const uint32_t stage_bytes = (uint32_t)C * T2_XR * T2_XS * 4u + (NS == 2 ? (uint32_t)C * T2_CR * T2_CS * 4u : 0u) +
                                  (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
-    const uint32_t tmem_cols = 256u;
+    const uint32_t tmem_cols = NS == 2 ? 256u : 128u;
     const int n_tiles = a.tl.n_tiles;
 
     griddep_launch();
@@ -119,10 +119,11 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     griddep_wait();          // the previous step's state (and coarse state) is complete and visible from here on
-    // columns: Dc 0..127 (two scales), D1 128..255 / 0..127; D2 and the bf16 hidden layer A2 (fc / 2 columns) reuse Dc's
-    // columns (dead once DcB is written) or, with one scale, the free upper half
-    const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = NS == 2 ? 0u : 192u, TM_A2 = NS == 2 ? 64u : 128u;
-
+    // columns, two scales: Dc 0..127, D1 128..255; D2 (0..15) and the bf16 hidden layer A2 (64..127, 8 columns per K step)
+    // reuse Dc's columns, dead once DcB is written.  One scale (128 columns, so that three CTAs fit an SM): A2 is written
+    // IN PLACE over D1 - a thread owns 64 columns of its lane, reads 32 of them and then stores the 16 packed columns over
+    // the part it has already read: K step ks sits at column 64*(ks/4) + 8*(ks%4); D2 goes to columns 32..47 (read by then).
+    const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = NS == 2 ? 0u : 32u;
     if (warp == 8) {
         // =========================== MMA / TMA warp ===========================
         const uint32_t idesc1 = umma_idesc_bf16(128, fc), idesc2 = umma_idesc_bf16(128, 16);
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
             if (leader) {
 #pragma unroll 8
                 for (int ks = 0; ks < k2steps; ++ks)
-                    umma_ts(tmem_base + TM_D2, tmem_base + TM_A2 + 8u * (uint32_t)ks, dB2 + (uint64_t)(ks * (512 >> 4)), idesc2, ks > 0);
+                    umma_ts(tmem_base + TM_D2, tmem_base + (NS == 2 ? 64u + 8u * (uint32_t)ks : 64u * (uint32_t)(ks >> 2) + 8u * (uint32_t)(ks & 3)),
+                            dB2 + (uint64_t)(ks * (512 >> 4)), idesc2, ks > 0);
                 umma_commit(barM);
             }
             T2_MSTAMP(6);
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) o[i] = pack_bf16_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                    tmem_st16(tmem_lane + TM_A2 + (uint32_t)(j0 >> 1), o);
+                    tmem_st16(tmem_lane + (NS == 2 ? 64u + (uint32_t)(j0 >> 1) : 64u * (uint32_t)half + 16u * (uint32_t)blk), o);
                 }
             }
             tmem_st_wait();
@@ -496,7 +498,7 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     a.tdbg = timing ? tdbg : nullptr;
     a.tl = t2_make_tiles(g.B, g.H, g.W);
     const size_t smem = t2_smem(g, a.bg).total;
-    const uint32_t tcols = 256u;
+    const uint32_t tcols = g.ns == 2 ? 256u : 128u;
     int occ = (int)((227 * 1024) / (smem + 1024));
     if (occ > (int)(512u / tcols)) occ = (int)(512u / tcols);
     if (occ < 1) occ = 1;

@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                                     }
                                 }
                                 if (j == 0 || j == 3) {
-                                    if (!border) {
+                                    if (!ragged && gxe >= 0 && gxe < W) {      // inside the image: no folding
                                         atomicAdd(gob + (size_t)gy * W + gxe, eo);
                                     } else {
                                         const int ty = tb_fold(gy, H, g.pad), tx = tb_fold(gxe, W, g.pad);
@@ -728,9 +728,12 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                             for (int i = 0; i < 4; ++i) out[i] = side ? hx[i] + hy[i] : hx[i] - hy[i];
                             const float eo = side ? ex + ey : ex - ey;
                             const int gy = side ? y0 + T2_TH : y0 - 1;
-                            if (!border) {
+                            if (!ragged && gy >= 0 && gy < H) {                // ring row inside the image: only the corners may fold
                                 red_add_v4(gob + (size_t)gy * W + gx0, out[0], out[1], out[2], out[3]);
-                                if (j == 0 || j == 3) atomicAdd(gob + (size_t)gy * W + gxe, eo);
+                                if (j == 0 || j == 3) {
+                                    const int tx = tb_fold(gxe, W, g.pad);
+                                    if (tx >= 0) atomicAdd(gob + (size_t)gy * W + tx, eo);
+                                }
                             } else {
                                 const int ty = tb_fold(gy, H, g.pad);
                                 if (ty >= 0) {
@@ -835,7 +838,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                             const int oy = 4 * vb + k;
                             if (oy >= 1 && oy <= T2_QH && ox >= 1 && ox <= T2_QW) out[k] += sCCtr[(c * T2_QH + oy - 1) * T2_QW + ox - 1];
                         }
-                        if (!border) {
+                        const int gxc = cx0 - 1 + ox, gyc = cy0 - 1 + 4 * vb;
+                        if (!border || (gxc >= 0 && gxc < Wc && gyc >= 0 && gyc + 4 <= Hc)) {
                             float* p = gcb + (size_t)(cy0 - 1 + 4 * vb) * Wc + cx0 - 1 + ox;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) { atomicAdd(p, out[k]); p += Wc; }
