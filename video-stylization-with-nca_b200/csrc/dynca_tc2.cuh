@@ -270,7 +270,29 @@ __device__ __forceinline__ void t2_coarse_to_zc(const DyncaGeom& g, const float*
                                                 int y0, int x0, bool border, int tid, int warp, int lane) {
     const int C = g.C;
     constexpr int NT = NW * 32;
-    if (lane < 2 * T2_QW) {
+    if (NW >= 16) {
+        // one channel per warp (16 warps, at most 16 channels): half the dependent chain of the pair version below
+        const int c = warp;
+        if (lane < 2 * T2_QW && c < C) {
+            const int hb = lane / T2_QW, qx = lane % T2_QW;
+            float id0[3], sx0[3], sy0[3], lp0[3];
+            t2_percept3c(sXc + c * T2_CR * T2_CS, 3 * hb, qx, id0, sx0, sy0, lp0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int q = (3 * hb + k) * T2_QW + qx;
+                uint2 v;
+                v.x = pack_bf16(id0[k], sx0[k]); v.y = pack_bf16(sy0[k], lp0[k]);
+                *reinterpret_cast<uint2*>(sZc + (uint32_t)(c >> 1) * 1024u + (uint32_t)q * 16u + (uint32_t)(c & 1) * 8u) = v;
+            }
+        }
+        if ((C & 1) && warp == C && lane < 2 * T2_QW) {       // odd channel count: the upper half of the last pair is zero
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int q = (3 * (lane / T2_QW) + k) * T2_QW + lane % T2_QW;
+                *reinterpret_cast<uint2*>(sZc + (uint32_t)(C >> 1) * 1024u + (uint32_t)q * 16u + 8u) = make_uint2(0u, 0u);
+            }
+        }
+    } else if (lane < 2 * T2_QW) {
         for (int cp = warp; cp < npairs; cp += NW) {
             const int hb = lane / T2_QW, qx = lane % T2_QW;
             float id0[3], sx0[3], sy0[3], lp0[3], id1[3] = {0.f, 0.f, 0.f}, sx1[3] = {0.f, 0.f, 0.f}, sy1[3] = {0.f, 0.f, 0.f}, lp1[3] = {0.f, 0.f, 0.f};

@@ -430,6 +430,8 @@ __global__ void enc_life_kernel(EncGeom g, const float* __restrict__ x, const fl
                                 uint8_t* __restrict__ life_out) {
     const int H = g.H, W = g.W, C = g.C;
     const size_t plane = (size_t)H * W, n = (size_t)g.B * plane;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // programmatic dependent launch (no-ops otherwise)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int xx = (int)(i % W), yy = (int)((i / W) % H);
         const size_t b = i / plane;
@@ -541,10 +543,20 @@ int nca_enc_forward(const NcaEncDesc* d, const NcaEncWeights* w, const float* go
         if (rc) return rc;
         for (int t = 0; t < T; ++t) {
             const int si = keep_history ? t : (t & 1), so = keep_history ? t + 1 : ((t + 1) & 1);
-            rc = enc_tc_forward_step(d, w, wsT, &maps, si, x1, enc_mask(d, g, masks, seed, t0, t), s);
+            // both kernels of a step launch programmatically: each starts under its predecessor's tail and waits
+            // (griddepcontrol.wait) before it touches the predecessor's output
+            rc = enc_tc_forward_step(d, w, wsT, &maps, si, x1, enc_mask(d, g, masks, seed, t0, t), s, t > 0);
             if (rc) return rc;
-            enc_life_kernel<<<lgrid, 256, 0, s>>>(g, states + (size_t)si * n, x1, states + (size_t)so * n,
-                                                  keep_history ? life_hist + (size_t)t * cells : nullptr);
+            {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)lgrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                NCA_CUDA_OK(cudaLaunchKernelEx(&cfg, enc_life_kernel, g, (const float*)(states + (size_t)si * n), (const float*)x1,
+                                               states + (size_t)so * n, keep_history ? life_hist + (size_t)t * cells : (uint8_t*)nullptr));
+            }
             NCA_LAUNCH_OK();
         }
         return NCA_OK;

@@ -53,8 +53,8 @@ __host__ __device__ static inline EncTcSmem etc_smem(const EncTcGeom& g) {
     s.gl = o; o += (uint32_t)g.C * T2_XR * T2_XS * 4u;
     s.pre = o; o += 192u * 4u;
     o = (o + 127u) & ~127u;
-    s.a1 = o; o += (uint32_t)(g.K1 / 8) * 2048u;      // A1, later A3 (first 16 KB)
-    s.a2 = o; o += 8u * 2048u;
+    s.a1 = o; o += (uint32_t)(g.K1 / 8) * 2048u;      // A1 (the hidden layers h1 / h2 live in tensor memory)
+    s.a2 = o;
     s.total = o;
     return s;
 }
@@ -83,13 +83,13 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
     float* sG = reinterpret_cast<float*>(smem + L.gl);
     float* sPre = reinterpret_cast<float*>(smem + L.pre);
     uint8_t* sA1 = smem + L.a1;
-    uint8_t* sA3 = smem + L.a1;
-    uint8_t* sA2 = smem + L.a2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = g.C, H = g.H, W = g.W;
     const size_t plane = (size_t)H * W;
     const int n_tiles = a.tl.n_tiles;
     const uint32_t stage_bytes = (uint32_t)(2 * C * T2_XR + ET2_LR) * T2_XS * 4u;
+
+    griddep_launch();
 
     for (uint32_t i = tid; i < (uint32_t)(g.K1 / 8) * 1024u / 16; i += ET2_NTHREADS)
         reinterpret_cast<uint4*>(sWa)[i] = __ldg(reinterpret_cast<const uint4*>(a.Wa) + i);
@@ -113,14 +113,17 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();          // the previous step's state is complete and visible from here on
+    // D1 0..63, D2 64..127, D3 0..31.  The bf16 hidden layers are the A operands of the next MMA straight from tensor memory,
+    // written IN PLACE: a thread packs the 32 columns of its lane it has just read into the first 16 of them, so K step ks
+    // (16 hidden units) of h1 sits at column 32*(ks/2) + 8*(ks%2), of h2 at 64 + the same.
     const uint32_t TM_D1 = 0u, TM_D2 = 64u, TM_D3 = 0u;
 
     if (warp == 8) {
         // =========================== MMA / TMA warp ===========================
         const uint32_t id64 = umma_idesc_bf16(128, 64), id32 = umma_idesc_bf16(128, 32);
         const uint64_t dA1 = umma_desc(smem_u32(sA1), 2048u, 128u), dWa = umma_desc(smem_u32(sWa), 1024u, 128u);
-        const uint64_t dA2 = umma_desc(smem_u32(sA2), 2048u, 128u), dWb = umma_desc(smem_u32(sWb), 1024u, 128u);
-        const uint64_t dA3 = umma_desc(smem_u32(sA3), 2048u, 128u), dWc = umma_desc(smem_u32(sWc), 512u, 128u);
+        const uint64_t dWb = umma_desc(smem_u32(sWb), 1024u, 128u), dWc = umma_desc(smem_u32(sWc), 512u, 128u);
         const int k1steps = g.K1 / 16;
         const CUtensorMap* const ptm_x = &tm_x;
         const CUtensorMap* const ptm_l = &tm_l;
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    umma_ss(tmem_base + TM_D2, dA2 + (uint64_t)(ks * (4096 >> 4)), dWb + (uint64_t)(ks * (2048 >> 4)), id64, ks > 0);
+                    umma_ts(tmem_base + TM_D2, tmem_base + TM_D1 + 32u * (uint32_t)(ks >> 1) + 8u * (uint32_t)(ks & 1),
+                            dWb + (uint64_t)(ks * (2048 >> 4)), id64, ks > 0);
                 umma_commit(barM);
             }
             mbar_wait(barC, phC);
@@ -163,7 +167,8 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    umma_ss(tmem_base + TM_D3, dA3 + (uint64_t)(ks * (4096 >> 4)), dWc + (uint64_t)(ks * (1024 >> 4)), id32, ks > 0);
+                    umma_ts(tmem_base + TM_D3, tmem_base + TM_D2 + 32u * (uint32_t)(ks >> 1) + 8u * (uint32_t)(ks & 1),
+                            dWc + (uint64_t)(ks * (1024 >> 4)), id32, ks > 0);
                 umma_commit(barM);
             }
         }
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
             bar_sync_n(1, 256);
             // ---- learned depthwise 3x3 -> A1: item = (channel pair, 4-row block); lane = (column, channel of the pair) ----
             {
-                const int hc = lane >> 4, pxx = lane & 15;
+                const int hc = lane & 1, pxx = lane >> 1;      // 8-byte stores of a half warp = 128 contiguous bytes
                 for (int item = warp; item < 2 * g.npairs; item += 8) {
                     const int cp = item >> 1, vb = item & 1, c = 2 * cp + hc;
                     float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -269,44 +274,33 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
             mbar_wait(barM, phM);
             phM ^= 1u;
             tc_fence_after();
-            // ---- E1: h1 = relu(D1) -> A2 (ba rides in the bias chunk) ----
+            // ---- E1: h1 = relu(D1) -> bf16, in place in tensor memory (ba rides in the bias chunk) ----
             {
-                uint32_t v[32];
+                uint32_t v[32], o[16];
                 tmem_ld32(tmem_lane + TM_D1 + 32u * (uint32_t)half, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    uint4 o;
-                    o.x = pack_bf16_relu(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                    o.y = pack_bf16_relu(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                    o.z = pack_bf16_relu(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                    o.w = pack_bf16_relu(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                    *reinterpret_cast<uint4*>(sA2 + (uint32_t)(4 * half + qq) * 2048u + row_off) = o;
-                }
+                for (int i = 0; i < 16; ++i) o[i] = pack_bf16_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                tmem_st16(tmem_lane + TM_D1 + 32u * (uint32_t)half, o);
+                tmem_st_wait();
             }
-            fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barB);
             mbar_wait(barM, phM);
             phM ^= 1u;
             tc_fence_after();
-            // ---- E2: h2 = relu(D2 + bb) -> A3 (over A1: MMA 1 is complete) ----
+            // ---- E2: h2 = relu(D2 + bb) -> bf16, in place in tensor memory ----
             {
-                uint32_t v[32];
+                uint32_t v[32], o[16];
                 tmem_ld32(tmem_lane + TM_D2 + 32u * (uint32_t)half, v);
                 tmem_ld_wait();
                 const float* bbp = sBb + 32 * half;
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    uint4 o;
-                    o.x = pack_bf16_relu(__uint_as_float(v[qq * 8 + 0]) + bbp[qq * 8 + 0], __uint_as_float(v[qq * 8 + 1]) + bbp[qq * 8 + 1]);
-                    o.y = pack_bf16_relu(__uint_as_float(v[qq * 8 + 2]) + bbp[qq * 8 + 2], __uint_as_float(v[qq * 8 + 3]) + bbp[qq * 8 + 3]);
-                    o.z = pack_bf16_relu(__uint_as_float(v[qq * 8 + 4]) + bbp[qq * 8 + 4], __uint_as_float(v[qq * 8 + 5]) + bbp[qq * 8 + 5]);
-                    o.w = pack_bf16_relu(__uint_as_float(v[qq * 8 + 6]) + bbp[qq * 8 + 6], __uint_as_float(v[qq * 8 + 7]) + bbp[qq * 8 + 7]);
-                    *reinterpret_cast<uint4*>(sA3 + (uint32_t)(4 * half + qq) * 2048u + row_off) = o;
-                }
+                for (int i = 0; i < 16; ++i)
+                    o[i] = pack_bf16_relu(__uint_as_float(v[2 * i]) + bbp[2 * i], __uint_as_float(v[2 * i + 1]) + bbp[2 * i + 1]);
+                tmem_st16(tmem_lane + TM_D2 + 32u * (uint32_t)half, o);
+                tmem_st_wait();
             }
-            fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barC);
             mbar_wait(barM, phM);
@@ -408,7 +402,7 @@ int enc_tc_make_maps(const NcaEncDesc* d, const float* states, int slots, const 
 }
 
 int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void* ws, const EncTcMaps* m, int slot_in, float* x1,
-                        const FireMask& fm, cudaStream_t s) {
+                        const FireMask& fm, cudaStream_t s, int pdl) {
     EncTcArgs a;
     etc_make_geom(d, &a.g);
     a.x1 = x1; a.slot_in = slot_in;
@@ -425,7 +419,8 @@ int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void*
     int grid = t2_num_sms() * occ;
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
     NCA_CUDA_OK(cudaFuncSetAttribute(enc_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    enc_fwd_tc_kernel<0><<<grid, ET2_NTHREADS, smem, s>>>(*(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l, *(const CUtensorMap*)m->g, a);
+    NCA_CUDA_OK(t2_launch(enc_fwd_tc_kernel<0>, grid, ET2_NTHREADS, smem, s, pdl != 0, *(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l,
+                          *(const CUtensorMap*)m->g, a));
     NCA_LAUNCH_OK();
     return NCA_OK;
 }

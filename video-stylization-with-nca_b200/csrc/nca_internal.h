@@ -58,7 +58,7 @@ size_t enc_tc_weight_bytes(const NcaEncDesc* d);
 int enc_tc_prep_weights(const NcaEncDesc* d, const NcaEncWeights* w, void* ws, cudaStream_t s);
 int enc_tc_make_maps(const NcaEncDesc* d, const float* states, int slots, const float* goal, EncTcMaps* m);
 int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void* ws, const EncTcMaps* m, int slot_in, float* x1,
-                        const FireMask& fm, cudaStream_t s);
+                        const FireMask& fm, cudaStream_t s, int pdl);
 bool enc_tc_bwd_supported(const NcaEncDesc* d);
 int enc_tc_make_gmap(const NcaEncDesc* d, const float* gnext, EncTcMaps* m);
 int enc_tc_backward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void* ws, const EncTcMaps* m, const EncTcMaps* gm,
