@@ -226,8 +226,8 @@ def main():
 
     # ---- dominant kernel: the BPTT step kernel, timed through the C ABI call that launches it T times ----
     cfg = model._cfg(_lib.NCA_COND_CPE, 2)
-    hist, coarse = Fn._dynca_forward_raw(cfg, x0, *[p.detach() for p in (model.w1.weight, model.w1.bias, model.w2.weight, model.w2.bias)],
-                                         None, None, 77, T, 0.5, True)
+    hist, coarse, ops = Fn._dynca_forward_raw(cfg, x0, *[p.detach() for p in (model.w1.weight, model.w1.bias, model.w2.weight, model.w2.bias)],
+                                              None, None, 77, T, 0.5, True, want_ops=True)
     import ctypes as Ct
     d = cfg.desc(B, H, W, 0.5, False)
     nbytes = lib.nca_dynca_workspace_bytes(Ct.byref(d), 1)
@@ -240,10 +240,10 @@ def main():
 
     def bwd_call(i):
         Fn.check(lib.nca_dynca_backward(Ct.byref(d), Ct.byref(wst), None, None, Ct.c_uint64(77), 0, T, hist.data_ptr(),
-                                        coarse.data_ptr() if coarse is not None else None, g_final.data_ptr(), (Ct.c_void_p * 1)(), (Ct.c_int32 * 1)(), 0, 1, 2.0,
+                                        coarse.data_ptr() if coarse is not None else None, ops.data_ptr() if ops is not None else None, g_final.data_ptr(), (Ct.c_void_p * 1)(), (Ct.c_int32 * 1)(), 0, 1, 2.0,
                                         gx0.data_ptr(), Ct.byref(gst), ws.data_ptr(), nbytes, stream))
     ms_bwd_call = timed(bwd_call, max(2, args.steps // 2), 1)
-    del hist, coarse
+    del hist, coarse, ops
     ms_kernel = ms_bwd_call / T
     hbm, tens, which = peaks()
     cu_kernel = B * H * W / (ms_kernel * 1e-3)          # cell-updates/s of one BPTT launch

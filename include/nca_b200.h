@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NCA_B200_ABI_VERSION 3
+#define NCA_B200_ABI_VERSION 4
 
 enum { NCA_OK = 0, NCA_ERR_ARG = -1, NCA_ERR_UNSUPPORTED = -2, NCA_ERR_CUDA = -3, NCA_ERR_WORKSPACE = -4 };
 
@@ -88,10 +88,18 @@ int nca_edge_extract(int B, int H, int W, const float* img, int tanh_transform, 
  *   coarse_hist: optional (may be NULL), only used when n_scales == 2 and keep_history != 0: float
  *            [T+1,B,C,H/2,W/2]; the forward writes the 2x2-mean coarse state of every states[t] there so that
  *            nca_dynca_backward does not have to recompute it (pass the same buffer to it)
+ *   op_hist: optional (may be NULL), only used when keep_history != 0 and nca_dynca_op_hist_bytes(d, T) != 0: that many
+ *            bytes, 16-byte aligned.  The forward records the bf16 perception operands of every tile of every step there
+ *            (one bulk copy per tile) so that nca_dynca_backward loads them instead of recomputing the perception: memory
+ *            (160-224 B per cell and step) traded for time; results are bit-identical with and without it
  *   workspace: nca_dynca_workspace_bytes(d, 0) bytes                                              */
 int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
                       uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, float* coarse_hist,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      void* op_hist, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Size of the optional operand history of a T-step rollout; 0 when the description does not dispatch to the kernels that
+ * use one (then pass op_hist = NULL). */
+size_t nca_dynca_op_hist_bytes(const NcaDyncaDesc* d, int32_t T);
 
 /* BPTT through the T steps recorded in `states` ([T+1,B,C,H,W] from nca_dynca_forward with keep_history).
  * Replaces autograd's replay of dynca.py:113-128 x T.
@@ -103,11 +111,12 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
  *   gx0      : dL/d states[0]  [B,C,H,W] (written)
  *   gw       : weight gradients, reference layout (written)
  *   coarse_hist: NULL or the buffer nca_dynca_forward filled (n_scales == 2)
+ *   op_hist  : NULL or the operand history nca_dynca_forward filled for the same d, T
  *   workspace: nca_dynca_workspace_bytes(d, 1) bytes
  * State gradients are accumulated with red.add (fp32 summation order is not deterministic).          */
 int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
                        uint64_t seed, int32_t t0, int32_t T, const float* states, const float* coarse_hist,
-                       const float* g_final, const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps,
+                       const void* op_hist, const float* g_final, const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps,
                        int32_t tap_c, float tap_scale, float* gx0, const NcaDyncaWeightGrads* gw,
                        void* workspace, size_t workspace_bytes, void* stream);
 

@@ -42,7 +42,8 @@ class EncWeights(C.Structure):
 
 # every symbol include/nca_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ["nca_last_error", "nca_abi_version", "nca_launch_count", "nca_launch_count_reset", "nca_dynca_perceive",
-           "nca_edge_extract", "nca_dynca_forward", "nca_dynca_backward", "nca_dynca_workspace_bytes", "nca_dynca_kernel_variant",
+           "nca_edge_extract", "nca_dynca_forward", "nca_dynca_backward", "nca_dynca_workspace_bytes", "nca_dynca_op_hist_bytes",
+           "nca_dynca_kernel_variant",
            "nca_philox_mask", "nca_enc_forward", "nca_enc_backward", "nca_enc_workspace_bytes"]
 
 
@@ -70,9 +71,11 @@ def load_library():
     lib.nca_dynca_perceive.argtypes = [C.POINTER(DyncaDesc), P, P, P, P]
     lib.nca_edge_extract.argtypes = [C.c_int, C.c_int, C.c_int, P, C.c_int, P, P]
     lib.nca_philox_mask.argtypes = [I, I, I, F, I, U64, I, I, P, P]
-    lib.nca_dynca_forward.argtypes = [C.POINTER(DyncaDesc), C.POINTER(DyncaWeights), P, P, U64, I, I, I, P, P, P, SZ, P]
+    lib.nca_dynca_op_hist_bytes.restype = SZ
+    lib.nca_dynca_op_hist_bytes.argtypes = [C.POINTER(DyncaDesc), I]
+    lib.nca_dynca_forward.argtypes = [C.POINTER(DyncaDesc), C.POINTER(DyncaWeights), P, P, U64, I, I, I, P, P, P, P, SZ, P]
     lib.nca_dynca_kernel_variant.argtypes = [C.POINTER(DyncaDesc), I]
-    lib.nca_dynca_backward.argtypes = [C.POINTER(DyncaDesc), C.POINTER(DyncaWeights), P, P, U64, I, I, P, P, P,
+    lib.nca_dynca_backward.argtypes = [C.POINTER(DyncaDesc), C.POINTER(DyncaWeights), P, P, U64, I, I, P, P, P, P,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int32), I, I, F, P,
                                        C.POINTER(DyncaWeights), P, SZ, P]
     lib.nca_enc_workspace_bytes.restype = SZ
@@ -80,7 +83,7 @@ def load_library():
     lib.nca_enc_forward.argtypes = [C.POINTER(EncDesc), C.POINTER(EncWeights), P, P, U64, I, I, I, P, P, P, SZ, P]
     lib.nca_enc_backward.argtypes = [C.POINTER(EncDesc), C.POINTER(EncWeights), P, P, U64, I, I, P, P, P, P, P,
                                      C.POINTER(EncWeights), P, SZ, P]
-    if lib.nca_abi_version() != 3:
+    if lib.nca_abi_version() != 4:
         raise NcaError("libnca_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -28,6 +28,7 @@ struct T2FwdArgs {
     const __nv_bfloat16* B1; const __nv_bfloat16* B2; const float* b2p; const __nv_bfloat16* U;
     FireMask fm;
     T2Tiles tl;
+    uint8_t* op_out;   // operand history of this step (A1 | Zc of every tile, for the BPTT) or NULL
     int dbg;
     int pdl;           // launch with the programmatic-serialization attribute (not the first step of a call)
     long long* tdbg;   // optional phase timestamps of CTA 0 (debug)
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
         const uint64_t dB2 = umma_desc(smem_u32(sB2w), 256u, 128u);
         const uint64_t sB1k = (uint64_t)((2u * lbo_b1) >> 4);
         const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, k2steps = fc / 16;
+        const uint32_t op_bytes = dynca_tc2_op_tile_bytes(g);
         const CUtensorMap* const ptm_x = &tm_x;
         const CUtensorMap* const ptm_xc = &tm_xc;
         const CUtensorMap* const ptm_c = &tm_c;
@@ -165,6 +167,9 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
             tc_fence_after();
             T2_MSTAMP(1);
             if (leader) {
+                // operand history: the perception operands of this tile (A1 and, behind it, Zc) go to global memory as one
+                // bulk copy, so that the BPTT loads them instead of recomputing the perception
+                if (a.op_out) bulk_store(a.op_out + (size_t)tile * op_bytes, sA1, op_bytes);
                 if (NS == 2) {
                     // Dc = Zc . W1h^T over the perception columns.  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of
                     // the M = 128 instruction alias the next chunk (finite values) and produce rows of Dc nobody reads
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid
             tc_fence_after();
             T2_MSTAMP(5);
             if (leader) {
+                if (a.op_out) bulk_store_wait_read();             // A1 / Zc have been read: the next tile may overwrite them
 #pragma unroll 8
                 for (int ks = 0; ks < k2steps; ++ks)
                     umma_ts(tmem_base + TM_D2, tmem_base + (NS == 2 ? 64u + 8u * (uint32_t)ks : 64u * (uint32_t)(ks >> 2) + 8u * (uint32_t)(ks & 3)),
@@ -435,6 +441,12 @@ __global__ void dynca_tc2_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __r
 }
 
 // ---- host side --------------------------------------------------------------------------------------------
+// operand history: per step, per tile, A1 [K1/8 chunks x 128 rows x 16 B] followed (two scales) by Zc [8 x 64 x 16 B]
+size_t dynca_tc2_op_hist_bytes(const DyncaGeom& g, int T) {
+    const T2Tiles tl = t2_make_tiles(g.B, g.H, g.W);
+    return (size_t)T * tl.n_tiles * dynca_tc2_op_tile_bytes(g);
+}
+
 bool dynca_tc2_supported(const DyncaGeom& g) {
     Bf16Geom bg;
     if (g.fc % 32 != 0 || g.fc < 32 || g.fc > 128 || g.cc + 2 > 8 || g.C > 16) return false;
@@ -479,9 +491,11 @@ int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, cons
 }
 
 int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Maps* m, int slot_in, const float* x_in, float* x_out,
-                           int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s, int pdl) {
+                           int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s, int pdl,
+                           uint8_t* op_out) {
     T2FwdArgs a;
     a.pdl = pdl;
+    a.op_out = op_out;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
     a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.x_out = x_out; a.xc_out = xc_out;

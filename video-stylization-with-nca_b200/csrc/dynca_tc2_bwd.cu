@@ -57,6 +57,7 @@ struct T2BwdArgs {
     FireMask fm;
     T2Tiles tl;
     int pdl;           // launch with the programmatic-serialization attribute (not the first step of a call)
+    const uint8_t* op_in;   // operand history of this step (A1 | Zc per tile, written by the forward) or NULL = recompute the perception
     long long* tdbg;
 };
 
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     uint64_t* barD = reinterpret_cast<uint64_t*>(smem + 72);      // GaU (bf16) written
     uint64_t* barE = reinterpret_cast<uint64_t*>(smem + 80);      // D6 / D7 read back (their TMEM columns are D3's)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 88);
+    uint64_t* barO = reinterpret_cast<uint64_t*>(smem + 96);      // [2]: operand-history tiles (A1 | Zc) of buffer 0 / 1 loaded
     float* sFire2 = reinterpret_cast<float*>(smem + 128);               // 2 x 128 floats
     uint32_t* sCpe2 = reinterpret_cast<uint32_t*>(smem + 128 + 1024);   // 2 x 24
     uint8_t* sB1 = smem + L.b1;
@@ -216,9 +218,13 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     const size_t plane = (size_t)H * W;
     const int n_tiles = a.tl.n_tiles;
     const int N6 = 16 * ((bg.npairs + 1) / 2);                 // perception columns of g_z, padded to the MMA granularity
-    const uint32_t stage_bytes = (uint32_t)C * (T2_XR * T2_XS + T2_TH * T2_TW) * 4u +
-                                 (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u) +
-                                 (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
+    // with an operand history the perception operands arrive by bulk copy and only the gradient tiles are staged
+    const bool ophist = a.op_in != nullptr;
+    const uint32_t stage_bytes = ophist ? (uint32_t)C * (T2_TH * T2_TW + (NS == 2 ? 32 : 0)) * 4u
+                                        : (uint32_t)C * (T2_XR * T2_XS + T2_TH * T2_TW) * 4u +
+                                              (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u) +
+                                              (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
+    const uint32_t op_bytes = dynca_tc2_op_tile_bytes(g);
 
     griddep_launch();
     // ---- one-time setup (independent of the previous launch's output: may overlap its tail) ----
@@ -235,6 +241,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         mbar_init(barM1, 1); mbar_init(barM2, 1); mbar_init(barM3, 1); mbar_init(barM4, 1); mbar_init(barT, 1);
         mbar_init(barA, TB_NCOMP); mbar_init(barG, TB_NCOMP); mbar_init(barB, TB_NCOMP);
         mbar_init(barC, TB_NCOMP); mbar_init(barD, TB_NCOMP); mbar_init(barE, TB_NCOMP);
+        mbar_init(barO, 1); mbar_init(barO + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(tmem_slot, 512u);
@@ -283,24 +290,46 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         int tb_, ty_, tx_;                                                                                               \
         t2_tile_decode(a.tl, tt_, tb_, ty_, tx_);                                                                        \
         mbar_expect_tx(barT, stage_bytes);                                                                               \
-        tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                               \
+        if (!ophist) tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                  \
         tma_load_5d(sGn, ptm_g, barT, tx_, ty_, 0, tb_, 0);                                                              \
-        if (g.cond_kind == NCA_COND_TENSOR) tma_load_5d(sCond, ptm_c, barT, tx_, ty_, 0, tb_, 0);                        \
+        if (!ophist && g.cond_kind == NCA_COND_TENSOR) tma_load_5d(sCond, ptm_c, barT, tx_, ty_, 0, tb_, 0);             \
         if (NS == 2) {                                                                                                   \
-            tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);                          \
+            if (!ophist) tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);             \
             tma_load_5d(sGcn, ptm_gc, barT, tx_ >> 1, ty_ >> 1, 0, tb_, 0);                                              \
         }                                                                                                                \
     } while (0)
-        if (leader && (int)blockIdx.x < n_tiles) TB_ISSUE_TMA(blockIdx.x);
+        // operand-history tile of sequence index par_ (buffer par_ & 1): A1 then Zc, one mbarrier per buffer
+#define TB_ISSUE_OP(tile_, par_)                                                                                         \
+    do {                                                                                                                 \
+        const uint8_t* src_ = a.op_in + (size_t)(tile_) * op_bytes;                                                      \
+        uint64_t* bo_ = barO + ((par_) & 1);                                                                             \
+        mbar_expect_tx(bo_, op_bytes);                                                                                   \
+        bulk_load(sA12 + (uint32_t)((par_) & 1) * bg.a1_bytes, src_, bg.a1_bytes, bo_);                                  \
+        if (NS == 2) bulk_load(sZc2 + (uint32_t)((par_) & 1) * 8192u, src_ + bg.a1_bytes, 8192u, bo_);                   \
+    } while (0)
+        if (leader && (int)blockIdx.x < n_tiles) {
+            TB_ISSUE_TMA(blockIdx.x);
+            if (ophist) {
+                TB_ISSUE_OP(blockIdx.x, 0);
+                if ((int)(blockIdx.x + gridDim.x) < n_tiles) TB_ISSUE_OP(blockIdx.x + gridDim.x, 1);
+            }
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint64_t par = (uint64_t)(it & 1);
+            if (ophist && it >= 1) {
+                // the operand buffer of the previous tile is free once its last reader (the second gradient batch, or the
+                // first with one scale) is complete: load the tile after this one into it
+                mbar_wait(NS == 2 ? barM4 : barM3, (uint32_t)((it - 1) & 1));
+                if (leader && tile + (int)gridDim.x < n_tiles) TB_ISSUE_OP(tile + gridDim.x, it + 1);
+            }
             const uint64_t dA1 = dA1_0 + par * oA1, dA1t = dA1t_0 + par * oA1;
             const uint64_t dZc = dZc_0 + par * oZc, dZct = dZct_0 + par * oZc;
             const uint64_t dGy = dGy_0 + par * oGy, dGyt = dGyt_0 + par * oGy;
             // ---- recompute batch: the compute warps produced these operands while the previous tile's gradient MMAs ran ----
             mbar_wait(barA, phA);
             phA ^= 1u;
+            if (ophist) mbar_wait(barO + (it & 1), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             if (leader) {
                 if (NS == 2) {
@@ -419,6 +448,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             const bool inimg = gy < H && gx < W;
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
                                 (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
+            if (ophist) return;                              // A1 / Zc arrive from the operand history (the MMA warp waits for them)
             uint8_t* sA1 = sA12 + (uint32_t)(itn & 1) * bg.a1_bytes;
             const uint32_t* sCpe = sCpe2 + (itn & 1) * 24;
             mbar_wait(barT, phT);
@@ -452,7 +482,12 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             uint8_t* sZc = sZc2 + (uint32_t)par * 8192u;
             uint8_t* sGy = sGy2 + (uint32_t)par * 4096u;
             const float* sFire = sFire2 + par * 128;
-            if (NS == 2) t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
+            if (ophist) {                                     // the gradient stage is this phase's only input
+                mbar_wait(barT, phT);
+                phT ^= 1u;
+            } else if (NS == 2) {
+                t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
+            }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barA);
@@ -972,9 +1007,10 @@ int dynca_tc2_add_coarse(const DyncaGeom& g, const float* gc, float* gx, cudaStr
 int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const DyncaTc2Maps* xm, int slot_in, const float* x_in,
                             int cslot_in, const float* xc_in, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
                             int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out,
-                            const float* cond, const FireMask& fm, cudaStream_t s, int pdl) {
+                            const float* cond, const FireMask& fm, cudaStream_t s, int pdl, const uint8_t* op_in) {
     T2BwdArgs a;
     a.pdl = pdl;
+    a.op_in = op_in;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
     a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.slot_in = slot_in; a.cslot_in = cslot_in;

@@ -110,9 +110,17 @@ int nca_philox_mask(int32_t B, int32_t H, int32_t W, float rate, int32_t enc, ui
     return nca_philox_mask_launch(B, H, W, rate, enc, seed, t0, T, out, (cudaStream_t)stream);
 }
 
+size_t nca_dynca_op_hist_bytes(const NcaDyncaDesc* d, int32_t T) {
+    DyncaGeom g;
+    if (d == nullptr || T <= 0 || dynca_make_geom(d, &g)) return 0;
+    if (d->precision != NCA_PREC_BF16 && d->precision != NCA_PREC_FP32) return 0;
+    if (dynca_variant(d, g, 0) != 2 || dynca_variant(d, g, 1) != 2) return 0;
+    return dynca_tc2_op_hist_bytes(g, T);
+}
+
 int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
                       uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, float* coarse_hist,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      void* op_hist, void* workspace, size_t workspace_bytes, void* stream) {
     DyncaGeom g;
     int rc = check_common(d, &g, cond, masks);
     if (rc) return rc;
@@ -135,6 +143,9 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
     if (rc) return rc;
     // coarse states (two perception scales on the tensor-core paths): a history when the caller keeps one, else ping-pong
     const bool chist = keep_history && coarse_hist != nullptr && g.ns == 2;
+    const bool ohist = keep_history && op_hist != nullptr && variant == 2 && dynca_tc2_bwd_supported(g);
+    NCA_CHECK_ARG(NCA_ALIGNED16(op_hist), "op_hist must be 16-byte aligned");
+    const size_t op_step = ohist ? dynca_tc2_op_hist_bytes(g, 1) : 0;
     float* cbase = chist ? coarse_hist : wsXc;
     const size_t cstride = chist ? (size_t)g.B * g.C * (g.H / 2) * (g.W / 2) : nc;
     DyncaTc2Maps maps;
@@ -154,7 +165,8 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
             if (g.ns == 2 && t == 0) { rc = dynca_bf16_coarsen(g, xin, cbase + (size_t)ci * cstride, s); if (rc) return rc; }
             const bool need_next = g.ns == 2 && (t + 1 < T || chist);
             rc = dynca_tc2_forward_step(g, wsB, &maps, si, xin, xout, ci, g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr,
-                                        need_next ? cbase + (size_t)co * cstride : nullptr, cond, fm, s, t > 0);
+                                        need_next ? cbase + (size_t)co * cstride : nullptr, cond, fm, s, t > 0,
+                                        ohist ? (uint8_t*)op_hist + (size_t)t * op_step : nullptr);
         } else if (variant == 1) {
             float* xc = g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr;
             rc = dynca_bf16_forward_step(g, wsB, xc, xin, xout, cond, fm, s);
@@ -169,7 +181,7 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
 
 int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
                        uint64_t seed, int32_t t0, int32_t T, const float* states, const float* coarse_hist,
-                       const float* g_final, const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps,
+                       const void* op_hist, const float* g_final, const float* const* g_taps, const int32_t* tap_steps, int32_t n_taps,
                        int32_t tap_c, float tap_scale, float* gx0, const NcaDyncaWeightGrads* gw, void* workspace,
                        size_t workspace_bytes, void* stream) {
     DyncaGeom g;
@@ -242,7 +254,8 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
             rc = dynca_tc2_backward_step(g, wsB, wsG, &xm, t, states + (size_t)t * n, chist ? t : 0, xc_t,
                                          from_final ? &gm_final : &gm[p_in], from_final ? const_cast<float*>(g_final) : F[p_in], G[p_in],
                                          from_final ? 0 : 1, 1, tap, tap_c, tap_scale, gout, G[p_out], cond, fm, s,
-                                         t < T - 1 && (chist || g.ns != 2));      // no coarsen launch in between
+                                         t < T - 1 && (chist || g.ns != 2),       // no coarsen launch in between
+                                         op_hist ? (const uint8_t*)op_hist + (size_t)t * dynca_tc2_op_hist_bytes(g, 1) : nullptr);
             if (rc) return rc;
             p_in = p_out;
         }

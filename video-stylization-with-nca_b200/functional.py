@@ -4,6 +4,7 @@ Everything here runs on CUDA through libnca_b200.so; tensors are fp32, contiguou
 for device memory, streams and autograd bookkeeping.
 """
 import collections.abc
+import os
 import ctypes as C
 
 import torch
@@ -105,7 +106,14 @@ def philox_mask(B, H, W, rate, seed, T, t0=0, enc=False, device="cuda"):
     return out
 
 
-def _dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, masks, seed, T, rate, keep_history):
+# Operand history (nca_b200.h: op_hist): the forward records the bf16 perception operands of every step so that the BPTT
+# loads them instead of recomputing the perception.  160-224 B per cell and step; used while it stays below this many bytes
+# (NCA_OP_HIST_MAX_GB, default 48; 0 disables), results are bit-identical either way.
+def _op_hist_limit():
+    return int(float(os.environ.get("NCA_OP_HIST_MAX_GB", "48")) * (1 << 30))
+
+
+def _dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, masks, seed, T, rate, keep_history, want_ops=False):
     lib = load_library()
     B, Cc, H, W = x0.shape
     d = cfg.desc(B, H, W, rate, masks is not None)
@@ -115,12 +123,19 @@ def _dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, masks, seed, T, rate, keep
     coarse = None
     if keep_history and cfg.ns == 2:     # coarse (2x2-mean) state history, reused by the BPTT
         coarse = torch.empty(n_slots, B, Cc, H // 2, W // 2, device=x0.device, dtype=torch.float32)
+    ops = None
     with torch.cuda.device(x0.device):
+        if keep_history and want_ops and T > 0:
+            ob = lib.nca_dynca_op_hist_bytes(C.byref(d), T)
+            if 0 < ob <= _op_hist_limit():
+                ops = torch.empty(ob, device=x0.device, dtype=torch.uint8)
         nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
         ws = torch.empty(max(nbytes, 16), device=x0.device, dtype=torch.uint8)
         wst = _weights_struct(w1, b1, w2, b2)
         check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(seed), 0, T,
-                                    int(keep_history), _ptr(states), _ptr(coarse), _ptr(ws), nbytes, _stream()))
+                                    int(keep_history), _ptr(states), _ptr(coarse), _ptr(ops), _ptr(ws), nbytes, _stream()))
+    if keep_history and want_ops:
+        return states, coarse, ops
     if keep_history:
         return states, coarse
     return states
@@ -140,8 +155,9 @@ class _DyncaRollout(torch.autograd.Function):
     def forward(ctx, x0, w1, b1, w2, b2, cond, masks, cfg, T, rate, seed, handle):
         x0c, w1c, b1c, w2c, b2c = _c(x0), _c(w1), _c(b1), _c(w2), _c(b2)
         cond, masks = _c(cond), _c(masks)
-        hist, coarse = _dynca_forward_raw(cfg, x0c, w1c, b1c, w2c, b2c, cond, masks, seed, T, rate, True)
+        hist, coarse, ops = _dynca_forward_raw(cfg, x0c, w1c, b1c, w2c, b2c, cond, masks, seed, T, rate, True, want_ops=True)
         ctx.coarse = coarse
+        ctx.ops = ops
         ctx.cfg, ctx.T, ctx.rate, ctx.seed, ctx.handle = cfg, T, rate, seed, handle
         ctx.w_shapes = (w1.shape, b1.shape, w2.shape, b2.shape)
         ctx.save_for_backward(w1c, b1c, w2c, b2c, cond, masks)
@@ -172,9 +188,10 @@ class _DyncaRollout(torch.autograd.Function):
             wst = _weights_struct(w1, b1, w2, b2)
             gst = _weights_struct(gw1, gb1, gw2, gb2)
             check(lib.nca_dynca_backward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(ctx.seed), 0, T,
-                                         _ptr(hist), _ptr(ctx.coarse), _ptr(g_final), tap_ptrs, tap_steps, n_taps, max(tap_c, 1), 2.0,
+                                         _ptr(hist), _ptr(ctx.coarse), _ptr(ctx.ops), _ptr(g_final), tap_ptrs, tap_steps, n_taps, max(tap_c, 1), 2.0,
                                          _ptr(gx0), C.byref(gst), _ptr(ws), nbytes, _stream()))
         ctx.handle.tap_grads = {}
+        ctx.ops = None
         s1, sb1, s2, sb2 = ctx.w_shapes
         return (gx0, gw1.view(s1), gb1.view(sb1), gw2.view(s2), gb2.view(sb2), None, None, None, None, None, None, None)
 
