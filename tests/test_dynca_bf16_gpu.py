@@ -220,3 +220,38 @@ def test_tc2_c5_frame_properties():
         xs, ms = torch.roll(x0, (dy, dx), (2, 3)), torch.roll(masks, (dy, dx), (3, 4))
         c, _ = mb.forward_nsteps(xs.contiguous(), T, masks=ms.contiguous())
         assert torch.equal(torch.roll(a, (dy, dx), (2, 3)), c)
+
+
+@pytest.mark.parametrize("case", EMU_SHAPES[:4] + [(2, 16, 128, 64, 96, 3, "replicate", (0, 1), "cpe")],
+                         ids=lambda c: "B%d_C%d_fc%d_%dx%d_T%d_%s_s%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], len(c[7]), c[8]))
+def test_tc2_operand_history_matches_recompute(case, monkeypatch):
+    """The BPTT that loads the perception operands the forward recorded (nca_b200.h: op_hist) and the BPTT that recomputes
+    the perception from the state history see bit-identical operands: gradients agree to fp32 summation order."""
+    import ctypes as Ct
+    B, C, fc, H, W, T, pad, scales, cond = case
+    g = torch.Generator().manual_seed(5)
+    cc = {"cpe": 2, None: 0, "tensor": 3}[cond]
+    kind = {"cpe": _lib.NCA_COND_CPE, None: _lib.NCA_COND_NONE, "tensor": _lib.NCA_COND_TENSOR}[cond]
+    cfg = Fn.DyncaConfig(C, fc, pad, list(scales), kind, cc, precision="bf16")
+    lib = nca_b200.load_library()
+    d = cfg.desc(B, H, W, 0.5, True)
+    tiles = B * ((H + 7) // 8) * ((W + 15) // 16)
+    assert lib.nca_dynca_op_hist_bytes(Ct.byref(d), T) % (T * tiles) == 0 and lib.nca_dynca_op_hist_bytes(Ct.byref(d), T) > 0
+    d32 = Fn.DyncaConfig(C, fc, pad, list(scales), kind, cc, precision="fp32").desc(B, H, W, 0.5, True)
+    assert lib.nca_dynca_op_hist_bytes(Ct.byref(d32), T) == 0            # the fp32 kernels recompute
+    params = [torch.randn(fc, 4 * C + cc, generator=g) * 0.15, torch.randn(fc, generator=g) * 0.1,
+              torch.randn(C, fc, generator=g) * 0.1, torch.randn(C, generator=g) * 0.02]
+    x0 = torch.rand(B, C, H, W, generator=g) - 0.5
+    masks = (torch.rand(T, B, 1, H, W, generator=g) + 0.5).floor().to(DEV)
+    cf = torch.randn(B, C, H, W, generator=g).to(DEV)
+    cond_t = torch.randn(B, 3, H, W, generator=g).to(DEV) if cond == "tensor" else None
+    grads = []
+    for limit in ("48", "0"):
+        monkeypatch.setenv("NCA_OP_HIST_MAX_GB", limit)
+        pg = [p.clone().to(DEV).requires_grad_(True) for p in [x0] + params]
+        fg, _ = Fn.dynca_rollout(cfg, *pg, T, 0.5, cond=cond_t, masks=masks)
+        (fg * cf).sum().backward()
+        grads.append([fg.detach().cpu()] + [p.grad.cpu() for p in pg])
+    assert torch.equal(grads[0][0], grads[1][0])                          # the forward is the same kernel either way
+    for a, b in zip(grads[0][1:], grads[1][1:]):
+        assert rel_err(a, b) < 2e-5
