@@ -23,9 +23,13 @@
 #define T2_THREADS 256
 #define T2_HDR 1536u
 
-// tile index -> (sample, y0, x0) without runtime integer division: q = floor(n / d) = umul64hi(n, ceil(2^64 / d))
+// tile index -> (sample, y0, x0) without runtime integer division: q = floor(n / d) = umul64hi(n, ceil(2^64 / d)).
+// The column is rotated by the row index (skew): a persistent CTA visits tiles blockIdx.x + k * gridDim.x, and with 16 tiles
+// per row and 148 / 296 CTAs that stride is 4 / 8 columns, so without the rotation a quarter (an eighth) of the CTAs would
+// process an image-border column every 4th (2nd) tile and the others never - border tiles cost ~40 % more, and the launch ends
+// with the slowest CTA.  With the rotation every CTA cycles through all columns.
 struct T2Tiles {
-    int tiles_x, tiles_y, n_tiles, per_b;
+    int tiles_x, tiles_y, n_tiles, per_b, skew_mask;
     unsigned long long mx, mb;      // ceil(2^64 / tiles_x), ceil(2^64 / per_b); 0 when the divisor is 1
 };
 static inline T2Tiles t2_make_tiles(int B, int H, int W) {
@@ -34,13 +38,18 @@ static inline T2Tiles t2_make_tiles(int B, int H, int W) {
     t.per_b = t.tiles_x * t.tiles_y; t.n_tiles = B * t.per_b;
     t.mx = t.tiles_x == 1 ? 0ull : ~0ull / (unsigned long long)t.tiles_x + 1ull;
     t.mb = t.per_b == 1 ? 0ull : ~0ull / (unsigned long long)t.per_b + 1ull;
+    int p = 1;
+    while (2 * p <= t.tiles_x) p *= 2;      // largest power of two <= tiles_x: the skew stays below tiles_x
+    t.skew_mask = p - 1;
     return t;
 }
 __device__ __forceinline__ void t2_tile_decode(const T2Tiles& t, int tile, int& b, int& y0, int& x0) {
     const unsigned q1 = t.mx ? (unsigned)__umul64hi((unsigned long long)tile, t.mx) : (unsigned)tile;      // tile / tiles_x
     const unsigned bb = t.mb ? (unsigned)__umul64hi((unsigned long long)tile, t.mb) : (unsigned)tile;      // tile / per_b
     b = (int)bb;
-    x0 = (tile - (int)q1 * t.tiles_x) * T2_TW;
+    int tx = tile - (int)q1 * t.tiles_x + ((int)q1 & t.skew_mask);
+    if (tx >= t.tiles_x) tx -= t.tiles_x;
+    x0 = tx * T2_TW;
     y0 = ((int)q1 - (int)bb * t.tiles_y) * T2_TH;
 }
 
