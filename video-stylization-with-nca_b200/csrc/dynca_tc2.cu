@@ -513,21 +513,37 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     a.tl = t2_make_tiles(g.B, g.H, g.W);
     const size_t smem = t2_smem(g, a.bg).total;
     const uint32_t tcols = g.ns == 2 ? 256u : 128u;
-    int occ = (int)((227 * 1024) / (smem + 1024));
+    // persistent grid = SMs x CTAs that are really co-resident: shared memory, REGISTERS (72 per thread with one scale: three
+    // CTAs, not the four that shared memory and TMEM would allow - a fourth wave of CTAs would run alone afterwards) and TMEM.
+    // Computed once per (kernel, shared-memory size).
+    const CUtensorMap* tx = (const CUtensorMap*)m->x;
+    const CUtensorMap* txc = (const CUtensorMap*)m->xc;
+    const CUtensorMap* tcn = (const CUtensorMap*)m->cond;
+    static size_t occ_smem[2] = {0, 0};
+    static int occ_val[2] = {0, 0};
+    const int oi = g.ns == 2 ? 1 : 0;
+    if (occ_val[oi] == 0 || occ_smem[oi] != smem) {
+        int o = 0;
+        if (g.ns == 2) {
+            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<2>, T2_NTHREADS);
+        } else {
+            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<1>, T2_NTHREADS);
+        }
+        const int by_smem = (int)((227 * 1024) / (smem + 1024));
+        if (o > by_smem) o = by_smem;
+        occ_val[oi] = o < 1 ? 1 : o;
+        occ_smem[oi] = smem;
+        if (getenv("NCA_T2_DBG")) fprintf(stderr, "tc2 fwd: ns %d smem %zu -> %d CTAs per SM (registers, shared memory)\n", g.ns, smem, occ_val[oi]);
+    }
+    int occ = occ_val[oi];
     if (occ > (int)(512u / tcols)) occ = (int)(512u / tcols);
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
-    const CUtensorMap* tx = (const CUtensorMap*)m->x;
-    const CUtensorMap* txc = (const CUtensorMap*)m->xc;
-    const CUtensorMap* tcn = (const CUtensorMap*)m->cond;
-    if (g.ns == 2) {
-        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<2>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
-    } else {
-        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<1>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
-    }
+    if (g.ns == 2) NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<2>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
+    else NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<1>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps (cycles since the tile's first stamp)
         long long h[256];

@@ -409,6 +409,17 @@ static inline int t2_make_map(CUtensorMap* tm, const float* base, int slots, siz
     return NCA_OK;
 }
 
+// CTAs of a kernel that are co-resident on an SM by registers (the occupancy API answers 1 for the kernels that allocate tensor
+// memory, so count by hand: registers are allocated per warp in units of 256)
+template <typename K>
+static inline int t2_occupancy_by_regs(K kernel, int threads) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess || fa.numRegs <= 0) return 1;
+    const int per_warp = (fa.numRegs * 32 + 255) / 256 * 256, warps = (threads + 31) / 32;
+    const int occ = 65536 / (per_warp * warps);
+    return occ < 1 ? 1 : occ;
+}
+
 static inline int t2_num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -413,12 +413,23 @@ int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void*
     a.fm = fm;
     a.tl = t2_make_tiles(d->B, d->H, d->W);
     const size_t smem = etc_smem(a.g).total;
-    int occ = (int)((227 * 1024) / (smem + 1024));
+    // co-resident CTAs: registers, shared memory (once per shared-memory size), TMEM (128 columns each)
+    static size_t occ_smem = 0;
+    static int occ_val = 0;
+    if (occ_val == 0 || occ_smem != smem) {
+        int o = 0;
+        NCA_CUDA_OK(cudaFuncSetAttribute(enc_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        o = t2_occupancy_by_regs(enc_fwd_tc_kernel<0>, ET2_NTHREADS);
+        const int by_smem = (int)((227 * 1024) / (smem + 1024));
+        if (o > by_smem) o = by_smem;
+        occ_val = o < 1 ? 1 : o;
+        occ_smem = smem;
+    }
+    int occ = occ_val;
     if (occ > 4) occ = 4;
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
-    NCA_CUDA_OK(cudaFuncSetAttribute(enc_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NCA_CUDA_OK(t2_launch(enc_fwd_tc_kernel<0>, grid, ET2_NTHREADS, smem, s, pdl != 0, *(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l,
                           *(const CUtensorMap*)m->g, a));
     NCA_LAUNCH_OK();
