@@ -62,7 +62,7 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
 #define T2_NTHREADS 288     // 8 compute warps + 1 MMA / TMA warp
 
 template <int NS>
-__global__ void __launch_bounds__(T2_NTHREADS) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
+__global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                      const __grid_constant__ CUtensorMap tm_xc,
                                                                      const __grid_constant__ CUtensorMap tm_c, const T2FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
