@@ -167,9 +167,6 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
             tc_fence_after();
             T2_MSTAMP(1);
             if (leader) {
-                // operand history: the perception operands of this tile (A1 and, behind it, Zc) go to global memory as one
-                // bulk copy, so that the BPTT loads them instead of recomputing the perception
-                if (a.op_out) bulk_store(a.op_out + (size_t)tile * op_bytes, sA1, op_bytes);
                 if (NS == 2) {
                     // Dc = Zc . W1h^T over the perception columns.  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of
                     // the M = 128 instruction alias the next chunk (finite values) and produce rows of Dc nobody reads
@@ -183,6 +180,10 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
                     umma_ss(tmem_base + TM_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
                 if (NS == 1) umma_commit(barM);
                 if (tile + (int)gridDim.x < n_tiles) T2_ISSUE_TMA(tile + gridDim.x);     // the stage is free
+                // operand history: the perception operands of this tile (A1 and, behind it, Zc) go to global memory as one
+                // bulk copy, so that the BPTT loads them instead of recomputing the perception (behind the MMAs and the
+                // prefetch, which the compute warps are waiting for)
+                if (a.op_out) bulk_store(a.op_out + (size_t)tile * op_bytes, sA1, op_bytes);
             }
             T2_MSTAMP(2);
             if (NS == 2) {
