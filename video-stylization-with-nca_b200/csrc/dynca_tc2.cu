@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
             }
             T2_MSTAMP(6);
         }
+        // the operand-history copies of this CTA are complete (not only read) before it exits
+        if (leader && a.op_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
         // =========================== compute warps ===========================
         const int r = tid & 127, half = tid >> 7;
