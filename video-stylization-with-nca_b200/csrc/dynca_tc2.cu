@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
     uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 24);    // 256 arrivals: DcB written
     uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 32);    // 256 arrivals: A2 written
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 40);
+    uint64_t* barZ = reinterpret_cast<uint64_t*>(smem + 48);    // 256 arrivals: Zc written (two scales: the coarse MMA starts under the fine perception)
     float* sB2 = reinterpret_cast<float*>(smem + 64);           // 16 floats
     float* sFire2 = reinterpret_cast<float*>(smem + 128);       // 2 x 128 floats (double buffered over tiles)
     uint32_t* sCpe2 = reinterpret_cast<uint32_t*>(smem + 128 + 1024);   // 2 x 24: bf16 hi | lo << 16 of the CPE rows / columns
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
         mbar_init(barA, 256);
         mbar_init(barB, 256);
         mbar_init(barC, 256);
+        mbar_init(barZ, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
         const CUtensorMap* const ptm_x = &tm_x;
         const CUtensorMap* const ptm_xc = &tm_xc;
         const CUtensorMap* const ptm_c = &tm_c;
-        uint32_t phA = 0, phB = 0, phC = 0;
+        uint32_t phA = 0, phB = 0, phC = 0, phZ = 0;
         const bool leader = elect_one();
 #define T2_ISSUE_TMA(tile_)                                                                                              \
     do {                                                                                                                 \
@@ -162,19 +164,25 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
         int miter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++miter) {
             T2_MSTAMP(0);
-            mbar_wait(barA, phA);
-            phA ^= 1u;
-            tc_fence_after();
-            T2_MSTAMP(1);
-            if (leader) {
-                if (NS == 2) {
-                    // Dc = Zc . W1h^T over the perception columns.  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of
-                    // the M = 128 instruction alias the next chunk (finite values) and produce rows of Dc nobody reads
+            if (NS == 2) {
+                // Dc = Zc . W1h^T over the perception columns as soon as the coarse operand is there (the compute warps go on with
+                // the fine perception).  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of the M = 128 instruction alias the
+                // next chunk (finite values) and produce rows of Dc nobody reads
+                mbar_wait(barZ, phZ);
+                phZ ^= 1u;
+                tc_fence_after();
+                if (leader) {
 #pragma unroll 4
                     for (int ks = 0; ks < kcsteps; ++ks)
                         umma_ss(tmem_base + TM_DC, dZc + (uint64_t)(ks * (2048 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
                     umma_commit(barM);
                 }
+            }
+            mbar_wait(barA, phA);
+            phA ^= 1u;
+            tc_fence_after();
+            T2_MSTAMP(1);
+            if (leader) {
 #pragma unroll 5
                 for (int ks = 0; ks < k1steps; ++ks)
                     umma_ss(tmem_base + TM_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
@@ -269,6 +277,12 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
             } else if (warp == (iter & 7)) {
                 t2_fire_tile(a.fm, b, y0, x0, H, W, lane, sFire);
             }
+            if (NS == 2) {         // coarse operand first: its MMA (Dc) then runs under the fine perception
+                t2_coarse_to_zc<8>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(barZ);
+            }
             t2_fine_to_a1<8>(sX, sA1, C, bg.npairs, warp, lane);
             T2_STAMP(11);
             // residual state of this thread's cell (channels 8*half ..), cond chunk, zero tail chunks of A1
@@ -291,7 +305,6 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
                 for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
                     *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
             }
-            if (NS == 2) t2_coarse_to_zc<8>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
             T2_STAMP(2);
             fence_proxy_async();
             tc_fence_before();
