@@ -537,6 +537,32 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             mbar_arrive(barG);
         };
 
+        // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major, for the tile whose operands were produced last:
+        //      runs one tile ahead (before the coarse transposed stencil of the current tile), so that U . DcB and with it D1 are
+        //      complete when the next tile starts ----
+        auto dc_roundtrip = [&]() {
+            mbar_wait(barM1, phM1);
+            phM1 ^= 1u;
+            tc_fence_after();
+            if ((warp & 3) < 2 && 32 * qtr < fc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)qtr, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                    o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                    o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                    o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                    *reinterpret_cast<uint4*>(sDcB + (uint32_t)(4 * qtr + qq) * 1024u + row_off) = o;
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(barB);
+        };
+
         float gn[4] = {0.f, 0.f, 0.f, 0.f}, gn_next[4] = {0.f, 0.f, 0.f, 0.f};
         if ((int)blockIdx.x < n_tiles) tables(blockIdx.x, 0);
         bar_sync_n(1, TB_NCOMP);
@@ -545,6 +571,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             t2_tile_decode(a.tl, blockIdx.x, nb, ny0, nx0);
             p1a(nb, ny0, nx0, 0);
             p1b(blockIdx.x, nb, ny0, nx0, 0, gn);
+            if (NS == 2) dc_roundtrip();
         }
 #ifdef NCA_T2_TIMING
 #define TB_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
@@ -560,30 +587,6 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
                                 (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
             TB_STAMP(0);
-            if (NS == 2) {
-                mbar_wait(barM1, phM1);
-                phM1 ^= 1u;
-                tc_fence_after();
-                TB_STAMP(1);
-                // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
-                if ((warp & 3) < 2 && 32 * qtr < fc) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)qtr, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                        o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                        o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                        o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                        *reinterpret_cast<uint4*>(sDcB + (uint32_t)(4 * qtr + qq) * 1024u + row_off) = o;
-                    }
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                mbar_arrive(barB);
-            }
             TB_STAMP(2);
             const int next = tile + (int)gridDim.x;
             if (next < n_tiles) {                              // software pipeline, part 1: in the shadow of D1 / D3
@@ -854,6 +857,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         bar_sync_n(1, TB_NCOMP);
                     }
                 }
+                if (next < n_tiles) dc_roundtrip();           // next tile's DcB: its U . DcB runs under the coarse stencil below
                 TB_STAMP(11);
                 // ---- P6: transposed coarse perception -> red.add into the coarse gradient buffer.
                 //      warp = (channel pair, 4-row block), lane = (channel of the pair, column of the 8 x 12 coarse ring):
