@@ -94,6 +94,23 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
     return d;
 }
 
+// packed fp32 pairs (FADD2 / FFMA2 on sm_100: one issue slot for two lanes of IEEE rn arithmetic - bit-identical to the scalar forms)
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {       // a * b + c
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return f2fma(make_float2(-1.0f, -1.0f), b, a); }      // a - b (exact product)
+__device__ __forceinline__ float2 f2fma2(float2 b, float2 c) { return f2fma(make_float2(2.0f, 2.0f), b, c); }      // 2 b + c
+
 // 0xffff in each half whose bf16 value is non-zero (relu mask of a packed hidden pair: h != 0 <=> pre-activation > 0)
 __device__ __forceinline__ uint32_t bf16x2_nz_mask(uint32_t h) {
     uint32_t m;

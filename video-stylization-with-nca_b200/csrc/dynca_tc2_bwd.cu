@@ -129,23 +129,23 @@ __device__ __forceinline__ void tb_stencil_t(const float* __restrict__ X, const 
 // horizontal pass of the transposed stencils over one plane row: p = X plane at the thread's aligned column 4j+4, the Y and
 // L planes follow at +ps, +2ps.  hx / hy = the 4 interior outputs of the group, ex / ey = the ring column (0 for j = 0,
 // 17 for j = 3), which sees only cell column 0 (x[1]) / 15 (x[4]).
-__device__ __forceinline__ void tb_hrow(const float* __restrict__ p, int ps, int j, float hx[4], float hy[4], float& ex, float& ey) {
+__device__ __forceinline__ void tb_hrow(const float* __restrict__ p, int ps, int j, float2 hx[2], float2 hy[2], float& ex, float& ey) {
     const float4 xa = *reinterpret_cast<const float4*>(p);
     const float2 xb = *reinterpret_cast<const float2*>(p + 4);
     const float4 ya = *reinterpret_cast<const float4*>(p + ps);
     const float2 yb = *reinterpret_cast<const float2*>(p + ps + 4);
     const float4 la = *reinterpret_cast<const float4*>(p + 2 * ps);
     const float2 lb = *reinterpret_cast<const float2*>(p + 2 * ps + 4);
-    const float x[6] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y};
-    const float y[6] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y};
-    const float l[6] = {la.x, la.y, la.z, la.w, lb.x, lb.y};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        hx[i] = (x[i] - x[i + 2]) + fmaf(2.0f, l[i + 1], l[i] + l[i + 2]);
-        hy[i] = fmaf(2.0f, y[i + 1], y[i] + y[i + 2]);
-    }
-    ex = j == 0 ? l[1] - x[1] : x[4] + l[4];
-    ey = j == 0 ? y[1] : y[4];
+    // outputs i = 0..3 as the pairs (0,1), (2,3): hx[i] = (x[i] - x[i+2]) + (2 l[i+1] + (l[i] + l[i+2])), hy[i] = 2 y[i+1] + (y[i] + y[i+2])
+    const float2 x01 = make_float2(xa.x, xa.y), x23 = make_float2(xa.z, xa.w);
+    const float2 l01 = make_float2(la.x, la.y), l23 = make_float2(la.z, la.w);
+    const float2 y01 = make_float2(ya.x, ya.y), y23 = make_float2(ya.z, ya.w);
+    hx[0] = f2add(f2sub(x01, x23), f2fma2(make_float2(la.y, la.z), f2add(l01, l23)));
+    hx[1] = f2add(f2sub(x23, xb), f2fma2(make_float2(la.w, lb.x), f2add(l23, lb)));
+    hy[0] = f2fma2(make_float2(ya.y, ya.z), f2add(y01, y23));
+    hy[1] = f2fma2(make_float2(ya.w, yb.x), f2add(y23, yb));
+    ex = j == 0 ? la.y - xa.y : xb.x + lb.x;
+    ey = j == 0 ? ya.y : yb.x;
 }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {      // p 16-byte aligned
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -710,26 +710,27 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         const int gxe = j == 0 ? x0 - 1 : x0 + T2_TW;   // image column of the ring output (j = 0 / 3 only)
                         if (warp < 8) {
                             // output row kk = 0 / 1 reads plane rows kk .. kk+2: stream the 4 rows through the accumulators
-                            float o0[4], o1[4], e0, e1;
+                            float2 p0[2], p1[2];          // the two output rows, as column pairs (0,1), (2,3)
+                            float e0, e1;
                             {
-                                float hx[4], hy[4], ex, ey;
+                                float2 hx[2], hy[2];
+                                float ex, ey;
                                 tb_hrow(X, C * TB_PP, j, hx, hy, ex, ey);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) o0[i] = hx[i] + hy[i];
+                                p0[0] = f2add(hx[0], hy[0]); p0[1] = f2add(hx[1], hy[1]);
                                 e0 = ex + ey;
                                 tb_hrow(X + TB_PS, C * TB_PP, j, hx, hy, ex, ey);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) { o0[i] = fmaf(2.0f, hx[i], o0[i]); o1[i] = hx[i] + hy[i]; }
+                                p0[0] = f2fma2(hx[0], p0[0]); p0[1] = f2fma2(hx[1], p0[1]);
+                                p1[0] = f2add(hx[0], hy[0]); p1[1] = f2add(hx[1], hy[1]);
                                 e0 = fmaf(2.0f, ex, e0); e1 = ex + ey;
                                 tb_hrow(X + 2 * TB_PS, C * TB_PP, j, hx, hy, ex, ey);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) { o0[i] += hx[i] - hy[i]; o1[i] = fmaf(2.0f, hx[i], o1[i]); }
+                                p0[0] = f2add(p0[0], f2sub(hx[0], hy[0])); p0[1] = f2add(p0[1], f2sub(hx[1], hy[1]));
+                                p1[0] = f2fma2(hx[0], p1[0]); p1[1] = f2fma2(hx[1], p1[1]);
                                 e0 += ex - ey; e1 = fmaf(2.0f, ex, e1);
                                 tb_hrow(X + 3 * TB_PS, C * TB_PP, j, hx, hy, ex, ey);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) o1[i] += hx[i] - hy[i];
+                                p1[0] = f2add(p1[0], f2sub(hx[0], hy[0])); p1[1] = f2add(p1[1], f2sub(hx[1], hy[1]));
                                 e1 += ex - ey;
                             }
+                            const float o0[4] = {p0[0].x, p0[0].y, p0[1].x, p0[1].y}, o1[4] = {p1[0].x, p1[0].y, p1[1].x, p1[1].y};
                             const float* ctr = sCtr + (c * T2_TH + row0) * T2_TW + 4 * j;
 #pragma unroll
                             for (int kk = 0; kk < 2; ++kk) {
@@ -760,10 +761,14 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                             }
                         } else {
                             // ring row 0 sees only cell row 0 (taps a = 2), ring row 9 only cell row 7 (taps a = 0)
-                            float hx[4], hy[4], ex, ey, out[4];
+                            float2 hx[2], hy[2];
+                            float ex, ey, out[4];
                             tb_hrow(X, C * TB_PP, j, hx, hy, ex, ey);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) out[i] = side ? hx[i] + hy[i] : hx[i] - hy[i];
+                            {
+                                const float2 a0 = side ? f2add(hx[0], hy[0]) : f2sub(hx[0], hy[0]);
+                                const float2 a1 = side ? f2add(hx[1], hy[1]) : f2sub(hx[1], hy[1]);
+                                out[0] = a0.x; out[1] = a0.y; out[2] = a1.x; out[3] = a1.y;
+                            }
                             const float eo = side ? ex + ey : ex - ey;
                             const int gy = side ? y0 + T2_TH : y0 - 1;
                             if (!ragged && gy >= 0 && gy < H) {                // ring row inside the image: only the corners may fold
