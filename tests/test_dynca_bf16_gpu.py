@@ -226,7 +226,7 @@ def test_tc2_c5_frame_properties():
                          ids=lambda c: "B%d_C%d_fc%d_%dx%d_T%d_%s_s%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], len(c[7]), c[8]))
 def test_tc2_operand_history_matches_recompute(case, monkeypatch):
     """The BPTT that loads the perception operands the forward recorded (nca_b200.h: op_hist) and the BPTT that recomputes
-    the perception from the state history see bit-identical operands: gradients agree to fp32 summation order."""
+    the perception from the state history see bit-identical operands: gradients agree to the run-to-run noise of the BPTT."""
     import ctypes as Ct
     B, C, fc, H, W, T, pad, scales, cond = case
     g = torch.Generator().manual_seed(5)
@@ -253,5 +253,10 @@ def test_tc2_operand_history_matches_recompute(case, monkeypatch):
         (fg * cf).sum().backward()
         grads.append([fg.detach().cpu()] + [p.grad.cpu() for p in pg])
     assert torch.equal(grads[0][0], grads[1][0])                          # the forward is the same kernel either way
+    # Not bit-equal even between two runs of the SAME mode: the state gradient is accumulated with red.add (nca_b200.h), so
+    # cells that receive ring contributions from several tiles differ in the last fp32 bit from run to run, and once in a
+    # while such a value sits on a bf16 rounding boundary of the next step's g_y operand - one operand then moves by a bf16
+    # ulp and a 9x9 neighbourhood of dL/dx_0 by ~3e-4 of the maximum.  Bound the norm tightly and the maximum loosely.
     for a, b in zip(grads[0][1:], grads[1][1:]):
-        assert rel_err(a, b) < 2e-5
+        assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-4
+        assert rel_err(a, b) < 5e-3

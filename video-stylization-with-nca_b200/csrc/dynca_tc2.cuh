@@ -121,24 +121,31 @@ __device__ __forceinline__ uint32_t bf16x2_nz_mask(uint32_t h) {
 // perception of 4 vertically adjacent cells (rows r0 .. r0+3 of the tile) of one channel; col = stage column of the
 // left neighbour.  Separable: s = [1 2 1]^T, d = [-1 0 1]^T over rows.
 __device__ __forceinline__ void t2_percept4(const float* __restrict__ ch, int r0, int col, float id[4], float sx[4], float sy[4], float lp[4]) {
-    float s[3][4], d[3][4];
+    // rows k = 0..3 as the pairs (0,1), (2,3) on packed fp32 (same operations and order as the scalar form, so bit-identical)
+    float2 s[3][2], d[3][2], idp[2];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         float v[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) v[k] = ch[(r0 + k) * T2_XS + T2_XO + col + j];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            s[j][k] = fmaf(2.0f, v[k + 1], v[k] + v[k + 2]);
-            d[j][k] = v[k + 2] - v[k];
-            if (j == 1) id[k] = v[k + 1];
-        }
+        const float2 v01 = make_float2(v[0], v[1]), v23 = make_float2(v[2], v[3]), v45 = make_float2(v[4], v[5]);
+        const float2 v12 = make_float2(v[1], v[2]), v34 = make_float2(v[3], v[4]);
+        s[j][0] = f2fma2(v12, f2add(v01, v23));
+        s[j][1] = f2fma2(v34, f2add(v23, v45));
+        d[j][0] = f2sub(v23, v01);
+        d[j][1] = f2sub(v45, v23);
+        if (j == 1) { idp[0] = v12; idp[1] = v34; }
     }
+    const float2 m16 = make_float2(-16.0f, -16.0f);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        sx[k] = s[2][k] - s[0][k];
-        sy[k] = fmaf(2.0f, d[1][k], d[0][k] + d[2][k]);
-        lp[k] = fmaf(-16.0f, id[k], fmaf(2.0f, s[1][k], s[0][k] + s[2][k]));
+    for (int h = 0; h < 2; ++h) {
+        const float2 sxp = f2sub(s[2][h], s[0][h]);
+        const float2 syp = f2fma2(d[1][h], f2add(d[0][h], d[2][h]));
+        const float2 lpp = f2fma(m16, idp[h], f2fma2(s[1][h], f2add(s[0][h], s[2][h])));
+        id[2 * h] = idp[h].x; id[2 * h + 1] = idp[h].y;
+        sx[2 * h] = sxp.x; sx[2 * h + 1] = sxp.y;
+        sy[2 * h] = syp.x; sy[2 * h + 1] = syp.y;
+        lp[2 * h] = lpp.x; lp[2 * h + 1] = lpp.y;
     }
 }
 // same for 3 vertically adjacent coarse cells (coarse stage stride T2_CS)
@@ -246,7 +253,9 @@ static inline cudaError_t t2_launch(void (*kernel)(KArgs...), int grid, int bloc
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    static int no_pdl = -1;                      // NCA_NO_PDL=1: plain stream order (debugging)
+    if (no_pdl < 0) { const char* e = getenv("NCA_NO_PDL"); no_pdl = (e && e[0] == '1') ? 1 : 0; }
+    cfg.attrs = at; cfg.numAttrs = (pdl && !no_pdl) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
