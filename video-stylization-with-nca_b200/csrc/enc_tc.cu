@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(EB_NTHREADS, 1) enc_bwd_tc_kernel(const __grid
             bar_sync_n(1, EB_NCOMP);
             // ---- learned depthwise 3x3 -> A1 ----
             {
-                const int hc = lane >> 4, pxx = lane & 15;
+                const int hc = lane & 1, pxx = lane >> 1;      // 8-byte stores of a half warp = 128 contiguous bytes
                 for (int item = warp; item < 2 * g.npairs; item += 16) {
                     const int cp = item >> 1, vb = item & 1, c = 2 * cp + hc;
                     float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -880,11 +880,8 @@ __global__ void __launch_bounds__(EB_NTHREADS, 1) enc_bwd_tc_kernel(const __grid
                     const uint32_t hw[4] = {hb.x, hb.y, hb.z, hb.w};
                     uint32_t ow[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {      // relu outputs are >= 0: positive <=> bits != 0
-                        const float lo = (hw[k] & 0xffffu) ? __uint_as_float(v[qq * 8 + 2 * k]) : 0.0f;
-                        const float hi = (hw[k] >> 16) ? __uint_as_float(v[qq * 8 + 2 * k + 1]) : 0.0f;
-                        ow[k] = pack_bf16(lo, hi);
-                    }
+                    for (int k = 0; k < 4; ++k)        // relu outputs are >= 0: positive <=> non-zero (one HSET2 + LOP3 per pair)
+                        ow[k] = pack_bf16(__uint_as_float(v[qq * 8 + 2 * k]), __uint_as_float(v[qq * 8 + 2 * k + 1])) & bf16x2_nz_mask(hw[k]);
                     *reinterpret_cast<uint4*>(sGa2 + (uint32_t)(2 * qtr + qq) * 2048u + row_off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
             }
@@ -901,11 +898,8 @@ __global__ void __launch_bounds__(EB_NTHREADS, 1) enc_bwd_tc_kernel(const __grid
                     const uint32_t hw[4] = {hb.x, hb.y, hb.z, hb.w};
                     uint32_t ow[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float lo = (hw[k] & 0xffffu) ? __uint_as_float(v[qq * 8 + 2 * k]) : 0.0f;
-                        const float hi = (hw[k] >> 16) ? __uint_as_float(v[qq * 8 + 2 * k + 1]) : 0.0f;
-                        ow[k] = pack_bf16(lo, hi);
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        ow[k] = pack_bf16(__uint_as_float(v[qq * 8 + 2 * k]), __uint_as_float(v[qq * 8 + 2 * k + 1])) & bf16x2_nz_mask(hw[k]);
                     *reinterpret_cast<uint4*>(sGa1 + (uint32_t)(2 * qtr + qq) * 2048u + row_off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
             }
