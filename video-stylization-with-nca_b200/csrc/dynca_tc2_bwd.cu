@@ -67,7 +67,10 @@ struct TBSmem {
 // A1 / Zc / Gy are double buffered over tiles (the next tile's operands are produced while the gradient MMAs of the
 // current tile run); DcB shares its storage with GaU (DcB is dead once D1 is complete, GaU is written after that); the
 // fp32 planes overlay H | Ga (dead once the gradient MMAs are complete), the coarse planes reuse the fine planes.
-__host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16Geom& bg) {
+// With an operand history (oph) nothing is staged in x / xc: with two scales that space (grown to 30 KB) holds the coarse planes
+// instead, which then have a life of their own - their zero pads are written once per launch, and the D7 scatter runs on two
+// otherwise idle warps during the fine transposed stencil instead of in three barrier-separated phases after it.
+__host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16Geom& bg, bool oph) {
     TBSmem s;
     const uint32_t C = (uint32_t)g.C;
     uint32_t o = TB_HDR;
@@ -75,9 +78,10 @@ __host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16G
     s.b2d = o; o += (uint32_t)(g.fc / 8) * 256u;
     s.u = o; o += g.ns == 2 ? 16384u : 0u;
     o = (o + 127u) & ~127u;
-    s.x = o; o += C * T2_XR * T2_XS * 4u;
+    const uint32_t own_cp = (oph && g.ns == 2) ? 3u * C * TB_CPP * 4u + C * T2_QH * T2_QW * 4u : 0u;      // coarse planes + centre terms
+    s.x = o; o += own_cp ? 0u : C * T2_XR * T2_XS * 4u;
     o = (o + 127u) & ~127u;
-    s.xc = o; o += g.ns == 2 ? C * T2_CR * T2_CS * 4u : 0u;
+    s.xc = o; o += own_cp ? own_cp : (g.ns == 2 ? C * T2_CR * T2_CS * 4u : 0u);
     o = (o + 127u) & ~127u;
     s.gn = o; o += C * T2_TH * T2_TW * 4u;
     o = (o + 127u) & ~127u;
@@ -97,8 +101,12 @@ __host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16G
     s.ctr = p; p += C * T2_TH * T2_TW * 4u;
     const uint32_t pf = p;
     p = s.h;
-    s.cpx = p; p += g.ns == 2 ? 3u * C * TB_CPP * 4u : 0u;
-    s.cctr = p; p += g.ns == 2 ? C * T2_QH * T2_QW * 4u : 0u;
+    if (own_cp) {
+        s.cpx = s.xc; s.cctr = s.xc + 3u * C * TB_CPP * 4u;
+    } else {
+        s.cpx = p; p += g.ns == 2 ? 3u * C * TB_CPP * 4u : 0u;
+        s.cctr = p; p += g.ns == 2 ? C * T2_QH * T2_QW * 4u : 0u;
+    }
     const uint32_t pm = pf > p ? pf : p;
     s.total = (o > pm ? o : pm) + 1024u;                 // + slack for the aliasing reads of the last buffer
     return s;
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     extern __shared__ __align__(1024) uint8_t smem[];
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
-    const TBSmem L = tb_smem(g, bg);
+    const TBSmem L = tb_smem(g, bg, a.op_in != nullptr);
 #ifdef NCA_T2_TIMING
     if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) a.tdbg[128] = clock64();
 #endif
@@ -237,6 +245,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             reinterpret_cast<uint4*>(sU)[i] = __ldg(reinterpret_cast<const uint4*>(a.U) + i);
     // everything an MMA may read before the tile loop writes it must be finite: clear the dynamic area once
     for (uint32_t i = L.zc / 16 + tid; i < L.total / 16; i += TB_NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (NS == 2 && a.op_in != nullptr)      // persistent coarse planes: the zero pads are written here, once
+        for (uint32_t i = L.cpx / 16 + tid; i < (L.cctr + (uint32_t)g.C * T2_QH * T2_QW * 4u) / 16; i += TB_NTHREADS)
+            reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         mbar_init(barM1, 1); mbar_init(barM2, 1); mbar_init(barM3, 1); mbar_init(barM4, 1); mbar_init(barT, 1);
         mbar_init(barA, TB_NCOMP); mbar_init(barG, TB_NCOMP); mbar_init(barB, TB_NCOMP);
@@ -686,7 +697,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         }
                     }
                 }
-                if (NS == 1) { tc_fence_before(); mbar_arrive(barE); }      // D6 read: D3's columns are free again
+                // D6 read: D3's columns are free again as far as this thread is concerned (with own coarse planes D7 is read by
+                // warps 12 / 13 alone, during the fine transposed stencil)
+                if (NS == 1 || (ophist && warp != 12 && warp != 13)) { tc_fence_before(); mbar_arrive(barE); }
             }
             TB_STAMP(7);
             bar_sync_n(1, TB_NCOMP);
@@ -698,6 +711,34 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             //      one vector reduction per row. ----
             {
                 const bool ragged = y0 + T2_TH > H || x0 + T2_TW > W;
+                if (NS == 2 && ophist && (warp == 12 || warp == 13)) {
+                    // ---- D7 (coarse footprint rows 0..59, all N6 columns) -> the persistent coarse planes, by the two warps of
+                    //      lane quarters 0 / 1 that have nothing to do in this phase ----
+                    mbar_wait(barM4, phM4);                    // D5 coarse part, D7 complete
+                    phM4 ^= 1u;
+                    tc_fence_after();
+                    const int qy = r / T2_QW, qx = r % T2_QW;
+#pragma unroll 1
+                    for (int q4 = 0; 16 * q4 < N6; ++q4) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_lane + TB_D3 + 64u + 16u * (uint32_t)q4, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int c = 4 * q4 + i;
+                            if (c < C && r < T2_QH * T2_QW) {
+                                const int o = (c * TB_CPR + qy + 2) * TB_CPS + qx + 2;
+                                const float lp = __uint_as_float(v[4 * i + 3]);
+                                sCPX[o] = __uint_as_float(v[4 * i + 1]);
+                                sCPX[C * TB_CPP + o] = __uint_as_float(v[4 * i + 2]);
+                                sCPX[2 * C * TB_CPP + o] = lp;
+                                sCCtr[(c * T2_QH + qy) * T2_QW + qx] = fmaf(-16.0f, lp, __uint_as_float(v[4 * i + 0]));
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(barE);                         // D7 read: D3's columns are free again
+                }
                 if (warp < 12) {
                     const int j = lane & 3;
                     int c, row0, side = 0;
@@ -797,35 +838,39 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             TB_STAMP(9);
             if (NS == 2) {
-                mbar_wait(barM4, phM4);                        // D5 coarse part, D7 complete
-                phM4 ^= 1u;
-                tc_fence_after();
-                bar_sync_n(1, TB_NCOMP);                       // every P5 read of the fine planes is done: reuse them
+                if (!(ophist && (warp == 12 || warp == 13))) {
+                    mbar_wait(barM4, phM4);                    // D5 coarse part, D7 complete (GaU in shared memory is free)
+                    phM4 ^= 1u;
+                    tc_fence_after();
+                }
+                bar_sync_n(1, TB_NCOMP);                       // every P5 read of the fine planes is done; own coarse planes: written
                 TB_STAMP(10);
-                // ---- D7 -> coarse planes (zero padded [10][14], footprint cell (qy,qx) at [qy+2][qx+2]) ----
-                for (int i = tid; i < 3 * C * TB_CPP / 2; i += TB_NCOMP) reinterpret_cast<float2*>(sCPX)[i] = make_float2(0.f, 0.f);
-                bar_sync_n(1, TB_NCOMP);
-                if ((warp & 3) < 2 && 16 * qtr < N6) {      // warp-uniform: the TMEM load is .sync.aligned
-                    uint32_t v[16];
-                    const int qy = r / T2_QW, qx = r % T2_QW;
-                    tmem_ld16(tmem_lane + TB_D3 + 64u + 16u * (uint32_t)qtr, v);
-                    tmem_ld_wait();
+                if (!ophist) {
+                    // ---- D7 -> coarse planes (zero padded [10][14], footprint cell (qy,qx) at [qy+2][qx+2]), over the fine planes ----
+                    for (int i = tid; i < 3 * C * TB_CPP / 2; i += TB_NCOMP) reinterpret_cast<float2*>(sCPX)[i] = make_float2(0.f, 0.f);
+                    bar_sync_n(1, TB_NCOMP);
+                    if ((warp & 3) < 2 && 16 * qtr < N6) {      // warp-uniform: the TMEM load is .sync.aligned
+                        uint32_t v[16];
+                        const int qy = r / T2_QW, qx = r % T2_QW;
+                        tmem_ld16(tmem_lane + TB_D3 + 64u + 16u * (uint32_t)qtr, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int c = 4 * qtr + i;
-                        if (c < C && r < T2_QH * T2_QW) {
-                            const int o = (c * TB_CPR + qy + 2) * TB_CPS + qx + 2;
-                            const float lp = __uint_as_float(v[4 * i + 3]);
-                            sCPX[o] = __uint_as_float(v[4 * i + 1]);
-                            sCPX[C * TB_CPP + o] = __uint_as_float(v[4 * i + 2]);
-                            sCPX[2 * C * TB_CPP + o] = lp;
-                            sCCtr[(c * T2_QH + qy) * T2_QW + qx] = fmaf(-16.0f, lp, __uint_as_float(v[4 * i + 0]));
+                        for (int i = 0; i < 4; ++i) {
+                            const int c = 4 * qtr + i;
+                            if (c < C && r < T2_QH * T2_QW) {
+                                const int o = (c * TB_CPR + qy + 2) * TB_CPS + qx + 2;
+                                const float lp = __uint_as_float(v[4 * i + 3]);
+                                sCPX[o] = __uint_as_float(v[4 * i + 1]);
+                                sCPX[C * TB_CPP + o] = __uint_as_float(v[4 * i + 2]);
+                                sCPX[2 * C * TB_CPP + o] = lp;
+                                sCCtr[(c * T2_QH + qy) * T2_QW + qx] = fmaf(-16.0f, lp, __uint_as_float(v[4 * i + 0]));
+                            }
                         }
                     }
+                    tc_fence_before();
+                    mbar_arrive(barE);                             // D7 read: D3's columns are free again
+                    bar_sync_n(1, TB_NCOMP);
                 }
-                tc_fence_before();
-                mbar_arrive(barE);                             // D7 read: D3's columns are free again
-                bar_sync_n(1, TB_NCOMP);
                 const int Hc = H >> 1, Wc = W >> 1;
                 const int cy0 = (y0 >> 1) - 1, cx0 = (x0 >> 1) - 1;          // coarse coordinates of footprint cell (0,0)
                 if (border) {
@@ -980,7 +1025,7 @@ bool dynca_tc2_bwd_supported(const DyncaGeom& g) {
     Bf16Geom bg;
     if (!dynca_tc2_supported(g)) return false;
     if (dynca_bf16_geom(g, &bg)) return false;
-    return tb_smem(g, bg).total <= 227u * 1024u;
+    return tb_smem(g, bg, false).total <= 227u * 1024u && tb_smem(g, bg, true).total <= 227u * 1024u;
 }
 
 // operand images: [forward block of dynca_tc2_prep_weights (B1 | B2 | b2 | U)] then B2d
@@ -1035,7 +1080,7 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     const bool timing = getenv("NCA_T2_TDBG") != nullptr;
     if (timing && !tdbg) cudaMalloc(&tdbg, 160 * sizeof(long long));
     a.tdbg = timing ? tdbg : nullptr;
-    const size_t smem = tb_smem(g, a.bg).total;
+    const size_t smem = tb_smem(g, a.bg, op_in != nullptr).total;
     int grid = t2_num_sms();
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
     const CUtensorMap* tx = (const CUtensorMap*)xm->x;
