@@ -574,7 +574,46 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             mbar_arrive(barB);
         };
 
+        // ---- P6: transposed coarse perception of one tile (coordinates b_, y0_, x0_) -> red.add into the coarse gradient buffer.
+        //      warp = (channel pair, 4-row block), lane = (channel of the pair, column of the 8 x 12 coarse ring):
+        //      coarse channel planes are 140 floats = 12 banks apart -> conflict-free reads.  With an operand history the coarse
+        //      planes have their own storage, and the phase is deferred into the next tile's wait for its gradient MMAs. ----
+        auto p6 = [&](int b_, int y0_, int x0_) {
+            const int Hc = H >> 1, Wc = W >> 1;
+            const int cy0 = (y0_ >> 1) - 1, cx0 = (x0_ >> 1) - 1;
+            const bool border_ = y0_ == 0 || x0_ == 0 || y0_ + T2_TH >= H || x0_ + T2_TW >= W || (y0_ + T2_TH + 4 > H || x0_ + T2_TW + 4 > W);
+            const int cp = warp >> 1, vb = warp & 1, hc = lane / 12, ox = lane % 12;
+            const int c = 2 * cp + hc;
+            if (c < C && lane < 24) {
+                const float* X = sCPX + c * TB_CPP;
+                const float* Y = X + C * TB_CPP;
+                const float* Lp = Y + C * TB_CPP;
+                float out[4];
+                tb_stencil_t<4, TB_CPS>(X, Y, Lp, 4 * vb, ox, out);
+                float* gcb = a.gc_out + ((size_t)b_ * C + c) * (plane >> 2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int oy = 4 * vb + k;
+                    if (oy >= 1 && oy <= T2_QH && ox >= 1 && ox <= T2_QW) out[k] += sCCtr[(c * T2_QH + oy - 1) * T2_QW + ox - 1];
+                }
+                const int gxc = cx0 - 1 + ox, gyc = cy0 - 1 + 4 * vb;
+                if (!border_ || (gxc >= 0 && gxc < Wc && gyc >= 0 && gyc + 4 <= Hc)) {
+                    float* p = gcb + (size_t)(cy0 - 1 + 4 * vb) * Wc + cx0 - 1 + ox;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { atomicAdd(p, out[k]); p += Wc; }
+                } else {
+                    const int tx = tb_fold(cx0 - 1 + ox, Wc, g.pad);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int ty = tb_fold(cy0 - 1 + 4 * vb + k, Hc, g.pad);
+                        if (ty >= 0 && tx >= 0) atomicAdd(gcb + (size_t)ty * Wc + tx, out[k]);
+                    }
+                }
+            }
+        };
+
         float gn[4] = {0.f, 0.f, 0.f, 0.f}, gn_next[4] = {0.f, 0.f, 0.f, 0.f};
+        int pend_b = -1, pend_y0 = 0, pend_x0 = 0;      // tile whose coarse transposed stencil is still to do (operand history)
         if ((int)blockIdx.x < n_tiles) tables(blockIdx.x, 0);
         bar_sync_n(1, TB_NCOMP);
         int nb = 0, ny0 = 0, nx0 = 0;      // coordinates of the tile whose operands are produced ahead
@@ -641,6 +680,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             // ---- software pipeline, part 2: rest of the NEXT tile's operands while the gradient MMAs of this one run ----
             if (next < n_tiles) p1b(next, nb, ny0, nx0, iter + 1, gn_next);
             TB_STAMP(5);
+            if (NS == 2 && pend_b >= 0) { p6(pend_b, pend_y0, pend_x0); pend_b = -1; }      // previous tile's coarse stencil, under the MMAs
             mbar_wait(barM3, phM3);                            // D6, GaU, D4, D5 (fine) complete; H | Ga are free
             phM3 ^= 1u;
             tc_fence_after();
@@ -909,39 +949,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 }
                 if (next < n_tiles) dc_roundtrip();           // next tile's DcB: its U . DcB runs under the coarse stencil below
                 TB_STAMP(11);
-                // ---- P6: transposed coarse perception -> red.add into the coarse gradient buffer.
-                //      warp = (channel pair, 4-row block), lane = (channel of the pair, column of the 8 x 12 coarse ring):
-                //      coarse channel planes are 140 floats = 12 banks apart -> conflict-free reads ----
-                {
-                    const int cp = warp >> 1, vb = warp & 1, hc = lane / 12, ox = lane % 12;
-                    const int c = 2 * cp + hc;
-                    if (c < C && lane < 24) {
-                        const float* X = sCPX + c * TB_CPP;
-                        const float* Y = X + C * TB_CPP;
-                        const float* Lp = Y + C * TB_CPP;
-                        float out[4];
-                        tb_stencil_t<4, TB_CPS>(X, Y, Lp, 4 * vb, ox, out);
-                        float* gcb = a.gc_out + ((size_t)b * C + c) * (plane >> 2);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int oy = 4 * vb + k;
-                            if (oy >= 1 && oy <= T2_QH && ox >= 1 && ox <= T2_QW) out[k] += sCCtr[(c * T2_QH + oy - 1) * T2_QW + ox - 1];
-                        }
-                        const int gxc = cx0 - 1 + ox, gyc = cy0 - 1 + 4 * vb;
-                        if (!border || (gxc >= 0 && gxc < Wc && gyc >= 0 && gyc + 4 <= Hc)) {
-                            float* p = gcb + (size_t)(cy0 - 1 + 4 * vb) * Wc + cx0 - 1 + ox;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) { atomicAdd(p, out[k]); p += Wc; }
-                        } else {
-                            const int tx = tb_fold(cx0 - 1 + ox, Wc, g.pad);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int ty = tb_fold(cy0 - 1 + 4 * vb + k, Hc, g.pad);
-                                if (ty >= 0 && tx >= 0) atomicAdd(gcb + (size_t)ty * Wc + tx, out[k]);
-                            }
-                        }
-                    }
-                }
+                if (ophist) { pend_b = b; pend_y0 = y0; pend_x0 = x0; }      // deferred into the next tile's MMA wait
+                else p6(b, y0, x0);
             }
             TB_STAMP(12);
             bar_sync_n(1, TB_NCOMP);     // the planes overlay H | Ga, which the next tile's E1 writes
@@ -949,6 +958,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 4; ++i) gn[i] = gn_next[i];
         }
+        if (NS == 2 && pend_b >= 0) p6(pend_b, pend_y0, pend_x0);      // last tile
 #ifdef NCA_T2_TIMING
         if (a.tdbg && blockIdx.x == 0 && tid == 0) { a.tdbg[130] = clock64(); a.tdbg[132] = iter; }
 #endif
