@@ -171,7 +171,9 @@ __device__ __forceinline__ int tb_fold(int r, int n, int mode) {
     return r < 0 ? 1 : n - 2;                                         // reflect
 }
 
-template <int NS>
+// OPH = with an operand history (compile-time: the recompute paths - perception, border patches, overlaid coarse planes - are
+// then not in the kernel at all; the kernel is far larger than the instruction cache and jumps over dead regions cost fetches)
+template <int NS, bool OPH>
 __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                         const __grid_constant__ CUtensorMap tm_xc,
                                                                         const __grid_constant__ CUtensorMap tm_g,
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     extern __shared__ __align__(1024) uint8_t smem[];
     const DyncaGeom& g = a.g;
     const Bf16Geom& bg = a.bg;
-    const TBSmem L = tb_smem(g, bg, a.op_in != nullptr);
+    const TBSmem L = tb_smem(g, bg, OPH);
 #ifdef NCA_T2_TIMING
     if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) a.tdbg[128] = clock64();
 #endif
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     const int n_tiles = a.tl.n_tiles;
     const int N6 = 16 * ((bg.npairs + 1) / 2);                 // perception columns of g_z, padded to the MMA granularity
     // with an operand history the perception operands arrive by bulk copy and only the gradient tiles are staged
-    const bool ophist = a.op_in != nullptr;
+    constexpr bool ophist = OPH;
     const uint32_t stage_bytes = ophist ? (uint32_t)C * (T2_TH * T2_TW + (NS == 2 ? 32 : 0)) * 4u
                                         : (uint32_t)C * (T2_XR * T2_XS + T2_TH * T2_TW) * 4u +
                                               (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u) +
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             reinterpret_cast<uint4*>(sU)[i] = __ldg(reinterpret_cast<const uint4*>(a.U) + i);
     // everything an MMA may read before the tile loop writes it must be finite: clear the dynamic area once
     for (uint32_t i = L.zc / 16 + tid; i < L.total / 16; i += TB_NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    if (NS == 2 && a.op_in != nullptr)      // persistent coarse planes: the zero pads are written here, once
+    if (NS == 2 && OPH)      // persistent coarse planes: the zero pads are written here, once
         for (uint32_t i = L.cpx / 16 + tid; i < (L.cctr + (uint32_t)g.C * T2_QH * T2_QW * 4u) / 16; i += TB_NTHREADS)
             reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -778,6 +780,35 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
                     tc_fence_before();
                     mbar_arrive(barE);                         // D7 read: D3's columns are free again
+                    if (next < n_tiles) {
+                        // ---- and the NEXT tile's Dc (rows 0..63, all hidden columns) -> bf16 -> DcB: its U . DcB then runs under
+                        //      the rest of this phase, and D1 is complete when the next tile starts ----
+                        mbar_wait(barM1, phM1);
+                        phM1 ^= 1u;
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int q4 = 0; 32 * q4 < fc; ++q4) {
+                            uint32_t v[32];
+                            tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)q4, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) {
+                                uint4 o;
+                                o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
+                                o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
+                                o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
+                                o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
+                                *reinterpret_cast<uint4*>(sDcB + (uint32_t)(4 * q4 + qq) * 1024u + row_off) = o;
+                            }
+                        }
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(barB);
+                    }
+                } else if (NS == 2 && ophist && next < n_tiles) {
+                    phM1 ^= 1u;                                // this thread skips the Dc wait of the next tile
+                    tc_fence_before();
+                    mbar_arrive(barB);                         // (nothing to contribute to DcB)
                 }
                 if (warp < 12) {
                     const int j = lane & 3;
@@ -947,7 +978,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         bar_sync_n(1, TB_NCOMP);
                     }
                 }
-                if (next < n_tiles) dc_roundtrip();           // next tile's DcB: its U . DcB runs under the coarse stencil below
+                if (!ophist && next < n_tiles) dc_roundtrip();      // next tile's DcB: its U . DcB runs under the coarse stencil below
                 TB_STAMP(11);
                 if (ophist) { pend_b = b; pend_y0 = y0; pend_x0 = x0; }      // deferred into the next tile's MMA wait
                 else p6(b, y0, x0);
@@ -1098,13 +1129,13 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     const CUtensorMap* tg = (const CUtensorMap*)gm->x;
     const CUtensorMap* tgc = (const CUtensorMap*)gm->xc;
     const CUtensorMap* tcn = (const CUtensorMap*)xm->cond;
-    if (g.ns == 2) {
-        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<2>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a));
-    } else {
-        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<1>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a));
-    }
+#define TB_LAUNCH(NS_, OPH_)                                                                                                  \
+    do {                                                                                                                      \
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<NS_, OPH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<NS_, OPH_>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a)); \
+    } while (0)
+    if (g.ns == 2) { if (op_in) TB_LAUNCH(2, true); else TB_LAUNCH(2, false); }
+    else { if (op_in) TB_LAUNCH(1, true); else TB_LAUNCH(1, false); }
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps
         long long h[160];
