@@ -256,7 +256,7 @@ def main():
     else:
         roof = {"bound": "hbm", "achieved": ach_gb, "peak": hbm, "unit": "GB/s", "frac": ach_gb / hbm}
     variant = Fn.dynca_kernel_variant(cfg, B, H, W, backward=True)
-    kname = {0: "dynca_bwd_f32_kernel<2>", 1: "dynca_bwd_bf16_kernel<2>", 2: "dynca_bwd_tc2_kernel<2>"}[variant]
+    kname = {0: "dynca_bwd_f32_kernel<2>", 1: "dynca_bwd_bf16_kernel<2>", 2: "dynca_bwd_tc2_kernel<2, true>"}[variant]      # <two scales, operand history>
     traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
