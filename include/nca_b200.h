@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NCA_B200_ABI_VERSION 4
+#define NCA_B200_ABI_VERSION 5
 
 enum { NCA_OK = 0, NCA_ERR_ARG = -1, NCA_ERR_UNSUPPORTED = -2, NCA_ERR_CUDA = -3, NCA_ERR_WORKSPACE = -4 };
 
@@ -171,6 +171,59 @@ int nca_enc_backward(const NcaEncDesc* d, const NcaEncWeights* w, const float* g
                      const float* g_final, float* gx0, float* g_goal, const NcaEncWeightGrads* gw,
                      void* workspace, size_t workspace_bytes, void* stream);
 size_t nca_enc_workspace_bytes(const NcaEncDesc* d, int32_t backward);
+
+/* ---- the callers either side of the step (N1 pool + optimizer, N4 overflow loss, N2 frame stream) -------- */
+
+/* Batch assembly from the sample pool — ExtraChannels/experiments.py:203-211 (ConditioneDyNCA/experiments.py:210-218):
+ *   input_states = nca_pool[batch_idx]; input_states[:1] = seed; input_states = cat((input_states, aux_gs), 1)
+ * and EncoderConditioning/conditioned_trainer.py:107-113,167 (batch[:2] = generate_seed(2)), in one pass.
+ *   pool [N,Cp,H,W]; idx device int64 [B] (pool slots; an out-of-range slot reads as zeros);
+ *   extra [B,Cx,H,W] or NULL with Cx == 0: appended as channels Cp..Cp+Cx-1 (the EC conditioning channel);
+ *   the first inject_n samples are replaced by seed_state [Cp,H,W] (NULL = zeros, seed_mode 'zeros' dynca.py:142-143);
+ *   out [B,Cp+Cx,H,W] (written). */
+int nca_pool_gather(int32_t N, int32_t Cp, int32_t H, int32_t W, const float* pool, const int64_t* idx, int32_t B,
+                    const float* extra, int32_t Cx, const float* seed_state, int32_t inject_n, float* out, void* stream);
+
+/* Pool write-back — experiments.py:259: nca_pool[batch_idx] = nca_states_after[:, :12]; conditioned_trainer.py:155-156.
+ *   states [B,C,H,W], the first Cp channels go to pool[idx[b]]; idx must not repeat (np.random.choice(replace=False),
+ *   random.sample); an out-of-range slot is skipped. */
+int nca_pool_scatter(int32_t N, int32_t Cp, int32_t H, int32_t W, float* pool, const int64_t* idx, int32_t B,
+                     const float* states, int32_t C, void* stream);
+
+/* Per-parameter gradient normalisation fused with the Adam update, ONE launch for the whole model —
+ * experiments.py:252-255 (`p.grad /= (p.grad.norm() + 1e-8)` for every parameter; `optimizer.step()`) and
+ * conditioned_trainer.py:134-137 (eps 1e-10).  torch.optim.Adam semantics (amsgrad off, weight_decay 0): exp_avg lerp,
+ * exp_avg_sq, bias corrections for the 1-based `step`, denom = sqrt(v)/sqrt(bc2) + eps, p -= lr/bc1 * m/denom.
+ *   params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors device pointers (n_tensors <= NCA_ADAM_MAX_TENSORS),
+ *   numel: HOST array of element counts; normalise == 0 skips the normalisation; the normalised gradient is written back
+ *   to grads (as the reference's in-place division does) or zeros when zero_grads != 0 (optimizer.zero_grad()).
+ *   lr is the current learning rate (MultiStepLR stays on the host: it only changes this number). */
+#define NCA_ADAM_MAX_TENSORS 16
+int nca_normalized_adam_step(int32_t n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                             float* const* exp_avg_sq, const int64_t* numel, int32_t step, float lr, float beta1, float beta2,
+                             float eps, float norm_eps, int32_t normalise, int32_t zero_grads, void* stream);
+
+/* Loss.get_overflow_loss (ExtraChannels/utils/loss/loss.py:33-36; EncoderConditioning/loss/loss.py):
+ *   loss = mean |x - clamp(x, -1, 1)| over the n elements of the final state, and in the same pass its gradient
+ *   grad_scale * sign(x) * [|x| > 1] / n written (accumulate == 0) or added (accumulate != 0) to grad_out (NULL = loss only):
+ *   the BPTT's g_final gets the overflow term without a second pass over the state.
+ *   loss_out: device float[1]; workspace: nca_overflow_workspace_bytes() bytes.  Fixed reduction order (reproducible). */
+size_t nca_overflow_workspace_bytes(void);
+int nca_overflow_loss(const float* x, size_t n, float* loss_out, float* grad_out, float grad_scale, int32_t accumulate,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Inference stream, per target frame — ExtraChannels/utils/misc/video_utils.py:72: h = cat((h, RGBToGrayscale(frame)), 1)
+ * (preprocess_texture.py:178-179: mean over the three channels) and :76: h = nca_state[:, :-1].  The conditioning channel
+ * lives in the state buffer: this writes mean_rgb(frame) into channel `ch` of state [B,C,H,W] in place, so there is no
+ * per-frame cat / strip.  frame_rgb [B,3,H,W].  (C == 1, ch == 0 gives the plain grayscale image, CD's cond_img.) */
+int nca_frame_to_cond_channel(int32_t B, int32_t C, int32_t H, int32_t W, const float* frame_rgb, float* state, int32_t ch,
+                              void* stream);
+
+/* Frame read-out — video_utils.py:78-82 + VideoWriter.add (:20-27): img = clip(scale * state[:, :3], -1, 1);
+ * img = (img + 1) / 2; uint8(clip(img, 0, 1) * 255) (truncation), channels-last.  scale = 2 (DyNCA.to_rgb, dynca.py:130-131).
+ *   state [B,C,H,W] (C >= 3) -> out_hwc uint8 [B,H,W,3]. */
+int nca_state_to_rgb8(int32_t B, int32_t C, int32_t H, int32_t W, const float* state, float scale, uint8_t* out_hwc,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,9 @@ static int check_device() {
     return NCA_OK;
 }
 #define NCA_ALIGNED16(p) ((((uintptr_t)(p)) & 15u) == 0)
+}  // extern "C"
+int nca_check_device() { return check_device(); }   // for the other translation units (nca_callers.cu)
+extern "C" {
 
 static FireMask make_mask(const NcaDyncaDesc* d, const DyncaGeom& g, const float* masks, uint64_t seed, int t) {
     FireMask m;

@@ -1,0 +1,164 @@
+"""Host mirror of the reference's inference loop: `save_video` in
+ExtraChannels/utils/misc/video_utils.py:50-82 (extra-channel flavour) and ConditioneDyNCA/utils/misc/video_utils.py:50-82
+(`cond_img=` flavour) as a frame stream.
+
+Per target frame the reference runs `torch.cat` (append the grayscale frame), `forward_nsteps`, a channel slice, a blocking
+`.cpu().numpy()` and numpy clip / scale / uint8 on the host.  Here the state lives in one persistent two-slot device buffer with
+the conditioning channel inside it (`nca_frame_to_cond_channel` rewrites it in place), the T steps go out back to back on one
+stream, `nca_state_to_rgb8` packs the frame on the device (1/4 of the bytes cross PCIe/C2C) and the device->host copy of frame i
+runs on a second stream under the rollout of frame i+1.
+"""
+import ctypes as C
+
+import torch
+
+from . import functional as Fn
+from ._lib import NCA_COND_CPE, NCA_COND_NONE, NCA_COND_TENSOR, NcaError, check, load_library
+from .functional import _need_cuda, _ptr, _stream
+
+
+def frame_to_cond_channel(state, frame_rgb, ch=-1):
+    """state[:, ch] = mean over the 3 channels of frame_rgb (RGBToGrayscale, preprocess_texture.py:178-179), in place."""
+    _need_cuda(state, frame_rgb)
+    if not (state.is_contiguous() and frame_rgb.is_contiguous()):
+        raise NcaError("frame_to_cond_channel needs contiguous tensors")
+    B, Cc, H, W = state.shape
+    if tuple(frame_rgb.shape) != (B, 3, H, W):
+        raise NcaError(f"frame must be [{B},3,{H},{W}], got {tuple(frame_rgb.shape)}")
+    ch = ch + Cc if ch < 0 else ch
+    with torch.cuda.device(state.device):
+        check(load_library().nca_frame_to_cond_channel(B, Cc, H, W, _ptr(frame_rgb), _ptr(state), ch, _stream()))
+    return state
+
+
+def rgb_to_grayscale(frame_rgb):
+    """RGBToGrayscale (preprocess_texture.py:178-179): [B,3,H,W] -> [B,1,H,W]."""
+    B, _, H, W = frame_rgb.shape
+    out = torch.empty(B, 1, H, W, device=frame_rgb.device, dtype=torch.float32)
+    return frame_to_cond_channel(out, frame_rgb.contiguous(), 0)
+
+
+def state_to_rgb8(state, scale=2.0, out=None):
+    """uint8 [B,H,W,3] frame of a state: clip(scale * state[:, :3], -1, 1) -> (v + 1) / 2 -> uint8(clip(v, 0, 1) * 255)
+    (dynca.py:130-131, video_utils.py:78-82,20-27)."""
+    _need_cuda(state)
+    if not state.is_contiguous():
+        raise NcaError("state_to_rgb8 needs a contiguous state")
+    B, Cc, H, W = state.shape
+    if out is None:
+        out = torch.empty(B, H, W, 3, device=state.device, dtype=torch.uint8)
+    with torch.cuda.device(state.device):
+        check(load_library().nca_state_to_rgb8(B, Cc, H, W, _ptr(state), float(scale), _ptr(out), _stream()))
+    return out
+
+
+class FrameStylizer:
+    """The loop of `save_video` (video_utils.py:65-82) without the file writer.
+
+    model: a drop-in DyNCA (EC flavour: the frame's grayscale is the last state channel; CD flavour with
+    conditioning='edges': it is passed as `cond_img`; any other model is run unconditioned).  `push(frame)` advances the
+    automaton `step_n` steps on that frame and returns the uint8 image on the device; `run(frames)` does it for a whole clip
+    and returns a pinned host array, copies overlapped with compute."""
+
+    def __init__(self, model, size, step_n=8, steps_per_frame=1, batch=1, update_rate=0.5, seed=None):
+        self.model, self.step_n, self.steps_per_frame, self.rate = model, int(step_n), int(steps_per_frame), float(update_rate)
+        H, W = (size, size) if isinstance(size, int) else size
+        self.B, self.H, self.W = batch, H, W
+        self.dev = model.w1.weight.device
+        self.flavour = "cd" if hasattr(model, "conditioning") else "ec"
+        self.C = model.c_in
+        self.seed = Fn.new_seed() if seed is None else int(seed)
+        self.t0 = 0
+        self.slots = torch.zeros(2, batch, self.C, H, W, device=self.dev, dtype=torch.float32)
+        self.cur = 0
+        self.gray = torch.empty(batch, 1, H, W, device=self.dev) if self.flavour == "cd" and model.conditioning == 'edges' else None
+        self.reset()
+
+    def reset(self):
+        # h = nca_model.seed(1, size=...) (video_utils.py:66); the EC flavour seeds c_in - 1 channels, the last one is the frame
+        h = self.model.seed(self.B, size=(self.W, self.H))
+        self.slots.zero_()
+        self.slots[0, :, :h.shape[1]].copy_(h)
+        self.cur, self.t0 = 0, 0
+
+    @property
+    def state(self):
+        return self.slots[self.cur]
+
+    def _cfg_cond(self, frame):
+        m = self.model
+        if self.flavour == "ec":
+            frame_to_cond_channel(self.slots[self.cur], frame, self.C - 1)       # video_utils.py:72
+            kind, cc = m._kind()
+            return m._cfg(kind, cc), None
+        if m.conditioning == 'edges':
+            frame_to_cond_channel(self.gray, frame, 0)                           # CD video_utils.py:72: cond_img = gray frame
+            return m._cfg(NCA_COND_TENSOR, 3), m.cond_layer(self.gray)
+        return m._cfg(NCA_COND_CPE if m.conditioning == 'pos_emb' else NCA_COND_NONE, 2 if m.conditioning == 'pos_emb' else 0), None
+
+    @torch.no_grad()
+    def push(self, frame_rgb, out=None):
+        """frame_rgb [B,3,H,W] float in [-1,1] on the device -> uint8 [B,H,W,3] after `step_n` steps."""
+        if self.cur == 1:                      # an odd step_n left the state in slot 1: the C ABI reads its input from slot 0
+            self.slots[0].copy_(self.slots[1])
+            self.cur = 0
+        cfg, cond = self._cfg_cond(frame_rgb.contiguous())
+        m = self.model
+        lib = load_library()
+        d = cfg.desc(self.B, self.H, self.W, self.rate, False)
+        w = [t.detach() for t in m._w()]
+        with torch.cuda.device(self.dev):
+            nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
+            if getattr(self, "_ws", None) is None or self._ws.numel() < nbytes:
+                self._ws = torch.empty(max(nbytes, 16), device=self.dev, dtype=torch.uint8)
+            wst = Fn._weights_struct(*w)
+            check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), None, C.c_uint64(self.seed), self.t0, self.step_n,
+                                        0, _ptr(self.slots), None, None, _ptr(self._ws), nbytes, _stream()))
+        self.t0 += self.step_n
+        self.cur = self.step_n & 1
+        return state_to_rgb8(self.slots[self.cur], 2.0, out)
+
+    @torch.no_grad()
+    def run(self, frames):
+        """frames [F,3,H,W] (device or pinned host; one stream, batch 1) or [F,B,3,H,W] -> pinned uint8 [F*steps_per_frame,B,H,W,3]."""
+        if frames.dim() == 4:
+            frames = frames.unsqueeze(1)
+        F = frames.shape[0]
+        n_out = F * self.steps_per_frame
+        host = torch.empty(n_out, self.B, self.H, self.W, 3, dtype=torch.uint8).pin_memory()
+        dev_out = [torch.empty(self.B, self.H, self.W, 3, device=self.dev, dtype=torch.uint8) for _ in range(2)]
+        dev_in = [torch.empty(self.B, 3, self.H, self.W, device=self.dev) for _ in range(2)] if not frames.is_cuda else None
+        main, side = torch.cuda.current_stream(self.dev), torch.cuda.Stream(self.dev)
+        done = [None, None]      # D2H of the frame that used dev_out[k] has finished
+        up = [None, None]
+        if dev_in is not None:
+            with torch.cuda.stream(side):
+                dev_in[0].copy_(frames[0], non_blocking=True)
+                up[0] = torch.cuda.Event(); up[0].record(side)
+        j = 0
+        for f in range(F):
+            if dev_in is not None:
+                if f + 1 < F:
+                    free = torch.cuda.Event(); free.record(main)          # compute that read dev_in[(f+1)&1] (frame f-1) is queued before
+                    with torch.cuda.stream(side):
+                        side.wait_event(free)
+                        dev_in[(f + 1) & 1].copy_(frames[f + 1], non_blocking=True)
+                        up[(f + 1) & 1] = torch.cuda.Event(); up[(f + 1) & 1].record(side)
+                main.wait_event(up[f & 1])
+                frame = dev_in[f & 1]
+            else:
+                frame = frames[f]
+            for _ in range(self.steps_per_frame):
+                k = j & 1
+                if done[k] is not None:
+                    main.wait_event(done[k])
+                self.push(frame, dev_out[k])
+                ready = torch.cuda.Event(); ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    host[j].copy_(dev_out[k], non_blocking=True)
+                    done[k] = torch.cuda.Event(); done[k].record(side)
+                j += 1
+        main.wait_stream(side)
+        side.synchronize()
+        return host
