@@ -179,10 +179,19 @@ size_t nca_enc_workspace_bytes(const NcaEncDesc* d, int32_t backward);
  * and EncoderConditioning/conditioned_trainer.py:107-113,167 (batch[:2] = generate_seed(2)), in one pass.
  *   pool [N,Cp,H,W]; idx device int64 [B] (pool slots; an out-of-range slot reads as zeros);
  *   extra [B,Cx,H,W] or NULL with Cx == 0: appended as channels Cp..Cp+Cx-1 (the EC conditioning channel);
- *   the first inject_n samples are replaced by seed_state [Cp,H,W] (NULL = zeros, seed_mode 'zeros' dynca.py:142-143);
+ *   the first inject_n samples, and every sample b with reseed_flags[b] != 0 (device uint8 [B] or NULL), are replaced by
+ *   seed_state [Cp,H,W] (NULL = zeros, seed_mode 'zeros' dynca.py:142-143);
  *   out [B,Cp+Cx,H,W] (written). */
 int nca_pool_gather(int32_t N, int32_t Cp, int32_t H, int32_t W, const float* pool, const int64_t* idx, int32_t B,
-                    const float* extra, int32_t Cx, const float* seed_state, int32_t inject_n, float* out, void* stream);
+                    const float* extra, int32_t Cx, const float* seed_state, int32_t inject_n, const uint8_t* reseed_flags,
+                    float* out, void* stream);
+
+/* Dead-sample test of ConditionedNCATrainer.sample_batch (conditioned_trainer.py:107-112):
+ *   `torch.sum(self.nca.alive(batch[i].unsqueeze(0))) == 0.0` for every sampled slot, without the B host round trips:
+ *   flags[b] = 1 when pool[idx[b]][living_dim] has no value > alive_thr (the 3x3 max-pool of nca.py:152-163 is non-empty
+ *   exactly when the plane itself is), else 0.  flags: device uint8 [B], fed to nca_pool_gather as reseed_flags. */
+int nca_pool_dead_flags(int32_t N, int32_t Cp, int32_t H, int32_t W, const float* pool, const int64_t* idx, int32_t B,
+                        int32_t living_dim, float alive_thr, uint8_t* flags, void* stream);
 
 /* Pool write-back — experiments.py:259: nca_pool[batch_idx] = nca_states_after[:, :12]; conditioned_trainer.py:155-156.
  *   states [B,C,H,W], the first Cp channels go to pool[idx[b]]; idx must not repeat (np.random.choice(replace=False),

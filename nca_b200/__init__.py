@@ -7,7 +7,7 @@ __path__.append(_PKG)
 
 from ._lib import NcaError, lib_path, load_library  # noqa: E402,F401
 from . import functional, parallel, trainer, video  # noqa: E402,F401
-from .trainer import NormalizedAdam, pool_gather, pool_scatter, overflow_loss  # noqa: E402,F401
+from .trainer import NormalizedAdam, TensorSamplePool, pool_gather, pool_scatter, overflow_loss  # noqa: E402,F401
 from .video import FrameStylizer  # noqa: E402,F401
 from .dynca_ec import DyNCA as DyNCA_EC, CPE2D  # noqa: E402,F401
 from .dynca_cd import DyNCA as DyNCA_CD, EdgeExtractor  # noqa: E402,F401

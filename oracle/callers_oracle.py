@@ -27,6 +27,24 @@ def pool_gather(pool, idx, extra=None, seed_state=None, inject_n=0):
     return batch
 
 
+def enc_sample_batch(pool_list, idx, seed_state, living_dim, alive_thr=0.1, inject_n=2):
+    """EncoderConditioning/conditioned_trainer.py:100-113 + :167 on a list-backed SamplePool (sample_pool.py:14-33):
+        batch = pool[idxs]; None / dead (`torch.sum(nca.alive(batch[i])) == 0`) entries -> seed; stack; batch[:2] = seed
+    with alive() = max_pool2d(x[:, d:d+1], 3, 1, 1) > thr (nca.py:152-163)."""
+    import torch.nn.functional as F
+    batch = [pool_list[int(i)] for i in idx]
+    for i in range(len(batch)):
+        if batch[i] is None:
+            batch[i] = seed_state.clone()
+        else:
+            alive = F.max_pool2d(batch[i].unsqueeze(0)[:, living_dim:living_dim + 1], kernel_size=3, stride=1, padding=1) > alive_thr
+            if torch.sum(alive) == 0.0:
+                batch[i] = seed_state.clone()
+    batch = torch.stack(batch)
+    batch[:inject_n] = seed_state.unsqueeze(0)
+    return batch
+
+
 def pool_scatter(pool, idx, states):
     """experiments.py:259: nca_pool[batch_idx] = nca_states_after[:, :12, :, :]."""
     pool = pool.clone()

@@ -50,6 +50,36 @@ def test_pool_bad_arguments():
     assert float(got[0].abs().max()) == 0.0 and float(got[1].min()) == 1.0
 
 
+def test_enc_sample_batch_reseeds_dead_and_unwritten_slots():
+    """TensorSamplePool.sample_batch == ConditionedNCATrainer.sample_batch + `batch[:2] = seed` on the list-backed pool."""
+    g = torch.Generator().manual_seed(8)
+    Np, C, H, W, B, d = 12, 20, 16, 16, 6, 3
+    seed_state = torch.zeros(C, H, W)
+    seed_state[3:, H // 2, W // 2] = 1.0                       # generate_seed: centre cell on (nca.py:113-121)
+    pool_list = [None] * Np
+    tp = nca_b200.TensorSamplePool(Np, (C, H, W), DEV)
+    assert len(tp) == Np and tp[0] is None
+    vals = {}
+    for slot in (1, 4, 5, 7, 9):
+        x = torch.randn(C, H, W, generator=g) * 0.3
+        if slot in (4, 9):
+            x[d] = x[d].clamp(max=0.1)                         # dead: nothing above the threshold (0.1 itself is not alive)
+        if slot == 7:
+            x[d] = -1.0
+            x[d, 0, W - 1] = 0.1000001                         # a single living corner cell
+        vals[slot] = x
+    slots = sorted(vals)
+    tp[slots] = torch.stack([vals[s_] for s_ in slots]).to(DEV)
+    for s_ in slots:
+        pool_list[s_] = vals[s_]
+    assert tp[1] is not None and torch.equal(tp[1].cpu(), vals[1])
+    idx = [7, 2, 4, 1, 9, 5]
+    got = tp.sample_batch(idx, seed_state.to(DEV), d, 0.1, inject_n=2)
+    want = K.enc_sample_batch(pool_list, idx, seed_state, d, 0.1, 2)
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(got[3].cpu(), vals[1]) and torch.equal(got[4].cpu(), seed_state)
+
+
 def test_normalized_adam_golden_fixture():
     d = np.load(os.path.join(GOLDEN, "callers.npz"))
     ps = [torch.nn.Parameter(torch.from_numpy(d[f"p{i}"]).to(DEV)) for i in range(4)]

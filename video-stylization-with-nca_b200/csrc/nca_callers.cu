@@ -25,13 +25,13 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) pool_gather_kernel(int N, int Cp, int Cx, size_t hw, const float* __restrict__ pool,
                                                           const int64_t* __restrict__ idx, const float* __restrict__ extra,
                                                           const float* __restrict__ seed_state, int inject_n,
-                                                          float* __restrict__ out) {
+                                                          const uint8_t* __restrict__ reseed, float* __restrict__ out) {
     const int C = Cp + Cx;
     const int b = blockIdx.y / C, c = blockIdx.y - b * C;
     const float* src = nullptr;          // nullptr = zeros
     if (c >= Cp) {
         src = extra + ((size_t)b * Cx + (c - Cp)) * hw;
-    } else if (b < inject_n) {
+    } else if (b < inject_n || (reseed && reseed[b])) {
         src = seed_state ? seed_state + (size_t)c * hw : nullptr;
     } else {
         const int64_t s = idx[b];
@@ -48,6 +48,22 @@ __global__ void __launch_bounds__(256) pool_gather_kernel(int N, int Cp, int Cx,
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x)
             dst[i] = src ? __ldg(src + i) : 0.f;
     }
+}
+
+// flags[b] = 1 when pool[idx[b]] has no living cell: alive() = max_pool2d(x[:, d], 3, 1, 1) > thr (nca.py:152-163) is empty
+// exactly when no x[:, d] exceeds thr
+__global__ void __launch_bounds__(256) pool_dead_flags_kernel(int N, int Cp, size_t hw, const float* __restrict__ pool,
+                                                              const int64_t* __restrict__ idx, int living_dim, float thr,
+                                                              uint8_t* __restrict__ flags) {
+    const int b = blockIdx.x;
+    const int64_t s = idx[b];
+    int alive = 0;
+    if (s >= 0 && s < N) {
+        const float* x = pool + ((size_t)s * Cp + living_dim) * hw;
+        for (size_t i = threadIdx.x; i < hw; i += blockDim.x) alive |= __ldg(x + i) > thr;
+    }
+    alive = __syncthreads_or(alive);
+    if (threadIdx.x == 0) flags[b] = alive ? 0 : 1;
 }
 
 template <bool VEC>
@@ -262,7 +278,8 @@ __global__ void __launch_bounds__(256) state_rgb8_kernel(int C, size_t hw, const
 extern "C" {
 
 int nca_pool_gather(int32_t N, int32_t Cp, int32_t H, int32_t W, const float* pool, const int64_t* idx, int32_t B,
-                    const float* extra, int32_t Cx, const float* seed_state, int32_t inject_n, float* out, void* stream) {
+                    const float* extra, int32_t Cx, const float* seed_state, int32_t inject_n, const uint8_t* reseed_flags,
+                    float* out, void* stream) {
     NCA_CHECK_ARG(N > 0 && Cp > 0 && H > 0 && W > 0 && B > 0 && Cx >= 0, "nca_pool_gather: bad sizes N=%d Cp=%d H=%d W=%d B=%d Cx=%d", N, Cp, H, W, B, Cx);
     NCA_CHECK_ARG(pool && idx && out, "nca_pool_gather: pool, idx and out must not be NULL");
     NCA_CHECK_ARG(Cx == 0 || extra, "nca_pool_gather: Cx=%d extra channels need an extra pointer", Cx);
@@ -275,8 +292,20 @@ int nca_pool_gather(int32_t N, int32_t Cp, int32_t H, int32_t W, const float* po
     const unsigned planes = (unsigned)(B * (Cp + Cx));
     dim3 grid(plane_blocks(vec ? hw >> 2 : hw, planes), planes);
     cudaStream_t s = (cudaStream_t)stream;
-    if (vec) pool_gather_kernel<true><<<grid, 256, 0, s>>>(N, Cp, Cx, hw, pool, idx, extra, seed_state, inject_n, out);
-    else pool_gather_kernel<false><<<grid, 256, 0, s>>>(N, Cp, Cx, hw, pool, idx, extra, seed_state, inject_n, out);
+    if (vec) pool_gather_kernel<true><<<grid, 256, 0, s>>>(N, Cp, Cx, hw, pool, idx, extra, seed_state, inject_n, reseed_flags, out);
+    else pool_gather_kernel<false><<<grid, 256, 0, s>>>(N, Cp, Cx, hw, pool, idx, extra, seed_state, inject_n, reseed_flags, out);
+    NCA_LAUNCH_OK();
+    return NCA_OK;
+}
+
+int nca_pool_dead_flags(int32_t N, int32_t Cp, int32_t H, int32_t W, const float* pool, const int64_t* idx, int32_t B,
+                        int32_t living_dim, float alive_thr, uint8_t* flags, void* stream) {
+    NCA_CHECK_ARG(N > 0 && Cp > 0 && H > 0 && W > 0 && B > 0, "nca_pool_dead_flags: bad sizes N=%d Cp=%d H=%d W=%d B=%d", N, Cp, H, W, B);
+    NCA_CHECK_ARG(living_dim >= 0 && living_dim < Cp, "nca_pool_dead_flags: living_dim=%d outside 0..%d", living_dim, Cp - 1);
+    NCA_CHECK_ARG(pool && idx && flags, "nca_pool_dead_flags: NULL pointer");
+    int rc = nca_check_device();
+    if (rc) return rc;
+    pool_dead_flags_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(N, Cp, (size_t)H * W, pool, idx, living_dim, alive_thr, flags);
     NCA_LAUNCH_OK();
     return NCA_OK;
 }

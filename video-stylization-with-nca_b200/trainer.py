@@ -26,10 +26,11 @@ def _idx_tensor(idx, device):
     return t.contiguous()
 
 
-def pool_gather(pool, idx, extra=None, seed_state=None, inject_n=0):
+def pool_gather(pool, idx, extra=None, seed_state=None, inject_n=0, reseed_dead=None):
     """`nca_pool[batch_idx]` + seed injection into the first `inject_n` samples + `torch.cat((states, extra), 1)`
     (experiments.py:203-211) in one pass.  pool [N,Cp,H,W]; idx: numpy / list / tensor of B slots; extra [B,Cx,H,W] or None;
-    seed_state [Cp,H,W] or None (zeros).  Returns a new [B,Cp+Cx,H,W] tensor."""
+    seed_state [Cp,H,W] or None (zeros).  reseed_dead=(living_channel_dim, alpha_living_threshold) also replaces every sample
+    without a living cell by the seed (conditioned_trainer.py:107-112), tested on the device.  Returns a new [B,Cp+Cx,H,W] tensor."""
     _need_cuda(pool, extra, seed_state)
     if not pool.is_contiguous():
         raise NcaError("the pool tensor must be contiguous")
@@ -47,9 +48,15 @@ def pool_gather(pool, idx, extra=None, seed_state=None, inject_n=0):
         if seed_state.numel() != Cp * H * W:
             raise NcaError(f"seed_state must have {Cp}x{H}x{W} elements, got {tuple(seed_state.shape)}")
     out = torch.empty(B, Cp + Cx, H, W, device=pool.device, dtype=torch.float32)
+    lib = load_library()
     with torch.cuda.device(pool.device):
-        check(load_library().nca_pool_gather(N, Cp, H, W, _ptr(pool), _ptr(it), B, _ptr(extra), Cx, _ptr(seed_state),
-                                             int(inject_n), _ptr(out), _stream()))
+        flags = None
+        if reseed_dead is not None:
+            flags = torch.empty(B, device=pool.device, dtype=torch.uint8)
+            check(lib.nca_pool_dead_flags(N, Cp, H, W, _ptr(pool), _ptr(it), B, int(reseed_dead[0]), float(reseed_dead[1]),
+                                          _ptr(flags), _stream()))
+        check(lib.nca_pool_gather(N, Cp, H, W, _ptr(pool), _ptr(it), B, _ptr(extra), Cx, _ptr(seed_state),
+                                  int(inject_n), _ptr(flags), _ptr(out), _stream()))
     return out
 
 
@@ -67,6 +74,39 @@ def pool_scatter(pool, idx, states):
     with torch.cuda.device(pool.device):
         check(load_library().nca_pool_scatter(N, Cp, H, W, _ptr(pool), _ptr(it), B, _ptr(states), states.shape[1], _stream()))
     return pool
+
+
+class TensorSamplePool:
+    """Tensor-backed stand-in for EncoderConditioning/sample_pool.py:14-33 (`SamplePool`, a Python list of per-sample tensors):
+    same `len()` / `pool[idxs]` / `pool[idxs] = outputs` surface, but one contiguous device tensor [pool_size,C,H,W], so that
+    `sample_batch` (conditioned_trainer.py:100-113: stack the sampled slots, reseed the None / dead ones, then `batch[:2] = seed`
+    :167) is two launches instead of B host round trips.  Slots never written are all-zero, which the dead test reseeds exactly
+    like the reference's `None`."""
+
+    def __init__(self, pool_size, shape, device):
+        self.pool_size = int(pool_size)
+        self.data = torch.zeros(self.pool_size, *shape, device=device, dtype=torch.float32)
+        self._written = [False] * self.pool_size
+
+    def __len__(self):
+        return self.pool_size
+
+    def __getitem__(self, idx):
+        if isinstance(idx, int):
+            return self.data[idx] if self._written[idx] else None
+        return [self[int(i)] for i in idx]
+
+    def __setitem__(self, idx, value):
+        if isinstance(idx, int):
+            self.data[idx].copy_(value)
+            self._written[idx] = True
+            return
+        pool_scatter(self.data, idx, value)
+        for i in idx:
+            self._written[int(i)] = True
+
+    def sample_batch(self, idx, seed_state, living_dim, alive_thr=0.1, inject_n=2):
+        return pool_gather(self.data, idx, None, seed_state, inject_n, reseed_dead=(living_dim, alive_thr))
 
 
 class NormalizedAdam(torch.optim.Optimizer):
