@@ -19,7 +19,12 @@ DEV = torch.device("cuda:0")
 HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 
+QUICK = "--quick" in sys.argv      # a few launches of every kernel for an ncu launch list (numbers printed in this mode are not bench values)
+
+
 def timed(fn, iters=20, warm=3):
+    if QUICK:
+        iters, warm = 2, 1
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -143,7 +148,7 @@ def main():
         return torch.cat((states[k[0] % 4][:, :-1], torch.mean(frames[k[0] % 8], dim=1, keepdim=True)), 1)
     line("frame_to_cond_channel 1080p (in place) vs cat((h, gray), 1)", timed(ours_gray, 50), Hf * Wf * 16, timed(ref_gray, 50), launches=1)
 
-    for step_n, F in ((8, 24), (256, 3)):
+    for step_n, F in (((8, 2),) if QUICK else ((8, 24), (256, 3))):
         m = nca_b200.DyNCA_EC(C, 3, fc_dim=96, padding_mode="circular", pos_emb=None, perception_scales=[0], device=DEV, precision="bf16")
         clip = (torch.rand(F, 3, Hf, Wf) * 2 - 1).pin_memory()
         st = V.FrameStylizer(m, (Hf, Wf), step_n=step_n, seed=1)

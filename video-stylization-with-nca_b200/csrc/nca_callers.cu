@@ -84,10 +84,11 @@ __global__ void __launch_bounds__(256) pool_scatter_kernel(int N, int Cp, int C,
     }
 }
 
-// blocks along a plane: enough that every SM has ~8 CTAs in total, at most one per 1024 elements (4 float4 per thread)
+// blocks along a plane: enough that every SM has ~8 CTAs (2048 threads, ~100 KB of loads in flight) in total, at most one per
+// 256 items (one float4 per thread: with few planes - a single 1080p frame - parallelism matters more than loop amortisation)
 unsigned plane_blocks(size_t n_items, unsigned planes) {
     const size_t want = ((size_t)sm_count() * 8 + planes - 1) / planes;
-    const size_t most = (n_items + 1023) / 1024;
+    const size_t most = (n_items + 255) / 256;
     size_t g = want < most ? want : most;
     return (unsigned)(g < 1 ? 1 : g);
 }

@@ -72,6 +72,7 @@ class FrameStylizer:
         self.slots = torch.zeros(2, batch, self.C, H, W, device=self.dev, dtype=torch.float32)
         self.cur = 0
         self.gray = torch.empty(batch, 1, H, W, device=self.dev) if self.flavour == "cd" and model.conditioning == 'edges' else None
+        self._host = self._dev_out = self._dev_in = self._side = None
         self.reset()
 
     def reset(self):
@@ -119,16 +120,33 @@ class FrameStylizer:
         return state_to_rgb8(self.slots[self.cur], 2.0, out)
 
     @torch.no_grad()
-    def run(self, frames):
-        """frames [F,3,H,W] (device or pinned host; one stream, batch 1) or [F,B,3,H,W] -> pinned uint8 [F*steps_per_frame,B,H,W,3]."""
+    def run(self, frames, out=None):
+        """frames [F,3,H,W] (device or pinned host; one stream, batch 1) or [F,B,3,H,W] -> pinned uint8 [F*steps_per_frame,B,H,W,3]
+        (`out`, or an internal pinned buffer that the next run() of the same length overwrites)."""
         if frames.dim() == 4:
             frames = frames.unsqueeze(1)
         F = frames.shape[0]
         n_out = F * self.steps_per_frame
-        host = torch.empty(n_out, self.B, self.H, self.W, 3, dtype=torch.uint8).pin_memory()
-        dev_out = [torch.empty(self.B, self.H, self.W, 3, device=self.dev, dtype=torch.uint8) for _ in range(2)]
-        dev_in = [torch.empty(self.B, 3, self.H, self.W, device=self.dev) for _ in range(2)] if not frames.is_cuda else None
-        main, side = torch.cuda.current_stream(self.dev), torch.cuda.Stream(self.dev)
+        if out is None:
+            # pinning is a cudaHostAlloc (~0.2 ms / MB): the buffer is kept and reused by later calls of the same length, so the
+            # caller must consume (or copy) a result before the next run()
+            if self._host is None or self._host.shape[0] != n_out:
+                self._host = torch.empty(n_out, self.B, self.H, self.W, 3, dtype=torch.uint8).pin_memory()
+            out = self._host
+        elif tuple(out.shape) != (n_out, self.B, self.H, self.W, 3) or out.dtype != torch.uint8 or out.is_cuda:
+            raise NcaError(f"out must be a host uint8 tensor of shape {(n_out, self.B, self.H, self.W, 3)}")
+        host = out
+        if self._dev_out is None:
+            self._dev_out = [torch.empty(self.B, self.H, self.W, 3, device=self.dev, dtype=torch.uint8) for _ in range(2)]
+            self._side = torch.cuda.Stream(self.dev)
+        dev_out = self._dev_out
+        dev_in = None
+        if not frames.is_cuda:
+            if self._dev_in is None:
+                self._dev_in = [torch.empty(self.B, 3, self.H, self.W, device=self.dev) for _ in range(2)]
+            dev_in = self._dev_in
+        main, side = torch.cuda.current_stream(self.dev), self._side
+        side.wait_stream(main)
         done = [None, None]      # D2H of the frame that used dev_out[k] has finished
         up = [None, None]
         if dev_in is not None:
