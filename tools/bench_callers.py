@@ -115,8 +115,9 @@ def main():
             o_ref.step()
         t_o, t_r = timed(ours_adam, 200, 20), timed(ref_adam, 200, 20)
         # wall clock per call too: these are launch-bound, the host cost is what the training loop sees
-        t0 = time.perf_counter(); [ours_adam() for _ in range(200)]; torch.cuda.synchronize(); w_o = (time.perf_counter() - t0) / 200
-        t0 = time.perf_counter(); [ref_adam() for _ in range(200)]; torch.cuda.synchronize(); w_r = (time.perf_counter() - t0) / 200
+        NW = 2 if QUICK else 200
+        t0 = time.perf_counter(); [ours_adam() for _ in range(NW)]; torch.cuda.synchronize(); w_o = (time.perf_counter() - t0) / NW
+        t0 = time.perf_counter(); [ref_adam() for _ in range(NW)]; torch.cuda.synchronize(); w_r = (time.perf_counter() - t0) / NW
         line("normalise + Adam step, " + name, t_o, None, t_r, launches=1, wall_us=w_o * 1e6, torch_wall_us=w_r * 1e6)
 
     # ---- N2: frame kernels and the frame stream at c5 (1920x1080, C=13 EC flavour) ----
