@@ -215,11 +215,12 @@ int nca_normalized_adam_step(int32_t n_tensors, float* const* params, float* con
 /* Loss.get_overflow_loss (ExtraChannels/utils/loss/loss.py:33-36; EncoderConditioning/loss/loss.py):
  *   loss = mean |x - clamp(x, -1, 1)| over the n elements of the final state, and in the same pass its gradient
  *   grad_scale * sign(x) * [|x| > 1] / n written (accumulate == 0) or added (accumulate != 0) to grad_out (NULL = loss only):
- *   the BPTT's g_final gets the overflow term without a second pass over the state.
+ *   the BPTT's g_final gets the overflow term without a second pass over the state.  grad_scale_dev (device float[1] or NULL)
+ *   multiplies grad_scale on the device: autograd's incoming dL/dloss is used without a host round trip or an extra pass.
  *   loss_out: device float[1]; workspace: nca_overflow_workspace_bytes() bytes.  Fixed reduction order (reproducible). */
 size_t nca_overflow_workspace_bytes(void);
-int nca_overflow_loss(const float* x, size_t n, float* loss_out, float* grad_out, float grad_scale, int32_t accumulate,
-                      void* workspace, size_t workspace_bytes, void* stream);
+int nca_overflow_loss(const float* x, size_t n, float* loss_out, float* grad_out, float grad_scale, const float* grad_scale_dev,
+                      int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Inference stream, per target frame — ExtraChannels/utils/misc/video_utils.py:72: h = cat((h, RGBToGrayscale(frame)), 1)
  * (preprocess_texture.py:178-179: mean over the three channels) and :76: h = nca_state[:, :-1].  The conditioning channel

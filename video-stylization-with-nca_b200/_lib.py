@@ -92,7 +92,7 @@ def load_library():
     lib.nca_normalized_adam_step.argtypes = [I, PP, PP, PP, PP, C.POINTER(C.c_int64), I, F, F, F, F, F, I, I, P]
     lib.nca_overflow_workspace_bytes.restype = SZ
     lib.nca_overflow_workspace_bytes.argtypes = []
-    lib.nca_overflow_loss.argtypes = [P, SZ, P, P, F, I, P, SZ, P]
+    lib.nca_overflow_loss.argtypes = [P, SZ, P, P, F, P, I, P, SZ, P]
     lib.nca_frame_to_cond_channel.argtypes = [I, I, I, I, P, P, I, P]
     lib.nca_state_to_rgb8.argtypes = [I, I, I, I, P, F, P, P]
     if lib.nca_abi_version() != 5:

@@ -156,9 +156,11 @@ __device__ __forceinline__ float overflow_term(float x, float gs, float* g) {
 }
 
 __global__ void __launch_bounds__(256) overflow_partial_kernel(const float* __restrict__ x, size_t n, float* __restrict__ partial,
-                                                               float* __restrict__ grad, float gs, int accumulate) {
+                                                               float* __restrict__ grad, float gs, const float* __restrict__ gs_dev,
+                                                               int accumulate) {
     __shared__ float sh[32];
     float acc = 0.f;
+    if (gs_dev) gs *= __ldg(gs_dev);          // the incoming gradient of the loss, read on the device (no host round trip)
     const size_t n4 = n >> 2;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad)) & 15u) == 0;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
@@ -358,8 +360,8 @@ int nca_normalized_adam_step(int32_t n_tensors, float* const* params, float* con
 
 size_t nca_overflow_workspace_bytes(void) { return 1024 * sizeof(float); }
 
-int nca_overflow_loss(const float* x, size_t n, float* loss_out, float* grad_out, float grad_scale, int32_t accumulate,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+int nca_overflow_loss(const float* x, size_t n, float* loss_out, float* grad_out, float grad_scale, const float* grad_scale_dev,
+                      int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream) {
     NCA_CHECK_ARG(x && loss_out && n > 0, "nca_overflow_loss: x / loss_out NULL or n == 0");
     if (!workspace || workspace_bytes < nca_overflow_workspace_bytes()) {
         nca_set_error("nca_overflow_loss: workspace of %zu bytes needed, got %zu", nca_overflow_workspace_bytes(), workspace_bytes);
@@ -374,7 +376,7 @@ int nca_overflow_loss(const float* x, size_t n, float* loss_out, float* grad_out
     float* partial = (float*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
     // d/dx mean|x - clamp(x)| = sign(x) [|x| > 1] / n
-    overflow_partial_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, n, partial, grad_out, (float)((double)grad_scale / (double)n), accumulate);
+    overflow_partial_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, n, partial, grad_out, (float)((double)grad_scale / (double)n), grad_scale_dev, accumulate);
     NCA_LAUNCH_OK();
     overflow_final_kernel<<<1, 1024, 0, s>>>(partial, (int)blocks, (float)(1.0 / (double)n), loss_out);
     NCA_LAUNCH_OK();

@@ -164,26 +164,35 @@ class NormalizedAdam(torch.optim.Optimizer):
         return loss
 
 
+def _overflow_call(x, grad, scale, scale_dev, accumulate):
+    lib = load_library()
+    loss = torch.empty(1, device=x.device, dtype=torch.float32)
+    nws = lib.nca_overflow_workspace_bytes()
+    ws = torch.empty(nws, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        check(lib.nca_overflow_loss(_ptr(x), x.numel(), _ptr(loss), _ptr(grad), float(scale), _ptr(scale_dev), int(accumulate),
+                                    _ptr(ws), nws, _stream()))
+    return loss.reshape(())
+
+
 class _OverflowLoss(torch.autograd.Function):
+    """forward: one read of the state -> loss.  backward: one read of the state + one write of the gradient, scaled by the incoming
+    dL/dloss read on the device (12 B per element in total; the reference's expression moves ~64 B per element)."""
+
     @staticmethod
     def forward(ctx, x):
-        lib = load_library()
         xc = x.detach().contiguous()
-        loss = torch.empty(1, device=x.device, dtype=torch.float32)
-        need = x.requires_grad
-        grad = torch.empty_like(xc) if need else None
-        nws = lib.nca_overflow_workspace_bytes()
-        ws = torch.empty(nws, device=x.device, dtype=torch.uint8)
-        with torch.cuda.device(x.device):
-            check(lib.nca_overflow_loss(_ptr(xc), xc.numel(), _ptr(loss), _ptr(grad), 1.0, 0, _ptr(ws), nws, _stream()))
-        ctx.grad = grad
+        ctx.save_for_backward(xc)
         ctx.shape = x.shape
-        return loss.reshape(())
+        return _overflow_call(xc, None, 1.0, None, 0)
 
     @staticmethod
     def backward(ctx, gout):
-        g, ctx.grad = ctx.grad, None
-        return None if g is None else (g * gout).view(ctx.shape)
+        (xc,) = ctx.saved_tensors
+        grad = torch.empty_like(xc)
+        gout = gout.detach().to(device=xc.device, dtype=torch.float32).reshape(1).contiguous()
+        _overflow_call(xc, grad, 1.0, gout, 0)
+        return grad.view(ctx.shape)
 
 
 def overflow_loss(nca_state):
@@ -199,11 +208,4 @@ def overflow_loss_into(nca_state, g_final, weight=1.0):
     _need_cuda(nca_state, g_final)
     if not (nca_state.is_contiguous() and g_final.is_contiguous()) or nca_state.shape != g_final.shape:
         raise NcaError("overflow_loss_into needs contiguous state / gradient tensors of the same shape")
-    lib = load_library()
-    loss = torch.empty(1, device=nca_state.device, dtype=torch.float32)
-    nws = lib.nca_overflow_workspace_bytes()
-    ws = torch.empty(nws, device=nca_state.device, dtype=torch.uint8)
-    with torch.cuda.device(nca_state.device):
-        check(lib.nca_overflow_loss(_ptr(nca_state.detach()), nca_state.numel(), _ptr(loss), _ptr(g_final), float(weight), 1,
-                                    _ptr(ws), nws, _stream()))
-    return loss.reshape(())
+    return _overflow_call(nca_state.detach(), g_final, weight, None, 1)
