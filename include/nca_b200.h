@@ -132,6 +132,11 @@ int nca_dynca_kernel_variant(const NcaDyncaDesc* d, int32_t backward);
 int nca_philox_mask(int32_t B, int32_t H, int32_t W, float rate, int32_t enc, uint64_t seed, int32_t t0,
                     int32_t T, float* out, void* stream);
 
+/* The same masks for steps t0 + *t0_dev .. (t0_dev: device uint32[1] or NULL): the step counter lives on the device, so a
+ * captured CUDA graph (mask draw + rollout with NCA_MASK_SUPPLIED + a counter increment) draws new masks on every replay. */
+int nca_philox_mask_at(int32_t B, int32_t H, int32_t W, float rate, int32_t enc, uint64_t seed, int32_t t0, const uint32_t* t0_dev,
+                       int32_t T, float* out, void* stream);
+
 /* ---- ConditionedNCA (EncoderConditioning/nca.py) --------------------------------------- */
 
 typedef struct NcaEncDesc {

@@ -254,3 +254,67 @@ def test_frame_stylizer_cd_edges_and_device_frames():
             masks = nca_b200.functional.philox_mask(1, H, W, 0.5, 99, 6, t0=6 * f)
             h, feat = m.forward_nsteps(h, 6, cond_img=gray, masks=masks)
             assert np.array_equal(got[f, 0], K.state_to_rgb8(h)[0]), f
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_frame_sequence_is_graph_capturable(precision):
+    """include/nca_b200.h promises that every entry point only enqueues work on the caller's stream: the per-frame sequence of the
+    inference stream (conditioning channel, step_n steps with programmatic dependent launches and TMA tensor maps, rgb8 packing)
+    is captured into one CUDA graph and replayed on new inputs."""
+    H, W, T = 64, 64, 6
+    m = _ec_model(precision=precision)
+    g0 = torch.Generator().manual_seed(3)
+    xa = (torch.rand(2, 13, H, W, generator=g0) - 0.5).to(DEV)
+    xb = (torch.rand(2, 13, H, W, generator=g0) - 0.5).to(DEV)
+    fr = (torch.rand(2, 3, H, W, generator=g0) * 2 - 1).to(DEV)
+
+    def seq(xin, out8):
+        V.frame_to_cond_channel(xin, fr, -1)
+        s, _ = m.forward_nsteps(xin, T, seed=5)
+        V.state_to_rgb8(s, 2.0, out8)
+        return s
+
+    with torch.no_grad():
+        refs = []
+        for x in (xa, xb):
+            o8 = torch.empty(2, H, W, 3, device=DEV, dtype=torch.uint8)
+            refs.append((seq(x.clone(), o8).clone(), o8))
+        torch.cuda.synchronize()
+        xs = xa.clone()
+        out8 = torch.empty(2, H, W, 3, device=DEV, dtype=torch.uint8)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            got = seq(xs, out8)
+        for x, (ref, ref8) in zip((xb, xa), (refs[1], refs[0])):
+            xs.copy_(x)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref) and torch.equal(out8, ref8)
+
+
+@pytest.mark.parametrize("flavour,step_n,precision", [("ec", 8, "fp32"), ("ec", 5, "bf16"), ("cd", 6, "bf16")])
+def test_frame_stylizer_graph_mode_equals_eager(flavour, step_n, precision):
+    """graph=True (mask draw from a device-side step counter + rollout with supplied masks + rgb8, one CUDA graph per frame)
+    produces the frames of the eager stream bit for bit, across two clips and a reset."""
+    H, W, F = 32, 64, 5
+    if flavour == "ec":
+        m = _ec_model(precision=precision)
+    else:
+        torch.manual_seed(0)
+        m = nca_b200.DyNCA_CD(12, 3, fc_dim=96, padding_mode="circular", conditioning="edges", edge_transform="tanh",
+                              perception_scales=[0], device=torch.device(DEV), precision=precision)
+        with torch.no_grad():
+            m.w2.weight.mul_(3.0)
+    frames = (torch.rand(F, 3, H, W, generator=torch.Generator().manual_seed(7)) * 2 - 1)
+    eager = V.FrameStylizer(m, (H, W), step_n=step_n, seed=77)
+    graph = V.FrameStylizer(m, (H, W), step_n=step_n, seed=77, graph=True)
+    a1 = eager.run(frames.pin_memory()).clone().numpy()
+    b1 = graph.run(frames.to(DEV)).clone().numpy()
+    assert np.array_equal(a1, b1) and a1.std() > 0
+    assert torch.equal(eager.state, graph.state)
+    # the stream continues (step counter on the device keeps advancing), then starts over after reset()
+    a2 = eager.run(frames.flip(0).pin_memory()).clone().numpy()
+    b2 = graph.run(frames.flip(0).pin_memory()).clone().numpy()
+    assert np.array_equal(a2, b2) and not np.array_equal(a1, a2)
+    eager.reset(); graph.reset()
+    assert np.array_equal(graph.run(frames.to(DEV)).numpy(), a1)

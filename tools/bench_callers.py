@@ -149,6 +149,39 @@ def main():
         return torch.cat((states[k[0] % 4][:, :-1], torch.mean(frames[k[0] % 8], dim=1, keepdim=True)), 1)
     line("frame_to_cond_channel 1080p (in place) vs cat((h, gray), 1)", timed(ours_gray, 50), Hf * Wf * 16, timed(ref_gray, 50), launches=1)
 
+    # the reference's own video size (nca_size 256, video_utils.py:50-52): host bound without the per-frame CUDA graph
+    m = nca_b200.DyNCA_EC(C, 3, fc_dim=96, padding_mode="circular", pos_emb=None, perception_scales=[0], device=DEV, precision="bf16")
+    F = 4 if QUICK else 300
+    clip = (torch.rand(F, 3, 256, 256) * 2 - 1).pin_memory()
+    res = {}
+    for mode in ("eager", "graph"):
+        st = V.FrameStylizer(m, (256, 256), step_n=8, seed=1, graph=(mode == "graph"))
+        st.run(clip)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); st.reset(); st.run(clip); torch.cuda.synchronize(); res[mode] = time.perf_counter() - t0
+
+    def ref_stream_small():
+        with torch.no_grad():
+            h = m.seed(1, size=(256, 256))
+            out = []
+            for f in range(F):
+                fr = clip[f].unsqueeze(0).to(DEV)
+                h = torch.cat((h, torch.mean(fr, dim=1, keepdim=True)), 1)
+                nca_state, z = m.forward_nsteps(h, 8, seed=1)
+                h = nca_state[:, :-1, :, :]
+                img = z.detach().cpu().numpy()[0].transpose(1, 2, 0)
+                img = np.clip(img, -1.0, 1.0)
+                img = (img + 1.0) / 2.0
+                out.append(np.uint8(img.clip(0, 1) * 255))
+            return out
+    ref_stream_small()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); ref_stream_small(); torch.cuda.synchronize(); t_r = time.perf_counter() - t0
+    print(json.dumps({"item": f"frame stream 256x256 EC C=13 bf16, step_n=8, {F} frames (wall clock)",
+                      "frames_per_s_eager": F / res["eager"], "frames_per_s_graph": F / res["graph"],
+                      "cell_updates_per_s_graph": F * 8 * 65536 / res["graph"], "reference_loop_frames_per_s": F / t_r,
+                      "speedup_graph_vs_reference_loop": t_r / res["graph"], "speedup_graph_vs_eager": res["eager"] / res["graph"]}), flush=True)
+
     for step_n, F in (((8, 2),) if QUICK else ((8, 24), (256, 3))):
         m = nca_b200.DyNCA_EC(C, 3, fc_dim=96, padding_mode="circular", pos_emb=None, perception_scales=[0], device=DEV, precision="bf16")
         clip = (torch.rand(F, 3, Hf, Wf) * 2 - 1).pin_memory()

@@ -44,7 +44,7 @@ class EncWeights(C.Structure):
 SYMBOLS = ["nca_last_error", "nca_abi_version", "nca_launch_count", "nca_launch_count_reset", "nca_dynca_perceive",
            "nca_edge_extract", "nca_dynca_forward", "nca_dynca_backward", "nca_dynca_workspace_bytes", "nca_dynca_op_hist_bytes",
            "nca_dynca_kernel_variant",
-           "nca_philox_mask", "nca_enc_forward", "nca_enc_backward", "nca_enc_workspace_bytes",
+           "nca_philox_mask", "nca_philox_mask_at", "nca_enc_forward", "nca_enc_backward", "nca_enc_workspace_bytes",
            "nca_pool_gather", "nca_pool_dead_flags", "nca_pool_scatter", "nca_normalized_adam_step", "nca_overflow_workspace_bytes", "nca_overflow_loss",
            "nca_frame_to_cond_channel", "nca_state_to_rgb8"]
 
@@ -73,6 +73,7 @@ def load_library():
     lib.nca_dynca_perceive.argtypes = [C.POINTER(DyncaDesc), P, P, P, P]
     lib.nca_edge_extract.argtypes = [C.c_int, C.c_int, C.c_int, P, C.c_int, P, P]
     lib.nca_philox_mask.argtypes = [I, I, I, F, I, U64, I, I, P, P]
+    lib.nca_philox_mask_at.argtypes = [I, I, I, F, I, U64, I, P, I, P, P]
     lib.nca_dynca_op_hist_bytes.restype = SZ
     lib.nca_dynca_op_hist_bytes.argtypes = [C.POINTER(DyncaDesc), I]
     lib.nca_dynca_forward.argtypes = [C.POINTER(DyncaDesc), C.POINTER(DyncaWeights), P, P, U64, I, I, I, P, P, P, P, SZ, P]

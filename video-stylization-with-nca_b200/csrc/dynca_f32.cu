@@ -445,8 +445,9 @@ __global__ void nca_edge_extract_kernel(int B, int H, int W, const float* __rest
 }
 
 __global__ void nca_philox_mask_kernel(int B, int H, int W, unsigned long long thr, int enc, uint32_t k0, uint32_t k1,
-                                       int t0, int T, float* __restrict__ out) {
+                                       int t0, const uint32_t* __restrict__ t0_dev, int T, float* __restrict__ out) {
     const size_t plane = (size_t)H * W, n = (size_t)T * B * plane;
+    if (t0_dev) t0 += (int)__ldg(t0_dev);      // step counter kept on the device (CUDA-graph replays advance it)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t p = (uint32_t)(i % plane);
         const uint32_t b = (uint32_t)((i / plane) % B);
@@ -570,11 +571,11 @@ int nca_edge_extract_launch(int B, int H, int W, const float* img, int tanh_tran
     return NCA_OK;
 }
 
-int nca_philox_mask_launch(int B, int H, int W, float rate, int enc, uint64_t seed, int t0, int T, float* out, cudaStream_t s) {
+int nca_philox_mask_launch(int B, int H, int W, float rate, int enc, uint64_t seed, int t0, const uint32_t* t0_dev, int T, float* out, cudaStream_t s) {
     size_t n = (size_t)T * B * H * W;
     int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
     nca_philox_mask_kernel<<<grid, 256, 0, s>>>(B, H, W, (unsigned long long)nca_fire_threshold(rate, enc), enc,
-                                                (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), t0, T, out);
+                                                (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), t0, t0_dev, T, out);
     NCA_LAUNCH_OK();
     return NCA_OK;
 }

@@ -110,7 +110,15 @@ int nca_philox_mask(int32_t B, int32_t H, int32_t W, float rate, int32_t enc, ui
     NCA_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0 && out, "bad philox_mask arguments");
     int rc = check_device();
     if (rc) return rc;
-    return nca_philox_mask_launch(B, H, W, rate, enc, seed, t0, T, out, (cudaStream_t)stream);
+    return nca_philox_mask_launch(B, H, W, rate, enc, seed, t0, nullptr, T, out, (cudaStream_t)stream);
+}
+
+int nca_philox_mask_at(int32_t B, int32_t H, int32_t W, float rate, int32_t enc, uint64_t seed, int32_t t0, const uint32_t* t0_dev,
+                       int32_t T, float* out, void* stream) {
+    NCA_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0 && out, "bad philox_mask arguments");
+    int rc = check_device();
+    if (rc) return rc;
+    return nca_philox_mask_launch(B, H, W, rate, enc, seed, t0, t0_dev, T, out, (cudaStream_t)stream);
 }
 
 size_t nca_dynca_op_hist_bytes(const NcaDyncaDesc* d, int32_t T) {

@@ -14,7 +14,7 @@ int dynca_f32_backward_step(const DyncaGeom& g, const float* wsW, float* wsG, co
                             const FireMask& fm, cudaStream_t s);
 int dynca_f32_unpack_grads(const DyncaGeom& g, const float* wsG, const NcaDyncaWeightGrads* gw, cudaStream_t s);
 int nca_edge_extract_launch(int B, int H, int W, const float* img, int tanh_transform, float* out, cudaStream_t s);
-int nca_philox_mask_launch(int B, int H, int W, float rate, int enc, uint64_t seed, int t0, int T, float* out, cudaStream_t s);
+int nca_philox_mask_launch(int B, int H, int W, float rate, int enc, uint64_t seed, int t0, const uint32_t* t0_dev, int T, float* out, cudaStream_t s);
 
 // dynca_bf16.cu (tcgen05 path)
 size_t dynca_bf16_weight_bytes(const DyncaGeom& g);

@@ -60,8 +60,12 @@ class FrameStylizer:
     automaton `step_n` steps on that frame and returns the uint8 image on the device; `run(frames)` does it for a whole clip
     and returns a pinned host array, copies overlapped with compute."""
 
-    def __init__(self, model, size, step_n=8, steps_per_frame=1, batch=1, update_rate=0.5, seed=None):
+    def __init__(self, model, size, step_n=8, steps_per_frame=1, batch=1, update_rate=0.5, seed=None, graph=False):
         self.model, self.step_n, self.steps_per_frame, self.rate = model, int(step_n), int(steps_per_frame), float(update_rate)
+        # graph=True: the per-frame sequence (conditioning, mask draw, step_n steps, rgb8, step counter) is captured once into a
+        # CUDA graph and replayed per frame - one launch from the host instead of step_n + 4.  Small frames (the reference's
+        # 256x256) are host bound without it.  The weights are read at replay time (the weight repack is inside the graph).
+        self.use_graph, self._graph = bool(graph), None
         H, W = (size, size) if isinstance(size, int) else size
         self.B, self.H, self.W = batch, H, W
         self.dev = model.w1.weight.device
@@ -73,6 +77,7 @@ class FrameStylizer:
         self.cur = 0
         self.gray = torch.empty(batch, 1, H, W, device=self.dev) if self.flavour == "cd" and model.conditioning == 'edges' else None
         self._host = self._dev_out = self._dev_in = self._side = None
+        self._tdev = torch.zeros(1, device=self.dev, dtype=torch.int32)      # Philox step counter of the graph mode
         self.reset()
 
     def reset(self):
@@ -81,6 +86,7 @@ class FrameStylizer:
         self.slots.zero_()
         self.slots[0, :, :h.shape[1]].copy_(h)
         self.cur, self.t0 = 0, 0
+        self._tdev.zero_()
 
     @property
     def state(self):
@@ -97,24 +103,67 @@ class FrameStylizer:
             return m._cfg(NCA_COND_TENSOR, 3), m.cond_layer(self.gray)
         return m._cfg(NCA_COND_CPE if m.conditioning == 'pos_emb' else NCA_COND_NONE, 2 if m.conditioning == 'pos_emb' else 0), None
 
-    @torch.no_grad()
-    def push(self, frame_rgb, out=None):
-        """frame_rgb [B,3,H,W] float in [-1,1] on the device -> uint8 [B,H,W,3] after `step_n` steps."""
-        if self.cur == 1:                      # an odd step_n left the state in slot 1: the C ABI reads its input from slot 0
-            self.slots[0].copy_(self.slots[1])
-            self.cur = 0
-        cfg, cond = self._cfg_cond(frame_rgb.contiguous())
-        m = self.model
+    def _steps(self, cfg, cond, masks, t0):
+        """step_n steps from slot 0 into slot step_n & 1 (masks: supplied [T,B,1,H,W] or None = in-kernel Philox from t0)."""
         lib = load_library()
-        d = cfg.desc(self.B, self.H, self.W, self.rate, False)
-        w = [t.detach() for t in m._w()]
+        d = cfg.desc(self.B, self.H, self.W, self.rate, masks is not None)
+        w = [t.detach() for t in self.model._w()]
         with torch.cuda.device(self.dev):
             nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
             if getattr(self, "_ws", None) is None or self._ws.numel() < nbytes:
                 self._ws = torch.empty(max(nbytes, 16), device=self.dev, dtype=torch.uint8)
             wst = Fn._weights_struct(*w)
-            check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), None, C.c_uint64(self.seed), self.t0, self.step_n,
+            check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(self.seed), t0, self.step_n,
                                         0, _ptr(self.slots), None, None, _ptr(self._ws), nbytes, _stream()))
+
+    def _capture(self):
+        lib = load_library()
+        self._gframe = torch.zeros(self.B, 3, self.H, self.W, device=self.dev)
+        self._gout8 = torch.empty(self.B, self.H, self.W, 3, device=self.dev, dtype=torch.uint8)
+        self._gmasks = torch.empty(self.step_n, self.B, 1, self.H, self.W, device=self.dev)
+        keep = (self.slots.clone(), self._tdev.clone())
+
+        def sequence():
+            cfg, cond = self._cfg_cond(self._gframe)
+            with torch.cuda.device(self.dev):
+                check(lib.nca_philox_mask_at(self.B, self.H, self.W, self.rate, 0, C.c_uint64(self.seed), 0, _ptr(self._tdev),
+                                             self.step_n, _ptr(self._gmasks), _stream()))
+            self._steps(cfg, cond, self._gmasks, 0)
+            state_to_rgb8(self.slots[self.step_n & 1], 2.0, self._gout8)
+            if self.step_n & 1:                 # every replay starts from slot 0
+                self.slots[0].copy_(self.slots[1])
+            self._tdev.add_(self.step_n)
+
+        # warm-up on a side stream (allocations, function attributes), then capture; the state is restored afterwards
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            sequence()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            sequence()
+        self.slots.copy_(keep[0])
+        self._tdev.copy_(keep[1])
+
+    @torch.no_grad()
+    def push(self, frame_rgb, out=None):
+        """frame_rgb [B,3,H,W] float in [-1,1] on the device -> uint8 [B,H,W,3] after `step_n` steps."""
+        if self.use_graph:
+            if self._graph is None:
+                self._capture()
+            self._gframe.copy_(frame_rgb)
+            self._graph.replay()
+            self.t0 += self.step_n
+            if out is None:
+                return self._gout8
+            out.copy_(self._gout8)
+            return out
+        if self.cur == 1:                      # an odd step_n left the state in slot 1: the C ABI reads its input from slot 0
+            self.slots[0].copy_(self.slots[1])
+            self.cur = 0
+        cfg, cond = self._cfg_cond(frame_rgb.contiguous())
+        self._steps(cfg, cond, None, self.t0)
         self.t0 += self.step_n
         self.cur = self.step_n & 1
         return state_to_rgb8(self.slots[self.cur], 2.0, out)
