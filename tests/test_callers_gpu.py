@@ -318,3 +318,24 @@ def test_frame_stylizer_graph_mode_equals_eager(flavour, step_n, precision):
     assert np.array_equal(a2, b2) and not np.array_equal(a1, a2)
     eager.reset(); graph.reset()
     assert np.array_equal(graph.run(frames.to(DEV)).numpy(), a1)
+
+
+def test_pool_round_trip_at_c3_size():
+    """BASELINE.json config 3 at full size (pool 256 x 12 x 256 x 256, batch 64, + the EC conditioning channel): gather ->
+    scatter into a second pool reproduces exactly the sampled slots and touches nothing else; the appended channel is `extra`."""
+    N, Cp, H, W, B = 256, 12, 256, 256, 64
+    g = torch.Generator(device=DEV).manual_seed(0)
+    pool = torch.rand(N, Cp, H, W, device=DEV, generator=g) - 0.5
+    extra = torch.rand(B, 1, H, W, device=DEV, generator=g)
+    idx = torch.as_tensor(np.random.RandomState(1).choice(N, B, replace=False)).to(DEV)
+    batch = Tr.pool_gather(pool, idx, extra)
+    assert torch.equal(batch[:, :Cp], pool[idx]) and torch.equal(batch[:, Cp:], extra)
+    other = torch.zeros_like(pool)
+    Tr.pool_scatter(other, idx, batch)
+    assert torch.equal(other[idx], pool[idx])
+    untouched = torch.ones(N, dtype=torch.bool, device=DEV)
+    untouched[idx] = False
+    assert float(other[untouched].abs().max()) == 0.0
+    # seed injection replaces exactly the first sample
+    inj = Tr.pool_gather(pool, idx, extra, None, 1)
+    assert float(inj[0, :Cp].abs().max()) == 0.0 and torch.equal(inj[1:], batch[1:]) and torch.equal(inj[0, Cp:], extra[0])

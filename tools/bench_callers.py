@@ -151,6 +151,8 @@ def main():
 
     # the reference's own video size (nca_size 256, video_utils.py:50-52): host bound without the per-frame CUDA graph
     m = nca_b200.DyNCA_EC(C, 3, fc_dim=96, padding_mode="circular", pos_emb=None, perception_scales=[0], device=DEV, precision="bf16")
+    with torch.no_grad():
+        m.w2.weight.mul_(0.1)          # random-init weights: keep the 2400-step stream bounded (a trained model is)
     F = 4 if QUICK else 300
     clip = (torch.rand(F, 3, 256, 256) * 2 - 1).pin_memory()
     res = {}
@@ -184,6 +186,8 @@ def main():
 
     for step_n, F in (((8, 2),) if QUICK else ((8, 24), (256, 3))):
         m = nca_b200.DyNCA_EC(C, 3, fc_dim=96, padding_mode="circular", pos_emb=None, perception_scales=[0], device=DEV, precision="bf16")
+        with torch.no_grad():
+            m.w2.weight.mul_(0.1)
         clip = (torch.rand(F, 3, Hf, Wf) * 2 - 1).pin_memory()
         st = V.FrameStylizer(m, (Hf, Wf), step_n=step_n, seed=1)
 
