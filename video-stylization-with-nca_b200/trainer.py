@@ -123,6 +123,7 @@ class NormalizedAdam(torch.optim.Optimizer):
         if lr < 0.0 or eps < 0.0 or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, norm_eps=norm_eps, normalize=normalize, zero_grads=zero_grads))
+        self._tables = {}
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -153,12 +154,19 @@ class NormalizedAdam(torch.optim.Optimizer):
                 for o in range(0, len(plist), ADAM_MAX_TENSORS):
                     chunk = plist[o:o + ADAM_MAX_TENSORS]
                     n = len(chunk)
-                    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])      # noqa: E731
-                    numel = (C.c_int64 * n)(*[p.numel() for p in chunk])
+                    # the pointer tables are rebuilt only when a storage moved (autograd allocates new .grad tensors after
+                    # zero_grad(set_to_none=True); with zero_grads=True they stay put)
+                    key = tuple(t.data_ptr() for p in chunk for t in (p, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]))
+                    tables = self.__dict__.setdefault("_tables", {})       # not part of the pickled state
+                    cached = tables.get(id(chunk[0]))
+                    if cached is None or cached[0] != key:
+                        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])      # noqa: E731
+                        cached = (key, arr(chunk), arr([p.grad for p in chunk]), arr([self.state[p]["exp_avg"] for p in chunk]),
+                                  arr([self.state[p]["exp_avg_sq"] for p in chunk]), (C.c_int64 * n)(*[p.numel() for p in chunk]))
+                        tables[id(chunk[0])] = cached
                     with torch.cuda.device(chunk[0].device):
                         check(lib.nca_normalized_adam_step(
-                            n, arr(chunk), arr([p.grad for p in chunk]), arr([self.state[p]["exp_avg"] for p in chunk]),
-                            arr([self.state[p]["exp_avg_sq"] for p in chunk]), numel, step, float(group["lr"]),
+                            n, cached[1], cached[2], cached[3], cached[4], cached[5], step, float(group["lr"]),
                             float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]), float(group["norm_eps"]),
                             int(bool(group["normalize"])), int(bool(group["zero_grads"])), _stream()))
         return loss
