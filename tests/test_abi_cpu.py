@@ -81,3 +81,40 @@ def test_module_state_dict_layout():
     assert tuple(cd.seed(2, (8, 16)).shape) == (2, 12, 16, 8)
     c16 = nca_b200.DyNCA_EC(16, 3, fc_dim=128, perception_scales=[0, 1], device=torch.device("cpu"))
     assert tuple(c16.state_dict()["w1.weight"].shape) == (128, 66, 1, 1)
+
+
+def test_callers_argument_checks_and_no_cpu_fallback(lib):
+    """The callers' entry points validate their arguments before touching the device and, like the step, have no
+    CPU path: with host tensors and no GPU they return NCA_ERR_CUDA; the host mirror refuses CPU tensors."""
+    from nca_b200 import trainer as Tr, video as V
+    pool = torch.zeros(4, 3, 8, 8)
+    idx = torch.tensor([0, 1], dtype=torch.int64)
+    out = torch.zeros(2, 3, 8, 8)
+    st = None
+    assert lib.nca_pool_gather(4, 3, 8, 8, pool.data_ptr(), idx.data_ptr(), 2, None, 1, None, 0, None, out.data_ptr(), st) == -1
+    assert b"extra" in lib.nca_last_error()
+    assert lib.nca_pool_gather(4, 3, 8, 8, pool.data_ptr(), idx.data_ptr(), 2, None, 0, None, 3, None, out.data_ptr(), st) == -1
+    assert lib.nca_pool_scatter(4, 3, 8, 8, pool.data_ptr(), idx.data_ptr(), 2, out.data_ptr(), 2, st) == -1      # C < Cp
+    assert lib.nca_pool_dead_flags(4, 3, 8, 8, pool.data_ptr(), idx.data_ptr(), 2, 3, 0.1, out.data_ptr(), st) == -1   # living_dim
+    assert lib.nca_state_to_rgb8(1, 2, 8, 8, pool.data_ptr(), 2.0, out.data_ptr(), st) == -1                    # C < 3
+    assert lib.nca_frame_to_cond_channel(1, 3, 8, 8, pool.data_ptr(), out.data_ptr(), 3, st) == -1              # channel
+    assert lib.nca_overflow_loss(pool.data_ptr(), 16, out.data_ptr(), None, 1.0, None, 0, None, 0, st) == -4    # workspace
+    assert lib.nca_overflow_workspace_bytes() >= 1024
+    ptrs = (C.c_void_p * 1)(pool.data_ptr())
+    numel = (C.c_int64 * 1)(16)
+    assert lib.nca_normalized_adam_step(0, ptrs, ptrs, ptrs, ptrs, numel, 1, 1e-3, 0.9, 0.999, 1e-8, 1e-8, 1, 0, st) == -1
+    assert lib.nca_normalized_adam_step(1, ptrs, ptrs, ptrs, ptrs, numel, 0, 1e-3, 0.9, 0.999, 1e-8, 1e-8, 1, 0, st) == -1   # step
+    assert lib.nca_normalized_adam_step(17, ptrs, ptrs, ptrs, ptrs, numel, 1, 1e-3, 0.9, 0.999, 1e-8, 1e-8, 1, 0, st) == -1
+    if not torch.cuda.is_available():
+        assert lib.nca_pool_gather(4, 3, 8, 8, pool.data_ptr(), idx.data_ptr(), 2, None, 0, None, 0, None, out.data_ptr(), st) == -3
+        assert b"no CPU fallback" in lib.nca_last_error()
+        assert lib.nca_state_to_rgb8(1, 3, 8, 8, pool.data_ptr(), 2.0, out.data_ptr(), st) == -3
+        assert lib.nca_normalized_adam_step(1, ptrs, ptrs, ptrs, ptrs, numel, 1, 1e-3, 0.9, 0.999, 1e-8, 1e-8, 1, 0, st) == -3
+    for call in (lambda: Tr.pool_gather(pool, [0, 1]), lambda: Tr.pool_scatter(pool, [0, 1], out), lambda: Tr.overflow_loss(pool),
+                 lambda: V.state_to_rgb8(pool), lambda: V.rgb_to_grayscale(pool[:, :3])):
+        with pytest.raises(nca_b200.NcaError):
+            call()
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    with pytest.raises(nca_b200.NcaError):
+        nca_b200.NormalizedAdam([p]).step()
