@@ -339,3 +339,24 @@ def test_pool_round_trip_at_c3_size():
     # seed injection replaces exactly the first sample
     inj = Tr.pool_gather(pool, idx, extra, None, 1)
     assert float(inj[0, :Cp].abs().max()) == 0.0 and torch.equal(inj[1:], batch[1:]) and torch.equal(inj[0, Cp:], extra[0])
+
+
+def test_frame_stylizer_steps_per_frame_and_batch():
+    """steps_per_frame > 1 emits one image per block of step_n steps on the same target frame (video_utils.py:70-82); a batch of
+    independent streams [F,B,3,H,W] equals the streams run one by one with the same key (the Philox counter includes b)."""
+    H, W, F = 32, 32, 3
+    m = _ec_model()
+    frames = (torch.rand(F, 2, 3, H, W, generator=torch.Generator().manual_seed(9)) * 2 - 1).to(DEV)
+    st = V.FrameStylizer(m, (H, W), step_n=4, steps_per_frame=2, batch=2, seed=5)
+    got = st.run(frames).clone()
+    assert tuple(got.shape) == (2 * F, 2, H, W, 3)
+    ref = V.FrameStylizer(m, (H, W), step_n=4, steps_per_frame=1, batch=2, seed=5)
+    j = 0
+    for f in range(F):
+        for _ in range(2):
+            assert torch.equal(ref.push(frames[f]).cpu(), got[j]), (f, j)
+            j += 1
+    assert torch.equal(ref.state, st.state)
+    # stream 0 of the batch alone: same key, same b = 0 -> identical frames
+    one = V.FrameStylizer(m, (H, W), step_n=4, steps_per_frame=2, batch=1, seed=5)
+    assert torch.equal(one.run(frames[:, :1])[:, 0], got[:, 0])
