@@ -71,10 +71,11 @@ class DyNCABase(torch.nn.Module):
             size_x, size_y = size, size
         else:
             size_x, size_y = size
+        # zeros are created on the device (the reference builds them on the host and copies: 100 MB per 1080p seed)
         if self.seed_mode == 'zeros':
-            return torch.zeros(n, channels, size_y, size_x).to(self.device)
+            return torch.zeros(n, channels, size_y, size_x, device=self.device)
         elif self.seed_mode == 'center_on':
-            sd = torch.zeros(n, channels, size_y, size_x).to(self.device)
+            sd = torch.zeros(n, channels, size_y, size_x, device=self.device)
             sd[:, :, size_y // 2, size_x // 2] = 1.0
             return sd
         elif self.seed_mode == 'random':

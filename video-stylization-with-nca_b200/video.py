@@ -76,7 +76,7 @@ class FrameStylizer:
         self.slots = torch.zeros(2, batch, self.C, H, W, device=self.dev, dtype=torch.float32)
         self.cur = 0
         self.gray = torch.empty(batch, 1, H, W, device=self.dev) if self.flavour == "cd" and model.conditioning == 'edges' else None
-        self._host = self._dev_out = self._dev_in = self._side = None
+        self._host = self._dev_out = self._dev_in = self._side = self._side_up = None
         self._tdev = torch.zeros(1, device=self.dev, dtype=torch.int32)      # Philox step counter of the graph mode
         self.reset()
 
@@ -187,30 +187,32 @@ class FrameStylizer:
         host = out
         if self._dev_out is None:
             self._dev_out = [torch.empty(self.B, self.H, self.W, 3, device=self.dev, dtype=torch.uint8) for _ in range(2)]
-            self._side = torch.cuda.Stream(self.dev)
+            self._side = torch.cuda.Stream(self.dev)        # downloads
+            self._side_up = torch.cuda.Stream(self.dev)     # uploads: their own stream, so that both directions of the link are busy
         dev_out = self._dev_out
         dev_in = None
         if not frames.is_cuda:
             if self._dev_in is None:
                 self._dev_in = [torch.empty(self.B, 3, self.H, self.W, device=self.dev) for _ in range(2)]
             dev_in = self._dev_in
-        main, side = torch.cuda.current_stream(self.dev), self._side
+        main, side, side_up = torch.cuda.current_stream(self.dev), self._side, self._side_up
         side.wait_stream(main)
+        side_up.wait_stream(main)
         done = [None, None]      # D2H of the frame that used dev_out[k] has finished
         up = [None, None]
         if dev_in is not None:
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side_up):
                 dev_in[0].copy_(frames[0], non_blocking=True)
-                up[0] = torch.cuda.Event(); up[0].record(side)
+                up[0] = torch.cuda.Event(); up[0].record(side_up)
         j = 0
         for f in range(F):
             if dev_in is not None:
                 if f + 1 < F:
                     free = torch.cuda.Event(); free.record(main)          # compute that read dev_in[(f+1)&1] (frame f-1) is queued before
-                    with torch.cuda.stream(side):
-                        side.wait_event(free)
+                    with torch.cuda.stream(side_up):
+                        side_up.wait_event(free)
                         dev_in[(f + 1) & 1].copy_(frames[f + 1], non_blocking=True)
-                        up[(f + 1) & 1] = torch.cuda.Event(); up[(f + 1) & 1].record(side)
+                        up[(f + 1) & 1] = torch.cuda.Event(); up[(f + 1) & 1].record(side_up)
                 main.wait_event(up[f & 1])
                 frame = dev_in[f & 1]
             else:
@@ -227,5 +229,6 @@ class FrameStylizer:
                     done[k] = torch.cuda.Event(); done[k].record(side)
                 j += 1
         main.wait_stream(side)
+        main.wait_stream(side_up)
         side.synchronize()
         return host
