@@ -147,8 +147,8 @@ typedef struct NcaEncDesc {
     float   alive_thr;        /* 0.1 (nca.py:163)                                             */
     float   fire_rate;        /* cell_fire_rate (nca.py:67)                                   */
     float   clamp;            /* 10.0 (nca.py:194)                                            */
-    int32_t precision;        /* NCA_PREC_*: BF16 runs the forward update MLP on tcgen05 (W % 4 == 0,
-                                 alive_thr >= 0; other shapes and the BPTT use the fp32 kernels)      */
+    int32_t precision;        /* NCA_PREC_*: BF16 runs the update MLP of the forward AND of the BPTT on tcgen05
+                                 (enc_tc.cu; W % 4 == 0, alive_thr >= 0; other shapes use the fp32 kernels) */
 } NcaEncDesc;
 
 /* wp [3C,1,3,3] perception_net.weight; wa [hid,3C], ba [hid]; wb [hid,hid], bb [hid]; wc [C,hid]. */

@@ -543,14 +543,7 @@ __global__ void __launch_bounds__(BB_THREADS, 1) dynca_bwd_bf16_kernel(const Dyn
 }
 
 // ---- host launchers -----------------------------------------------------------------------------------
-static int bf16_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+static int bf16_num_sms() { return nca_sm_count(); }
 
 size_t dynca_bf16_weight_bytes(const DyncaGeom& g) {
     Bf16Geom bg;

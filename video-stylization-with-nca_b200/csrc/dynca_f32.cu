@@ -459,15 +459,7 @@ __global__ void nca_philox_mask_kernel(int B, int H, int W, unsigned long long t
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int nca_num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        g_num_sms = n;
-    }
-    return g_num_sms;
-}
+static int nca_num_sms() { return nca_sm_count(); }
 
 template <typename K>
 static int dynca_set_smem(K kernel, size_t bytes) {

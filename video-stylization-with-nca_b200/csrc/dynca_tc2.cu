@@ -14,6 +14,7 @@
 //          D1 = A1 . W1h^T + U . DcB                           = W1h (z_fine + up(z_coarse)) + cond / bias terms
 //   E1   : h = relu(D1) -> bf16 A2 ;  MMA: D2 = A2 . W2^T ;  E2: x' = x + (D2 + b2) * fire, coalesced NCHW store, and
 //          the 2x2 means of x' (the coarse state of the next step) by warp shuffles.
+#include <mutex>
 #include "dynca_tc2.cuh"
 
 struct T2FwdArgs {
@@ -535,9 +536,15 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     const CUtensorMap* tx = (const CUtensorMap*)m->x;
     const CUtensorMap* txc = (const CUtensorMap*)m->xc;
     const CUtensorMap* tcn = (const CUtensorMap*)m->cond;
-    static size_t occ_smem[2] = {0, 0};
-    static int occ_val[2] = {0, 0};
+    // (function attributes are per device and the launchers run on several threads: the cache is per device, under a mutex)
+    static std::mutex occ_mu;
+    static size_t occ_smem_dev[NCA_MAX_DEVICES][2];
+    static int occ_val_dev[NCA_MAX_DEVICES][2];
     const int oi = g.ns == 2 ? 1 : 0;
+    const int dev = nca_device_ordinal() % NCA_MAX_DEVICES;
+    std::unique_lock<std::mutex> occ_lock(occ_mu);
+    size_t* const occ_smem = occ_smem_dev[dev];
+    int* const occ_val = occ_val_dev[dev];
     if (occ_val[oi] == 0 || occ_smem[oi] != smem) {
         int o = 0;
         if (g.ns == 2) {
@@ -554,6 +561,7 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
         if (getenv("NCA_T2_DBG")) fprintf(stderr, "tc2 fwd: ns %d smem %zu -> %d CTAs per SM (registers, shared memory)\n", g.ns, smem, occ_val[oi]);
     }
     int occ = occ_val[oi];
+    occ_lock.unlock();
     if (occ > (int)(512u / tcols)) occ = (int)(512u / tcols);
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;

@@ -446,12 +446,5 @@ static inline int t2_occupancy_by_regs(K kernel, int threads) {
     return occ < 1 ? 1 : occ;
 }
 
-static inline int t2_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+static inline int t2_num_sms() { return nca_sm_count(); }
 

@@ -485,14 +485,7 @@ static int enc_check_device() {
     }
     return NCA_OK;
 }
-static int enc_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+static int enc_num_sms() { return nca_sm_count(); }
 static FireMask enc_mask(const NcaEncDesc* d, const EncGeom& g, const float* masks, uint64_t seed, int t0, int t) {
     FireMask m;
     m.supplied = d->mask_mode == NCA_MASK_SUPPLIED ? masks + (size_t)t * g.B * g.H * g.W : nullptr;

@@ -12,6 +12,7 @@
 //   p     : fp32, 4 vertically adjacent cells x 1 channel per thread, 27 learned taps -> A1 [128 x K1] bf16 with
 //           k' = 4c + filter (slot 3 of every channel is zero), then the bias chunk [1, 1, 0 ..] (ba as bf16 hi + lo)
 //   MMA   : D1 = A1.Wa'^T -> relu -> A2 ; D2 = A2.Wb^T -> + bb, relu -> A3 ; D3 = A3.Wc^T -> x1 = x + fire * D3
+#include <mutex>
 #include "dynca_tc2.cuh"
 
 #define ET2_NTHREADS 288
@@ -414,8 +415,13 @@ int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void*
     a.tl = t2_make_tiles(d->B, d->H, d->W);
     const size_t smem = etc_smem(a.g).total;
     // co-resident CTAs: registers, shared memory (once per shared-memory size), TMEM (128 columns each)
-    static size_t occ_smem = 0;
-    static int occ_val = 0;
+    static std::mutex occ_mu;
+    static size_t occ_smem_dev[NCA_MAX_DEVICES];
+    static int occ_val_dev[NCA_MAX_DEVICES];
+    const int dev = nca_device_ordinal() % NCA_MAX_DEVICES;
+    std::unique_lock<std::mutex> occ_lock(occ_mu);
+    size_t& occ_smem = occ_smem_dev[dev];
+    int& occ_val = occ_val_dev[dev];
     if (occ_val == 0 || occ_smem != smem) {
         int o = 0;
         NCA_CUDA_OK(cudaFuncSetAttribute(enc_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -426,6 +432,7 @@ int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void*
         occ_smem = smem;
     }
     int occ = occ_val;
+    occ_lock.unlock();
     if (occ > 4) occ = 4;
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;

@@ -14,6 +14,21 @@ void nca_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void nca_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int nca_device_ordinal() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev;
+}
+int nca_sm_count() {
+    static std::atomic<int> cache[NCA_MAX_DEVICES];      // zero-initialised; racing writers store the same value
+    const int dev = nca_device_ordinal();
+    int n = dev < NCA_MAX_DEVICES ? cache[dev].load(std::memory_order_relaxed) : 0;
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (dev < NCA_MAX_DEVICES) cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 
 extern "C" {
 
@@ -138,9 +153,16 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
     NCA_CHECK_ARG(w && w->w1 && w->b1 && w->w2 && w->b2, "weights are NULL");
     NCA_CHECK_ARG(states != nullptr && T >= 0, "states is NULL or T < 0");
     NCA_CHECK_ARG(NCA_ALIGNED16(states) && NCA_ALIGNED16(workspace) && NCA_ALIGNED16(coarse_hist), "states / coarse_hist / workspace must be 16-byte aligned");
-    if (workspace == nullptr || workspace_bytes < nca_dynca_workspace_bytes(d, 0)) {
-        nca_set_error("workspace too small: %zu < %zu", workspace_bytes, nca_dynca_workspace_bytes(d, 0));
-        return NCA_ERR_WORKSPACE;
+    {
+        const size_t need = nca_dynca_workspace_bytes(d, 0);
+        if (need == 0) {      // 0 = "this description cannot run" (e.g. a tensor-core precision with fc % 16 != 0 or more than 6 cond channels)
+            nca_set_error("unsupported geometry for precision %d (fc %d, cond channels %d)", d->precision, g.fc, g.cc);
+            return NCA_ERR_UNSUPPORTED;
+        }
+        if (workspace == nullptr || workspace_bytes < need) {
+            nca_set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+            return NCA_ERR_WORKSPACE;
+        }
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int variant = dynca_variant(d, g, 0);
@@ -206,9 +228,16 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         NCA_CHECK_ARG(g_taps[i] && tap_steps[i] >= 1 && tap_steps[i] <= T && (i == 0 || tap_steps[i] > tap_steps[i - 1]),
                       "tap_steps must be strictly increasing in 1..T with non-NULL gradients (entry %d)", i);
     NCA_CHECK_ARG(NCA_ALIGNED16(states) && NCA_ALIGNED16(workspace), "states / workspace must be 16-byte aligned");
-    if (workspace == nullptr || workspace_bytes < nca_dynca_workspace_bytes(d, 1)) {
-        nca_set_error("workspace too small: %zu < %zu", workspace_bytes, nca_dynca_workspace_bytes(d, 1));
-        return NCA_ERR_WORKSPACE;
+    {
+        const size_t need = nca_dynca_workspace_bytes(d, 1);
+        if (need == 0) {
+            nca_set_error("unsupported geometry for precision %d (fc %d, cond channels %d)", d->precision, g.fc, g.cc);
+            return NCA_ERR_UNSUPPORTED;
+        }
+        if (workspace == nullptr || workspace_bytes < need) {
+            nca_set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+            return NCA_ERR_WORKSPACE;
+        }
     }
     // NCA_PREC_BF16: tcgen05 BPTT kernels when the shape is supported (variant 2: 8x16 tiles + TMA, variant 1: 4x32 tiles),
     // else the fp32 kernel

@@ -9,14 +9,7 @@ int nca_check_device();   // nca_api.cu
 
 namespace {
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+int sm_count() { return nca_sm_count(); }
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Pool gather / scatter.  One (sample, channel) plane per blockIdx.y; blockIdx.x strides over the plane in float4.

@@ -8,6 +8,10 @@
 // ---- host-side error / launch accounting (nca_api.cu owns the storage) ---------------------
 void nca_set_error(const char* fmt, ...);
 void nca_count_launch(int n = 1);
+// SM count / ordinal of the CURRENT device (cached per device: one process may drive several GPUs, from several threads)
+int nca_sm_count();
+int nca_device_ordinal();
+#define NCA_MAX_DEVICES 64
 #define NCA_CHECK_ARG(cond, ...)                     \
     do {                                             \
         if (!(cond)) {                               \

@@ -46,9 +46,10 @@ class DyNCA(DyNCABase):
 
     def forward(self, x, update_rate=0.5, return_perception=False, cond_img=None, *, masks=None, seed=None):
         kind, cc, cond = self._cond(cond_img)
-        if return_perception:
-            cm = self.cond_layer(x) if self.conditioning == 'pos_emb' else cond
-            y_percept = self.perceive_multiscale(x, cond_mat=cm)
+        if return_perception:      # a diagnostic output: returned detached (no caller of the reference differentiates it)
+            with torch.no_grad():
+                cm = self.cond_layer(x) if self.conditioning == 'pos_emb' else cond
+                y_percept = self.perceive_multiscale(x, cond_mat=cm)
         x, _ = self._rollout(x, 1, update_rate, kind, cc, cond, masks, seed, False)
         if return_perception:
             return x, self.to_rgb(x), y_percept

@@ -37,8 +37,9 @@ class DyNCA(DyNCABase):
 
     def forward(self, x, update_rate=0.5, return_perception=False, *, masks=None, seed=None):
         kind, cc = self._kind()
-        if return_perception:
-            y_percept = self.perceive_multiscale(x, pos_emb_mat=self.pos_emb_2d(x) if self.pos_emb_2d else None)
+        if return_perception:      # a diagnostic output: returned detached (no caller of the reference differentiates it)
+            with torch.no_grad():
+                y_percept = self.perceive_multiscale(x, pos_emb_mat=self.pos_emb_2d(x) if self.pos_emb_2d else None)
         x, _ = self._rollout(x, 1, update_rate, kind, cc, None, masks, seed, False)
         if return_perception:
             return x, self.to_rgb(x), y_percept

@@ -73,6 +73,10 @@ def dynca_kernel_variant(cfg, B, H, W, backward=False):
 def dynca_perceive(cfg, x, cond=None):
     """DyNCA.perceive_multiscale (dynca.py:98-111) -> [B, 4C+cc, H, W]."""
     _need_cuda(x, cond)
+    if torch.is_grad_enabled() and (x.requires_grad or (cond is not None and cond.requires_grad)):
+        # the reference returns a differentiable tensor here; this entry point has no backward, so refuse instead of
+        # silently cutting the graph (the rollouts, which do have a BPTT, never come through here)
+        raise NcaError("perceive_* is forward-only on the CUDA path: call it under torch.no_grad() or on detached tensors")
     lib = load_library()
     x, cond = _c(x), _c(cond)
     B, Cc, H, W = x.shape
@@ -165,7 +169,9 @@ class _DyncaRollout(torch.autograd.Function):
         handle.hist = hist
         ctx.set_materialize_grads(False)
         token = x0.new_zeros(())
-        return hist[T], token
+        # a copy, not a view: the BPTT recomputes from `hist`, which autograd's version counters do not cover, so an in-place
+        # edit of the returned state (clamp_, overwriting the conditioning channel) must not reach it (1/T of the history)
+        return hist[T].clone(), token
 
     @staticmethod
     def backward(ctx, g_final, _g_token):
@@ -309,7 +315,7 @@ class _EncRollout(torch.autograd.Function):
         ctx.w_shapes = tuple(t.shape for t in (wp, wa, ba, wb, bb, wc))
         ctx.save_for_backward(goalc, masks, *ws)
         ctx.hist, ctx.life = hist, life
-        return hist[T]
+        return hist[T].clone()      # a copy: see _DyncaRollout.forward
 
     @staticmethod
     def backward(ctx, g_final):
