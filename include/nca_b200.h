@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NCA_B200_ABI_VERSION 5
+#define NCA_B200_ABI_VERSION 6
 
 enum { NCA_OK = 0, NCA_ERR_ARG = -1, NCA_ERR_UNSUPPORTED = -2, NCA_ERR_CUDA = -3, NCA_ERR_WORKSPACE = -4 };
 
@@ -36,7 +36,12 @@ enum { NCA_COND_NONE = 0,   /* pos_emb=None / conditioning=None                 
        NCA_COND_TENSOR = 2  /* caller-supplied [B,cc,H,W] (CD: EdgeExtractor output, cc=3)        */ };
 /* arithmetic of the update MLP */
 enum { NCA_PREC_FP32 = 0,   /* CUDA-core FFMA, parity 1e-5 per step                      */
-       NCA_PREC_BF16 = 1    /* tcgen05 BF16 operands, fp32 accumulate in TMEM, parity 1e-2 */ };
+       NCA_PREC_BF16 = 1,   /* tcgen05 BF16 operands, fp32 accumulate in TMEM, parity 1e-2 */
+       NCA_PREC_F16X3 = 2   /* tcgen05, every operand split into FP16 hi + lo (~22 significant bits) and every product
+                               issued as Ah.Bh + Al.Bh + Ah.Bl (fp32 accumulate): fp32-grade parity (state 1e-5,
+                               gradients 1e-4) on the tensor cores.  Weights are pre-scaled by 2^8 and gradient operands
+                               by a per-launch power of two (undone exactly), so |w| < 255 and |perception|, |hidden|
+                               < 65504 are required (beyond: NaN).  DyNCA only (ConditionedNCA: treated as FP32) */ };
 /* fire mask source */
 enum { NCA_MASK_SUPPLIED = 0, /* float [T,B,1,H,W], 1 = fire (parity runs)                 */
        NCA_MASK_PHILOX = 1    /* in-kernel Philox4x32-10 keyed on (seed, t0+t, b, y, x)    */ };
@@ -124,7 +129,9 @@ size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward);
 
 /* Which step kernel a description dispatches to (tests / reports): 0 = fp32 CUDA cores, 1 = tcgen05 with 4x32 tiles
  * and cp.async staging (any shape), 2 = tcgen05 with 8x16 tiles, TMA staging and the coarse scale on the tensor
- * cores (W % 4 == 0, W % 8 == 0 for two scales, fc % 32 == 0).  Negative = invalid description. */
+ * cores (W % 4 == 0, W % 8 == 0 for two scales, fc % 32 == 0), 3 = the 4x32-tile tcgen05 kernels with split-precision
+ * (hi + lo) operands (NCA_PREC_F16X3; falls back to 0 when the doubled operand images exceed shared memory).
+ * Negative = invalid description. */
 int nca_dynca_kernel_variant(const NcaDyncaDesc* d, int32_t backward);
 
 /* The Philox fire mask the kernels generate, materialised as float [T,B,1,H,W] (tests / debugging).

@@ -227,6 +227,46 @@ def _hilo(t):
     return hi + bf16r(t - hi)
 
 
+# --------------------------------------------------------------------------------------
+# "MLP in BF16" stated from the MATH of dynca.py:113-123, not from any kernel: the operands of the two 1x1-conv GEMMs
+# (perception vector, W1, hidden layer, W2) are rounded to bfloat16, products accumulate in fp32, everything else
+# (perception, cond inputs, biases, mask, residual) is fp32; the backward is torch autograd with the roundings as
+# straight-through estimators (so gradients are the fp32 gradients of the rounded forward, with no rounding of their own).
+# This is the independent yardstick for the tcgen05 path (BASELINE.json north_star: "1e-2 when the MLP runs in BF16"):
+# it knows nothing about tiles, operand layouts or where the kernels round in the backward pass.  The kernel-mirroring
+# emulation further below (dynca_bf16emu_*) is a regression tool only.
+# --------------------------------------------------------------------------------------
+class _RoundBf16STE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def dynca_step_bf16ops(x, w1, b1, w2, b2, mask, scales=(0,), mode="circular", cond=None):
+    q = _RoundBf16STE.apply
+    C = x.shape[1]
+    z = perceive_multiscale(x, scales, mode, None)
+    pre = torch.einsum("jk,bkhw->bjhw", q(w1[:, :4 * C]), q(z)) + b1[None, :, None, None]
+    if cond is not None:      # cond inputs stay fp32 (the reference feeds them unrounded); their weights are MLP weights
+        pre = pre + torch.einsum("jk,bkhw->bjhw", q(w1[:, 4 * C:]), cond)
+    h = torch.relu(pre)
+    y = torch.einsum("cj,bjhw->bchw", q(w2), q(h)) + b2[None, :, None, None]
+    return x + y * mask
+
+
+def dynca_rollout_bf16ops(x, w1, b1, w2, b2, masks, scales=(0,), mode="circular", cond=None, keep=False):
+    hist = [x]
+    for t in range(masks.shape[0]):
+        x = dynca_step_bf16ops(x, w1, b1, w2, b2, masks[t], scales, mode, cond)
+        if keep:
+            hist.append(x)
+    return (x, hist) if keep else x
+
+
 def perceive_coarse(x, mode):
     """[id | sobel_x | sobel_y | lap] of the 2x2-mean coarse state, NOT upsampled: [B,4C,H/2,W/2]."""
     xc = down2(x)

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_workspace(lib):
-    assert lib.nca_abi_version() == 5
+    assert lib.nca_abi_version() == 6
     d = _lib.DyncaDesc(8, 16, 256, 256, 128, _lib.NCA_COND_CPE, 2, 1, 2, 0, _lib.NCA_MASK_PHILOX, 0.5)
     fwd = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
     bwd = lib.nca_dynca_workspace_bytes(C.byref(d), 1)

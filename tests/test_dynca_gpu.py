@@ -3,7 +3,11 @@ the unmodified reference and against the CPU oracle on seeded inputs.
 
 Tolerances (fp32 MLP): per-step / rollout state 1e-5 relative (max-abs / max-abs), gradients 1e-4 relative
 (BASELINE.json north_star); trained-weight 24-step cases use 2e-3 on gradients because fp32 summation order
-alone moves them by 5e-4 between two CPU evaluations (see tests/test_oracle_golden.py)."""
+alone moves them by 5e-4 between two CPU evaluations (see tests/test_oracle_golden.py).
+
+Every parity case runs twice with the SAME tolerances: precision "fp32" (CUDA-core FFMA kernels) and "f16x3" (the
+update MLP of forward and BPTT on tcgen05 with split-precision bf16 hi + lo operands, NCA_PREC_F16X3) - the
+tensor-core mode that meets the fp32-grade bars."""
 import numpy as np
 import pytest
 import torch
@@ -35,10 +39,22 @@ def build_model(m, t, precision="fp32"):
     return model
 
 
+FP32_GRADE = ["fp32", "f16x3"]
+
+
+def _expect_variant(cfg, B, H, W, precision):
+    """f16x3 must really dispatch to the tensor-core kernels (variant 3), fp32 to the CUDA-core ones (0)"""
+    want = 3 if precision == "f16x3" else 0
+    assert Fn.dynca_kernel_variant(cfg, B, H, W) == want and Fn.dynca_kernel_variant(cfg, B, H, W, backward=True) == want
+
+
+@pytest.mark.parametrize("precision", FP32_GRADE)
 @pytest.mark.parametrize("name", DYNCA_CASES)
-def test_golden_case(name):
+def test_golden_case(name, precision):
     t, m = load_case(name)
-    model = build_model(m, t)
+    model = build_model(m, t, precision=precision)
+    kind, cc = {"cpe": (_lib.NCA_COND_CPE, 2), "edges": (_lib.NCA_COND_TENSOR, 3), None: (_lib.NCA_COND_NONE, 0)}[m["cond"]]
+    _expect_variant(Fn.DyncaConfig(m["C"], m["fc"], m["pad"], m["scales"], kind, cc, precision=precision), m["B"], m["H"], m["W"], precision)
     x0 = t["x0"].to(DEV).requires_grad_(True)
     masks = t["masks"].to(DEV)
     kwargs = dict(cond_img=t["cond_img"].to(DEV)) if m["flavour"] == "cd" and m["cond"] == "edges" else {}
@@ -120,8 +136,9 @@ ORACLE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("precision", FP32_GRADE)
 @pytest.mark.parametrize("case", ORACLE_CASES, ids=lambda c: "B%d_C%d_fc%d_%dx%d_T%d_%s_s%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], len(c[7]), c[8]))
-def test_against_oracle_seeded(case):
+def test_against_oracle_seeded(case, precision):
     B, C, fc, H, W, T, pad, scales, cond = case
     g = torch.Generator().manual_seed(1234 + ORACLE_CASES.index(case))   # fixed inputs (hash() of a tuple with str is per-process)
     cc = {"cpe": 2, None: 0, "tensor": 3}[cond]
@@ -142,7 +159,8 @@ def test_against_oracle_seeded(case):
     lo.backward()
     # CUDA path through the functional API
     kind = {"cpe": _lib.NCA_COND_CPE, None: _lib.NCA_COND_NONE, "tensor": _lib.NCA_COND_TENSOR}[cond]
-    cfg = Fn.DyncaConfig(C, fc, pad, scales, kind, cc)
+    cfg = Fn.DyncaConfig(C, fc, pad, scales, kind, cc, precision=precision)
+    _expect_variant(cfg, B, H, W, precision)
     pg = [p.clone().to(DEV).requires_grad_(True) for p in (x0, w1, b1, w2, b2)]
     fg, taps = Fn.dynca_rollout(cfg, pg[0], pg[1], pg[2], pg[3], pg[4], T, 0.5,
                                 cond=cond_t.to(DEV) if cond == "tensor" else None, masks=masks.to(DEV), return_taps=True)

@@ -11,7 +11,7 @@ _LIB = None
 
 NCA_PAD = {"constant": 0, "zeros": 0, "circular": 1, "replicate": 2, "reflect": 3}
 NCA_COND_NONE, NCA_COND_CPE, NCA_COND_TENSOR = 0, 1, 2
-NCA_PREC = {"fp32": 0, "bf16": 1}
+NCA_PREC = {"fp32": 0, "bf16": 1, "f16x3": 2}
 NCA_MASK_SUPPLIED, NCA_MASK_PHILOX = 0, 1
 
 
@@ -96,7 +96,7 @@ def load_library():
     lib.nca_overflow_loss.argtypes = [P, SZ, P, P, F, P, I, P, SZ, P]
     lib.nca_frame_to_cond_channel.argtypes = [I, I, I, I, P, P, I, P]
     lib.nca_state_to_rgb8.argtypes = [I, I, I, I, P, F, P, P]
-    if lib.nca_abi_version() != 5:
+    if lib.nca_abi_version() != 6:
         raise NcaError("libnca_b200.so ABI version mismatch")
     _LIB = lib
     return lib

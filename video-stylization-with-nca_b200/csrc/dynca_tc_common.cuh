@@ -3,6 +3,7 @@
 // and the geometry of the bf16 operand images.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "dynca_tile.cuh"
 #include "nca_internal.h"
 
@@ -109,6 +110,56 @@ __device__ __forceinline__ uint4 dynca_cond_chunk(const DyncaGeom& g, const floa
     uint4 v;
     v.x = pack_bf16(cv[0], cv[1]); v.y = pack_bf16(cv[2], cv[3]); v.z = pack_bf16(cv[4], cv[5]); v.w = pack_bf16(cv[6], cv[7]);
     return v;
+}
+// split precision (NCA_PREC_F16X3): v = hi + lo with hi = fp16(v), lo = fp16(v - hi), i.e. ~22 significant bits per operand
+// (bf16 pairs give 16, which measurably misses the 1e-5 bar); a product A.B is then evaluated as Ah.Bh + Al.Bh + Ah.Bl with fp32
+// accumulation (the Al.Bl term, 2^-22 relative, is dropped).  fp16 has 5 exponent bits, so the operands are kept in range by
+// exact power-of-two scales: weight images x 2^8 (NCA_X3_WSCALE; |w| < 255), gradient operands x a per-launch scale that brings
+// max|g| to [32, 64); perception / hidden values are used as they are (|v| < 65504: beyond it the step yields NaN, loudly).
+#define NCA_X3_WSCALE 256.0f
+#define NCA_X3_WINV (1.0f / 256.0f)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// instruction descriptors for kind::f16 with fp16 operands (formats 0), K-major / MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(int M, int N) { return umma_idesc_f16(M, N) | (1u << 15) | (1u << 16); }
+// gradient-operand scale of a launch from max|g| (device scalar written by dynca_absmax_kernel): 2^k with max * 2^k in [32, 64)
+__device__ __forceinline__ float nca_x3_gscale(float gmax) {
+    if (!(gmax > 0.0f) || !(gmax < 3.0e38f)) return 1.0f;
+    int e;
+    frexpf(gmax, &e);                       // gmax = f * 2^e, f in [0.5, 1)
+    e = 6 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return exp2f((float)e);
+}
+// the cond chunk as hi / lo images: same slots as dynca_cond_chunk; without room for the lo slots (cc > 3) the raw value goes
+// into the hi slot and its residual into the lo image
+__device__ __forceinline__ void dynca_cond_chunk_x3(const DyncaGeom& g, const float* __restrict__ cond, int b, int gy, int gx, bool inimg,
+                                                    uint4& hi, uint4& lo) {
+    float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (inimg) {
+        const bool split = dynca_cond_split(g.cc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int src = i < g.cc ? i : ((split && i >= g.cc + 2 && i < 2 * g.cc + 2) ? i - g.cc - 2 : -1);
+            if (src >= 0) {
+                float raw;
+                if (g.cond_kind == NCA_COND_CPE) raw = (src == 0) ? dynca_cpe(gy, g.H, g.cpe_oh) : dynca_cpe(gx, g.W, g.cpe_ow);
+                else raw = __ldg(cond + ((size_t)(b * g.cc + src) * g.H + gy) * g.W + gx);
+                const float h = __bfloat162float(__float2bfloat16_rn(raw));
+                cv[i] = i < g.cc ? (split ? h : raw) : raw - h;
+            } else if (i == g.cc || i == g.cc + 1) cv[i] = 1.0f;
+        }
+    }
+    split_f16x2(cv[0], cv[1], hi.x, lo.x); split_f16x2(cv[2], cv[3], hi.y, lo.y);
+    split_f16x2(cv[4], cv[5], hi.z, lo.z); split_f16x2(cv[6], cv[7], hi.w, lo.w);
 }
 // reference W1 column (or -1 = none, -2 = b1 hi, -3 = b1 lo) feeding slot s of the cond chunk
 __host__ __device__ __forceinline__ int dynca_cond_slot_src(int cc, int s) {

@@ -469,7 +469,7 @@ static int enc_make_geom(const NcaEncDesc* d, EncGeom* g) {
     NCA_CHECK_ARG(d->hid == ENC_HID, "ConditionedNCA: hidden width must be 64 (nca.py:40-46), got %d", d->hid);
     NCA_CHECK_ARG(d->living_dim < d->C, "living_dim=%d out of range", d->living_dim);
     NCA_CHECK_ARG(d->mask_mode == NCA_MASK_SUPPLIED || d->mask_mode == NCA_MASK_PHILOX, "bad mask_mode");
-    NCA_CHECK_ARG(d->precision == NCA_PREC_FP32 || d->precision == NCA_PREC_BF16, "bad precision %d", d->precision);
+    NCA_CHECK_ARG(d->precision == NCA_PREC_FP32 || d->precision == NCA_PREC_BF16 || d->precision == NCA_PREC_F16X3, "bad precision %d", d->precision);
     NCA_CHECK_ARG((long long)d->H * d->W < (1ll << 31), "H*W too large");
     g->B = d->B; g->C = d->C; g->H = d->H; g->W = d->W; g->liv = d->living_dim < 0 ? -1 : d->living_dim;
     g->thr = d->alive_thr; g->clampv = d->clamp;

@@ -65,14 +65,19 @@ static FireMask make_mask(const NcaDyncaDesc* d, const DyncaGeom& g, const float
 static int check_common(const NcaDyncaDesc* d, DyncaGeom* g, const float* cond, const float* masks) {
     int rc = dynca_make_geom(d, g);
     if (rc) return rc;
-    NCA_CHECK_ARG(d->precision == NCA_PREC_FP32 || d->precision == NCA_PREC_BF16, "bad precision %d", d->precision);
+    NCA_CHECK_ARG(d->precision == NCA_PREC_FP32 || d->precision == NCA_PREC_BF16 || d->precision == NCA_PREC_F16X3, "bad precision %d", d->precision);
     NCA_CHECK_ARG(g->cond_kind != NCA_COND_TENSOR || cond != nullptr, "cond_kind == TENSOR needs a cond pointer");
     NCA_CHECK_ARG(d->mask_mode != NCA_MASK_SUPPLIED || masks != nullptr, "mask_mode == SUPPLIED needs a masks pointer");
     return check_device();
 }
 
-// kernel variant of a description: 0 fp32, 1 tcgen05 (4x32 tiles, cp.async), 2 tcgen05 (8x16 tiles, TMA)
+// kernel variant of a description: 0 fp32 CUDA cores, 1 tcgen05 (4x32 tiles, cp.async), 2 tcgen05 (8x16 tiles, TMA),
+// 3 tcgen05 with split-precision operands (NCA_PREC_F16X3: the 4x32-tile kernels with hi + lo images)
 static int dynca_variant(const NcaDyncaDesc* d, const DyncaGeom& g, int backward) {
+    if (d->precision == NCA_PREC_F16X3) {
+        if (backward) return dynca_bf16_bwd_supported(g, true) ? 3 : 0;
+        return dynca_bf16_supported(g, true) ? 3 : 0;
+    }
     if (d->precision != NCA_PREC_BF16) return 0;
     if (backward) return dynca_tc2_bwd_supported(g) ? 2 : (dynca_bf16_bwd_supported(g) ? 1 : 0);
     return dynca_tc2_supported(g) ? 2 : 1;
@@ -80,7 +85,7 @@ static int dynca_variant(const NcaDyncaDesc* d, const DyncaGeom& g, int backward
 int nca_dynca_kernel_variant(const NcaDyncaDesc* d, int32_t backward) {
     DyncaGeom g;
     if (dynca_make_geom(d, &g)) return -1;
-    if (d->precision != NCA_PREC_FP32 && d->precision != NCA_PREC_BF16) return -1;
+    if (d->precision != NCA_PREC_FP32 && d->precision != NCA_PREC_BF16 && d->precision != NCA_PREC_F16X3) return -1;
     return dynca_variant(d, g, backward);
 }
 
@@ -92,10 +97,11 @@ size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward) {
     size_t n = dynca_f32_weight_floats(g);
     if (backward) n += dynca_f32_grad_floats(g) + 2 * nca_align_up((size_t)g.B * g.C * g.H * g.W, 64);
     size_t bytes = n * sizeof(float);
-    if (d->precision == NCA_PREC_BF16) {
-        size_t b = backward ? dynca_bf16_bwd_weight_bytes(g) : dynca_bf16_weight_bytes(g);
+    if (d->precision == NCA_PREC_BF16 || d->precision == NCA_PREC_F16X3) {
+        const bool x3 = d->precision == NCA_PREC_F16X3;
+        size_t b = backward ? dynca_bf16_bwd_weight_bytes(g, x3) : dynca_bf16_weight_bytes(g, x3);
         if (b == 0) return 0;
-        const size_t b2 = backward ? dynca_tc2_bwd_weight_bytes(g) : dynca_tc2_weight_bytes(g);
+        const size_t b2 = x3 ? 0 : (backward ? dynca_tc2_bwd_weight_bytes(g) : dynca_tc2_weight_bytes(g));
         // coarse slots: forward 2 (ping-pong states); backward 3 (coarse state of the step + 2 coarse-gradient buffers)
         bytes += (b > b2 ? b : b2) + (backward ? 3 : 2) * dynca_bf16_coarse_floats(g) * sizeof(float);
     }
@@ -139,7 +145,7 @@ int nca_philox_mask_at(int32_t B, int32_t H, int32_t W, float rate, int32_t enc,
 size_t nca_dynca_op_hist_bytes(const NcaDyncaDesc* d, int32_t T) {
     DyncaGeom g;
     if (d == nullptr || T <= 0 || dynca_make_geom(d, &g)) return 0;
-    if (d->precision != NCA_PREC_BF16 && d->precision != NCA_PREC_FP32) return 0;
+    if (d->precision != NCA_PREC_BF16) return 0;
     if (dynca_variant(d, g, 0) != 2 || dynca_variant(d, g, 1) != 2) return 0;
     return dynca_tc2_op_hist_bytes(g, T);
 }
@@ -166,13 +172,16 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int variant = dynca_variant(d, g, 0);
+    const bool x3 = d->precision == NCA_PREC_F16X3;
+    const bool gen1 = variant == 1 || variant == 3;       // the 4x32-tile kernels (variant 3: with hi + lo operand images)
     float* wsW = (float*)workspace;
     void* wsB = (uint8_t*)workspace + dynca_f32_weight_floats(g) * sizeof(float);
-    const size_t imgb = dynca_bf16_weight_bytes(g) > dynca_tc2_weight_bytes(g) ? dynca_bf16_weight_bytes(g) : dynca_tc2_weight_bytes(g);
+    const size_t imgb = x3 ? dynca_bf16_weight_bytes(g, true)
+                           : (dynca_bf16_weight_bytes(g) > dynca_tc2_weight_bytes(g) ? dynca_bf16_weight_bytes(g) : dynca_tc2_weight_bytes(g));
     float* wsXc = variant ? (float*)((uint8_t*)wsB + imgb) : nullptr;      // 2 coarse slots
     const size_t n = (size_t)g.B * g.C * g.H * g.W, nc = dynca_bf16_coarse_floats(g);
     if (T == 0) return NCA_OK;
-    rc = variant == 2 ? dynca_tc2_prep_weights(g, w, wsB, s) : (variant == 1 ? dynca_bf16_prep_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s));
+    rc = variant == 2 ? dynca_tc2_prep_weights(g, w, wsB, s) : (gen1 ? dynca_bf16_prep_weights(g, w, wsB, s, x3) : dynca_f32_prep_weights(g, w, wsW, s));
     if (rc) return rc;
     // coarse states (two perception scales on the tensor-core paths): a history when the caller keeps one, else ping-pong
     const bool chist = keep_history && coarse_hist != nullptr && g.ns == 2;
@@ -200,9 +209,9 @@ int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const flo
             rc = dynca_tc2_forward_step(g, wsB, &maps, si, xin, xout, ci, g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr,
                                         need_next ? cbase + (size_t)co * cstride : nullptr, cond, fm, s, t > 0,
                                         ohist ? (uint8_t*)op_hist + (size_t)t * op_step : nullptr);
-        } else if (variant == 1) {
+        } else if (gen1) {
             float* xc = g.ns == 2 ? cbase + (size_t)ci * cstride : nullptr;
-            rc = dynca_bf16_forward_step(g, wsB, xc, xin, xout, cond, fm, s);
+            rc = dynca_bf16_forward_step(g, wsB, xc, xin, xout, cond, fm, s, x3);
             if (!rc && chist && t + 1 == T) rc = dynca_bf16_coarsen(g, xout, cbase + (size_t)co * cstride, s);
         } else {
             rc = dynca_f32_forward_step(g, wsW, xin, xout, cond, fm, s);
@@ -243,16 +252,18 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
     // else the fp32 kernel
     const int variant = dynca_variant(d, g, 1);
     const bool bf16 = variant != 0;
+    const bool x3 = d->precision == NCA_PREC_F16X3;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)g.B * g.C * g.H * g.W, nb = n * sizeof(float);
     float* wsW = (float*)workspace;
     float* wsG = wsW + dynca_f32_weight_floats(g);
     float* gbuf[2] = {wsG + dynca_f32_grad_floats(g), wsG + dynca_f32_grad_floats(g) + nca_align_up(n, 64)};
     void* wsB = (void*)(gbuf[1] + nca_align_up(n, 64));
-    const size_t imgb = dynca_bf16_bwd_weight_bytes(g) > dynca_tc2_bwd_weight_bytes(g) ? dynca_bf16_bwd_weight_bytes(g) : dynca_tc2_bwd_weight_bytes(g);
+    const size_t imgb = x3 ? dynca_bf16_bwd_weight_bytes(g, true)
+                           : (dynca_bf16_bwd_weight_bytes(g) > dynca_tc2_bwd_weight_bytes(g) ? dynca_bf16_bwd_weight_bytes(g) : dynca_tc2_bwd_weight_bytes(g));
     float* wsXc = (float*)((uint8_t*)wsB + imgb);
     const size_t nc = dynca_bf16_coarse_floats(g), ncx = (size_t)g.B * g.C * (g.H / 2) * (g.W / 2);
-    rc = variant == 2 ? dynca_tc2_prep_bwd_weights(g, w, wsB, s) : (variant == 1 ? dynca_bf16_prep_bwd_weights(g, w, wsB, s) : dynca_f32_prep_weights(g, w, wsW, s));
+    rc = variant == 2 ? dynca_tc2_prep_bwd_weights(g, w, wsB, s) : (bf16 ? dynca_bf16_prep_bwd_weights(g, w, wsB, s, x3) : dynca_f32_prep_weights(g, w, wsW, s));
     if (rc) return rc;
     NCA_CUDA_OK(cudaMemsetAsync(wsG, 0, dynca_f32_grad_floats(g) * sizeof(float), s));
     int ti = n_taps - 1;   // taps are consumed from the last step backwards
@@ -311,7 +322,7 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         const float* tap = nullptr;   // gradient injected at states[t+1]
         if (ti >= 0 && tap_steps[ti] == t + 1) tap = g_taps[ti--];
         const float* xc_t = (coarse_hist && g.ns == 2) ? coarse_hist + (size_t)t * g.B * g.C * (g.H / 2) * (g.W / 2) : nullptr;
-        rc = bf16 ? dynca_bf16_backward_step(g, wsB, wsXc, xc_t, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s)
+        rc = bf16 ? dynca_bf16_backward_step(g, wsB, wsXc, xc_t, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s, x3)
                   : dynca_f32_backward_step(g, wsW, wsG, states + (size_t)t * n, gnext, tap, tap_c, tap_scale, gout, cond, fm, s);
         if (rc) return rc;
         gnext = gout;

@@ -17,17 +17,19 @@ int nca_edge_extract_launch(int B, int H, int W, const float* img, int tanh_tran
 int nca_philox_mask_launch(int B, int H, int W, float rate, int enc, uint64_t seed, int t0, const uint32_t* t0_dev, int T, float* out, cudaStream_t s);
 
 // dynca_bf16.cu (tcgen05 path)
-size_t dynca_bf16_weight_bytes(const DyncaGeom& g);
-int dynca_bf16_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s);
+// x3 = NCA_PREC_F16X3: hi + lo operand images, three MMAs per product
+size_t dynca_bf16_weight_bytes(const DyncaGeom& g, bool x3 = false);
+bool dynca_bf16_supported(const DyncaGeom& g, bool x3);
+int dynca_bf16_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s, bool x3 = false);
 int dynca_bf16_forward_step(const DyncaGeom& g, const void* ws, float* xc, const float* x_in, float* x_out, const float* cond,
-                            const FireMask& fm, cudaStream_t s);
+                            const FireMask& fm, cudaStream_t s, bool x3 = false);
 size_t dynca_bf16_coarse_floats(const DyncaGeom& g);
-size_t dynca_bf16_bwd_weight_bytes(const DyncaGeom& g);
-bool dynca_bf16_bwd_supported(const DyncaGeom& g);
-int dynca_bf16_prep_bwd_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s);
+size_t dynca_bf16_bwd_weight_bytes(const DyncaGeom& g, bool x3 = false);
+bool dynca_bf16_bwd_supported(const DyncaGeom& g, bool x3 = false);
+int dynca_bf16_prep_bwd_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s, bool x3 = false);
 int dynca_bf16_backward_step(const DyncaGeom& g, const void* ws, float* xc, const float* xc_ready, float* wsG, const float* x_in, const float* g_next,
                              const float* g_tap, int tap_c, float tap_scale, float* g_out, const float* cond,
-                             const FireMask& fm, cudaStream_t s);
+                             const FireMask& fm, cudaStream_t s, bool x3 = false);
 
 // dynca_tc2.cu (tcgen05 path, 8x16 tiles + TMA; shapes with W % 4 == 0, fc % 32 == 0)
 struct DyncaTc2Maps { alignas(64) unsigned char x[128]; alignas(64) unsigned char xc[128]; alignas(64) unsigned char cond[128]; };   // CUtensorMaps
