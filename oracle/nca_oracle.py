@@ -246,9 +246,17 @@ class _RoundBf16STE(torch.autograd.Function):
         return g
 
 
-def dynca_step_bf16ops(x, w1, b1, w2, b2, mask, scales=(0,), mode="circular", cond=None):
+def dynca_step_bf16ops(x, w1, b1, w2, b2, mask, scales=(0,), mode="circular", cond=None, fast=False):
+    """fast=True phrases the same arithmetic with the ATen ops of dynca_step_aten (4x quicker on big grids)."""
     q = _RoundBf16STE.apply
     C = x.shape[1]
+    if fast:
+        z = sum(perceive_aten(x, s, mode) for s in scales) / len(scales)
+        pre = F.conv2d(q(z), q(w1[:, :4 * C])[:, :, None, None], b1)
+        if cond is not None:
+            pre = pre + F.conv2d(cond, q(w1[:, 4 * C:])[:, :, None, None])
+        y = F.conv2d(q(torch.relu(pre)), q(w2)[:, :, None, None], b2)
+        return x + y * mask
     z = perceive_multiscale(x, scales, mode, None)
     pre = torch.einsum("jk,bkhw->bjhw", q(w1[:, :4 * C]), q(z)) + b1[None, :, None, None]
     if cond is not None:      # cond inputs stay fp32 (the reference feeds them unrounded); their weights are MLP weights
@@ -258,10 +266,10 @@ def dynca_step_bf16ops(x, w1, b1, w2, b2, mask, scales=(0,), mode="circular", co
     return x + y * mask
 
 
-def dynca_rollout_bf16ops(x, w1, b1, w2, b2, masks, scales=(0,), mode="circular", cond=None, keep=False):
+def dynca_rollout_bf16ops(x, w1, b1, w2, b2, masks, scales=(0,), mode="circular", cond=None, keep=False, fast=False):
     hist = [x]
     for t in range(masks.shape[0]):
-        x = dynca_step_bf16ops(x, w1, b1, w2, b2, masks[t], scales, mode, cond)
+        x = dynca_step_bf16ops(x, w1, b1, w2, b2, masks[t], scales, mode, cond, fast=fast)
         if keep:
             hist.append(x)
     return (x, hist) if keep else x
