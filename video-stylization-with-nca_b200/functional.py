@@ -187,7 +187,10 @@ class _DyncaRollout(torch.autograd.Function):
         tap_ptrs = (C.c_void_p * max(n_taps, 1))(*[t.data_ptr() for _, t in taps])
         tap_steps = (C.c_int32 * max(n_taps, 1))(*[s for s, _ in taps])
         gx0 = torch.empty(B, Cc, H, W, device=hist.device, dtype=torch.float32)
-        gw1, gb1, gw2, gb2 = (torch.empty_like(t) for t in (w1, b1, w2, b2))
+        # the four weight gradients are written back to back into ONE buffer (in parameter order): the data-parallel
+        # all-reduce then runs on it as it is (parallel.flat_view), without a flatten / concatenate launch
+        sizes = [t.numel() for t in (w1, b1, w2, b2)]
+        gw1, gb1, gw2, gb2 = torch.empty(sum(sizes), device=hist.device, dtype=torch.float32).split(sizes)
         with torch.cuda.device(hist.device):
             nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 1)
             ws = torch.empty(nbytes, device=hist.device, dtype=torch.uint8)
@@ -327,7 +330,8 @@ class _EncRollout(torch.autograd.Function):
         g_final = _c(g_final)
         gx0 = torch.empty(B, Cc, H, W, device=hist.device, dtype=torch.float32)
         ggoal = torch.empty_like(gx0)
-        gws = [torch.empty_like(t) for t in ws]
+        sizes = [t.numel() for t in ws]
+        gws = list(torch.empty(sum(sizes), device=hist.device, dtype=torch.float32).split(sizes))      # one flat buffer, parameter order
         with torch.cuda.device(hist.device):
             nbytes = lib.nca_enc_workspace_bytes(C.byref(d), 1)
             wsb = torch.empty(nbytes, device=hist.device, dtype=torch.uint8)

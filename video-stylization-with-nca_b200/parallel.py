@@ -24,6 +24,22 @@ def rank_seed(seed, rank):
     return (int(seed) * 0x9E3779B97F4A7C15 + (rank + 1) * 0xD1B54A32D192ED03) & ((1 << 62) - 1)
 
 
+def flat_view(tensors):
+    """A zero-copy flat view over `tensors` when they sit back to back in one storage (the BPTT entry points write the weight
+    gradients of a model that way, in parameter order), else None."""
+    tensors = list(tensors)
+    if not tensors or any(t is None for t in tensors):
+        return None
+    t0 = tensors[0]
+    base, o = t0.untyped_storage().data_ptr(), t0.storage_offset()
+    for t in tensors:
+        if (not t.is_contiguous() or t.dtype != t0.dtype or t.device != t0.device or t.untyped_storage().data_ptr() != base
+                or t.storage_offset() != o):
+            return None
+        o += t.numel()
+    return t0.as_strided((o - t0.storage_offset(),), (1,), t0.storage_offset())
+
+
 def flatten_grads(params, out=None):
     """Concatenate the .grad of every parameter (zeros where None) into one flat fp32 buffer."""
     params = list(params)
@@ -56,8 +72,14 @@ def unflatten_grads(params, flat):
 def allreduce_grads(params, group=None, flat=None):
     """Sum the weight gradients over all ranks in ONE collective; returns the flat buffer."""
     params = list(params)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    view = flat_view([p.grad for p in params]) if flat is None else None
+    if view is not None:        # the gradients already are one buffer: reduce it in place (no flatten, no copy back)
+        if multi:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+        return view
     flat = flatten_grads(params, flat)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if multi:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     unflatten_grads(params, flat)
     return flat
