@@ -62,13 +62,14 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
 
 #define T2_NTHREADS 288     // 8 compute warps + 1 MMA / TMA warp
 
-template <int NS>
+template <int NS, int CT, int FT>
 __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                      const __grid_constant__ CUtensorMap tm_xc,
                                                                      const __grid_constant__ CUtensorMap tm_c, const T2FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const DyncaGeom& g = a.g;
-    const Bf16Geom& bg = a.bg;
+    DyncaGeom g = a.g;
+    Bf16Geom bg = a.bg;
+    t2_specialize<CT, FT>(g, bg);
     const T2Smem L = t2_smem(g, bg);
     uint64_t* barM = reinterpret_cast<uint64_t*>(smem);         // MMA batch complete (tcgen05.commit)
     uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);     // TMA complete
@@ -538,22 +539,28 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     const CUtensorMap* tcn = (const CUtensorMap*)m->cond;
     // (function attributes are per device and the launchers run on several threads: the cache is per device, under a mutex)
     static std::mutex occ_mu;
-    static size_t occ_smem_dev[NCA_MAX_DEVICES][2];
-    static int occ_val_dev[NCA_MAX_DEVICES][2];
-    const int oi = g.ns == 2 ? 1 : 0;
+    static size_t occ_smem_dev[NCA_MAX_DEVICES][8];
+    static int occ_val_dev[NCA_MAX_DEVICES][8];
+    const bool T2_NOSPEC = t2_nospec("NCA_T2_NOSPEC_FWD");
+    const int spec = T2_NOSPEC ? 0 : ((g.C == 16 && g.fc == 128) ? 1 : ((g.C == 12 && g.fc == 96) ? 2 : ((g.C == 13 && g.fc == 96) ? 3 : 0)));
+    const int oi = (g.ns == 2 ? 4 : 0) + spec;
     const int dev = nca_device_ordinal() % NCA_MAX_DEVICES;
     std::unique_lock<std::mutex> occ_lock(occ_mu);
     size_t* const occ_smem = occ_smem_dev[dev];
     int* const occ_val = occ_val_dev[dev];
     if (occ_val[oi] == 0 || occ_smem[oi] != smem) {
         int o = 0;
-        if (g.ns == 2) {
-            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<2>, T2_NTHREADS);
-        } else {
-            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<1>, T2_NTHREADS);
-        }
+#define T2F_ATTR(CT_, FT_)                                                                                                          \
+    do {                                                                                                                            \
+        if (g.ns == 2) {                                                                                                            \
+            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2, CT_, FT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<2, CT_, FT_>, T2_NTHREADS);                                               \
+        } else {                                                                                                                    \
+            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1, CT_, FT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<1, CT_, FT_>, T2_NTHREADS);                                               \
+        }                                                                                                                           \
+    } while (0)
+        T2_DISPATCH_CF(g.C, g.fc, T2F_ATTR);
         const int by_smem = (int)((227 * 1024) / (smem + 1024));
         if (o > by_smem) o = by_smem;
         occ_val[oi] = o < 1 ? 1 : o;
@@ -566,8 +573,12 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
-    if (g.ns == 2) NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<2>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
-    else NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<1>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a));
+#define T2F_LAUNCH(CT_, FT_)                                                                                                        \
+    do {                                                                                                                            \
+        if (g.ns == 2) NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<2, CT_, FT_>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a)); \
+        else NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<1, CT_, FT_>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a)); \
+    } while (0)
+    T2_DISPATCH_CF(g.C, g.fc, T2F_LAUNCH);
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps (cycles since the tile's first stamp)
         long long h[256];

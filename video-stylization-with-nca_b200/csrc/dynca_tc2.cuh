@@ -287,6 +287,39 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
         : "memory");
 }
 
+// ---- compile-time specialisation: the step kernels are instantiated for the (C, fc) pairs of the reference's configurations
+// (CT = FT = 0: any shape, geometry read from the arguments).  The kernel works on local copies of the geometry structs with the
+// template values written in, so that every loop bound, shared-memory offset and descriptor that depends on C or fc folds to a
+// constant (the generic instantiation spends ~15 % of its instructions on that arithmetic).
+template <int CT, int FT>
+__device__ __forceinline__ void t2_specialize(DyncaGeom& g, Bf16Geom& bg) {
+    if (CT > 0) { g.C = CT; g.P = 4 * CT + g.cc; }
+    if (FT > 0) g.fc = FT;
+    if (CT > 0) {
+        bg.npairs = (CT + 1) / 2;
+        bg.K1 = ((bg.npairs + 1) * 8 + 15) / 16 * 16;
+        bg.a1_bytes = (uint32_t)(bg.K1 / 8) * 2048u;
+    }
+    if (FT > 0) {
+        bg.N1 = FT;
+        bg.a2_bytes = (uint32_t)(FT / 8) * 2048u;
+        bg.b2_bytes = (uint32_t)(FT / 8) * 256u;
+    }
+    if (CT > 0 && FT > 0) bg.b1_bytes = (uint32_t)(bg.K1 / 8) * (uint32_t)(FT / 8) * 128u;
+}
+static inline bool t2_nospec(const char* name) {      // NCA_T2_NOSPEC_FWD / NCA_T2_NOSPEC_BWD = 1: generic instantiation (debugging)
+    const char* e = getenv(name);
+    return e && e[0] == '1';
+}
+#define T2_DISPATCH_CF(C_, FC_, DO)                                  \
+    do {                                                              \
+        if (T2_NOSPEC) { DO(0, 0); }                                  \
+        else if ((C_) == 16 && (FC_) == 128) { DO(16, 128); }         \
+        else if ((C_) == 12 && (FC_) == 96) { DO(12, 96); }           \
+        else if ((C_) == 13 && (FC_) == 96) { DO(13, 96); }           \
+        else { DO(0, 0); }                                            \
+    } while (0)
+
 // ---- perception phases shared by the forward and the BPTT kernel (NW = number of compute warps, 8 or 16) ----
 // fine perception -> A1: item = (channel pair, vertical block of 4 rows); lane = (column px, channel of the pair), channel
 // in the low bit: channel planes are T2_XR * T2_XS = 240 floats apart = 16 banks, so the loads of a warp cover all 32 banks,

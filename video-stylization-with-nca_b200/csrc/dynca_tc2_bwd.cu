@@ -173,15 +173,16 @@ __device__ __forceinline__ int tb_fold(int r, int n, int mode) {
 
 // OPH = with an operand history (compile-time: the recompute paths - perception, border patches, overlaid coarse planes - are
 // then not in the kernel at all; the kernel is far larger than the instruction cache and jumps over dead regions cost fetches)
-template <int NS, bool OPH>
+template <int NS, bool OPH, int CT, int FT>
 __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                         const __grid_constant__ CUtensorMap tm_xc,
                                                                         const __grid_constant__ CUtensorMap tm_g,
                                                                         const __grid_constant__ CUtensorMap tm_gc,
                                                                         const __grid_constant__ CUtensorMap tm_c, const T2BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const DyncaGeom& g = a.g;
-    const Bf16Geom& bg = a.bg;
+    DyncaGeom g = a.g;
+    Bf16Geom bg = a.bg;
+    t2_specialize<CT, FT>(g, bg);
     const TBSmem L = tb_smem(g, bg, OPH);
 #ifdef NCA_T2_TIMING
     if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) a.tdbg[128] = clock64();
@@ -267,7 +268,11 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
 
     if (warp == 16) {
         // =========================== MMA / TMA warp ===========================
-        const uint32_t lbo_b1 = (uint32_t)(fc / 8) * 128u;
+        // deliberately from the ARGUMENTS, not from the specialised geometry: with every descriptor of this warp a compile-time
+        // constant, nvcc 12.9 generates a <2, true, 16, 128> instantiation whose recompute / weight-gradient products are wrong
+        // (caught by tests/test_dynca_bf16_gpu.py; either this value or the K-step count read at run time avoids it, the
+        // single-scale and the (12, 96) / (13, 96) instantiations are not affected).  The cost is nil: one warp's scalar arithmetic.
+        const uint32_t lbo_b1 = (uint32_t)(a.g.fc / 8) * 128u;
         const uint32_t id_fc = umma_idesc_bf16(128, fc), id_fc_bmn = id_fc | (1u << 16), id_fc_mn = umma_idesc_bf16_mn(128, fc);
         const uint32_t id_w2 = umma_idesc_bf16_mn(128, 16), id_w1 = umma_idesc_bf16_mn(128, bg.K1), id_w1c = umma_idesc_bf16_mn(128, N6);
         const uint32_t id_gz = umma_idesc_bf16(128, N6) | (1u << 16);
@@ -1129,13 +1134,17 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     const CUtensorMap* tg = (const CUtensorMap*)gm->x;
     const CUtensorMap* tgc = (const CUtensorMap*)gm->xc;
     const CUtensorMap* tcn = (const CUtensorMap*)xm->cond;
-#define TB_LAUNCH(NS_, OPH_)                                                                                                  \
+#define TB_LAUNCH(NS_, OPH_, CT_, FT_)                                                                                        \
     do {                                                                                                                      \
-        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<NS_, OPH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<NS_, OPH_>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a)); \
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<NS_, OPH_, CT_, FT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<NS_, OPH_, CT_, FT_>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a)); \
     } while (0)
-    if (g.ns == 2) { if (op_in) TB_LAUNCH(2, true); else TB_LAUNCH(2, false); }
-    else { if (op_in) TB_LAUNCH(1, true); else TB_LAUNCH(1, false); }
+    // specialised instantiations: the operand-history kernels of the reference's (C, fc) pairs; everything else is generic
+#define TB_LAUNCH_OPH(CT_, FT_) do { if (g.ns == 2) TB_LAUNCH(2, true, CT_, FT_); else TB_LAUNCH(1, true, CT_, FT_); } while (0)
+    const bool T2_NOSPEC = t2_nospec("NCA_T2_NOSPEC_BWD");
+    if (op_in) T2_DISPATCH_CF(g.C, g.fc, TB_LAUNCH_OPH);
+    else if (g.ns == 2) TB_LAUNCH(2, false, 0, 0);
+    else TB_LAUNCH(1, false, 0, 0);
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps
         long long h[160];
