@@ -184,6 +184,23 @@ int nca_enc_backward(const NcaEncDesc* d, const NcaEncWeights* w, const float* g
                      void* workspace, size_t workspace_bytes, void* stream);
 size_t nca_enc_workspace_bytes(const NcaEncDesc* d, int32_t backward);
 
+/* ImageEncoder of the encoder-conditioned NCA (EncoderConditioning/encoder.py:5-64; called once per rollout, nca.py:198), fused:
+ *   x [B,3,H,W] -> [sobel_x, sobel_y, laplacian of mean_rgb(x) | 5x5 gaussian blur per colour channel] -> conv3x3(6->16)+b1, ReLU
+ *   -> conv3x3(16->16)  = goal encoding, written into the LAST 16 channels of goal [B,goal_channels,H,W]; the leading channels are
+ *   zeroed (the zero padding of nca.py:199-203), i.e. `goal` is exactly the tensor nca_enc_forward consumes.
+ *   w1 [16,6,3,3] = encoder.embed.0.weight, b1 [16] = embed.0.bias, w2 [16,16,3,3] = embed.2.weight.
+ *   feats [B,6,H,W] and hidden [B,16,H,W] (post-ReLU) are kept for the backward when given (both or neither).
+ * Supported: channels == 3, embedding_dim == 16 (the reference's configuration, train.py:84); else NCA_ERR_UNSUPPORTED. */
+int nca_encoder_forward(int32_t B, int32_t channels, int32_t H, int32_t W, int32_t embedding_dim, const float* x, const float* w1,
+                        const float* b1, const float* w2, float* feats, float* hidden, float* goal, int32_t goal_channels,
+                        void* stream);
+/* Weight gradients of the ImageEncoder from d(goal) = the last 16 channels of g_goal [B,goal_channels,H,W] as written by
+ * nca_enc_backward (replaces autograd's replay of encoder.py:37-57; the input image gets no gradient: it is data,
+ * conditioned_trainer.py:118-137).  gw1 [16,6,3,3], gb1 [16], gw2 [16,16,3,3] are written. */
+int nca_encoder_backward(int32_t B, int32_t channels, int32_t H, int32_t W, int32_t embedding_dim, const float* feats,
+                         const float* hidden, const float* w2, const float* g_goal, int32_t goal_channels, float* gw1, float* gb1,
+                         float* gw2, void* stream);
+
 /* ---- the callers either side of the step (N1 pool + optimizer, N4 overflow loss, N2 frame stream) -------- */
 
 /* Batch assembly from the sample pool — ExtraChannels/experiments.py:203-211 (ConditioneDyNCA/experiments.py:210-218):

@@ -19,6 +19,7 @@ Reference lines followed (all fp32, NCHW):
       ConditioneDyNCA/models/dynca.py:117-138 (cond_img path), 182-213 (EdgeExtractor)
   * CPE2D positional encoding: ExtraChannels/models/dynca.py:180-207
   * ConditionedNCA (encoder-conditioned): EncoderConditioning/nca.py:29-58, 99-110, 152-209
+  * ImageEncoder: EncoderConditioning/encoder.py:5-64
 """
 from __future__ import annotations
 
@@ -417,6 +418,24 @@ def enc_alive(x, living_dim: int, thr: float = 0.1):
         for dx in range(3):
             m = torch.maximum(m, p[:, :, dy:dy + H, dx:dx + W])
     return m > thr
+
+
+def gaussian_kernel5():
+    """encoder.py:59-63: normalised 5x5 gaussian, sigma 1, built in float32 from python floats"""
+    k = torch.tensor([[(1 / (2 * math.pi)) * math.exp(-((i - 2) ** 2 + (j - 2) ** 2) / 2.0) for j in range(5)] for i in range(5)])
+    return (k / torch.sum(k)).float()
+
+
+def image_encoder(x, w1, b1, w2):
+    """ImageEncoder.forward (EncoderConditioning/encoder.py:37-57): x [B,ch,H,W] -> [B,E,H,W].
+    w1 [E,ch+3,3,3], b1 [E], w2 [E,E,3,3]; every convolution zero padded."""
+    ch = x.shape[1]
+    gray = torch.mean(x, dim=1, keepdim=True)
+    feats = [_stencil(gray, SOBEL_X, "constant"), _stencil(gray, SOBEL_Y, "constant"), _stencil(gray, LAPLACE, "constant")]
+    gk = gaussian_kernel5().to(x.dtype)[None, None]
+    feats += [F.conv2d(x[:, i:i + 1], gk, padding=2) for i in range(ch)]
+    h = torch.relu(F.conv2d(torch.cat(feats, dim=1), w1, b1, padding=1))
+    return F.conv2d(h, w2, None, padding=1)
 
 
 def enc_perception(x, wp):

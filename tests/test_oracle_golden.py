@@ -1,6 +1,7 @@
 """The oracle restatement vs. outputs of the UNMODIFIED reference (tests/golden, made by
 oracle/make_golden.py).  CPU only.  Tolerances: 2e-6 relative on states (summation-order noise
 between conv2d and explicit shifts), 2e-5 on gradients accumulated over T steps."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -80,3 +81,18 @@ def test_philox_mask_rate():
     assert philox.fire_mask(1, 0, 1, 1, 8, 8, 1.0).min() == 1.0
     assert philox.fire_mask(1, 0, 1, 1, 8, 8, 0.0).max() == 0.0
     assert abs(philox.fire_mask(7, 3, 2, 1, 64, 64, 0.25, enc=True).mean() - 0.25) < 0.03
+
+
+def test_image_encoder_oracle_matches_reference_golden():
+    """oracle.image_encoder restates EncoderConditioning/encoder.py:37-57; tests/golden/encoder.npz was made from the unmodified
+    reference module (oracle/make_golden_encoder.py)"""
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encoder.npz"))
+    t = {k: torch.from_numpy(d[k]) for k in d.files}
+    ps = [t[k].clone().requires_grad_(True) for k in ("w1", "b1", "w2")]
+    out = O.image_encoder(t["x"], *ps)
+    (out * t["coef"]).sum().backward()
+    assert rel_err(out.detach(), t["out"]) < 2e-6
+    for p, k in zip(ps, ("w1", "b1", "w2")):
+        assert rel_err(p.grad, t["g_" + k]) < 2e-5, k
+    assert rel_err(O.gaussian_kernel5(), t["gauss"][0, 0]) < 1e-6

@@ -45,6 +45,7 @@ SYMBOLS = ["nca_last_error", "nca_abi_version", "nca_launch_count", "nca_launch_
            "nca_edge_extract", "nca_dynca_forward", "nca_dynca_backward", "nca_dynca_workspace_bytes", "nca_dynca_op_hist_bytes",
            "nca_dynca_kernel_variant",
            "nca_philox_mask", "nca_philox_mask_at", "nca_enc_forward", "nca_enc_backward", "nca_enc_workspace_bytes",
+           "nca_encoder_forward", "nca_encoder_backward",
            "nca_pool_gather", "nca_pool_dead_flags", "nca_pool_scatter", "nca_normalized_adam_step", "nca_overflow_workspace_bytes", "nca_overflow_loss",
            "nca_frame_to_cond_channel", "nca_state_to_rgb8"]
 
@@ -86,6 +87,8 @@ def load_library():
     lib.nca_enc_forward.argtypes = [C.POINTER(EncDesc), C.POINTER(EncWeights), P, P, U64, I, I, I, P, P, P, SZ, P]
     lib.nca_enc_backward.argtypes = [C.POINTER(EncDesc), C.POINTER(EncWeights), P, P, U64, I, I, P, P, P, P, P,
                                      C.POINTER(EncWeights), P, SZ, P]
+    lib.nca_encoder_forward.argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, I, P]
+    lib.nca_encoder_backward.argtypes = [I, I, I, I, I, P, P, P, P, I, P, P, P, P]
     PP = C.POINTER(C.c_void_p)
     lib.nca_pool_gather.argtypes = [I, I, I, I, P, P, I, P, I, P, I, P, P, P]
     lib.nca_pool_dead_flags.argtypes = [I, I, I, I, P, P, I, I, F, P, P]

@@ -60,12 +60,24 @@ __host__ __device__ static inline EncTcSmem etc_smem(const EncTcGeom& g) {
     return s;
 }
 
-template <int DUMMY>
+// CT: compile-time channel count (20 = the reference's 3 rgb + 1 alpha + 16 hidden; 0 = read from the arguments).  The kernel works
+// on a local copy of the geometry with the template value written in, so that loop bounds and shared-memory offsets fold.
+template <int CT>
+__device__ __forceinline__ void etc_specialize(EncTcGeom& g) {
+    if (CT > 0) {
+        g.C = CT;
+        g.npairs = (CT + 1) / 2;
+        g.K1 = ((g.npairs + 1) * 8 + 15) / 16 * 16;
+    }
+}
+
+template <int CT>
 __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                    const __grid_constant__ CUtensorMap tm_l,
                                                                    const __grid_constant__ CUtensorMap tm_g, const EncTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const EncTcGeom& g = a.g;
+    EncTcGeom g = a.g;
+    etc_specialize<CT>(g);
     const EncTcSmem L = etc_smem(g);
     uint64_t* barM = reinterpret_cast<uint64_t*>(smem);
     uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);
@@ -416,16 +428,22 @@ int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void*
     const size_t smem = etc_smem(a.g).total;
     // co-resident CTAs: registers, shared memory (once per shared-memory size), TMEM (128 columns each)
     static std::mutex occ_mu;
-    static size_t occ_smem_dev[NCA_MAX_DEVICES];
-    static int occ_val_dev[NCA_MAX_DEVICES];
+    static size_t occ_smem_dev[NCA_MAX_DEVICES][2];
+    static int occ_val_dev[NCA_MAX_DEVICES][2];
     const int dev = nca_device_ordinal() % NCA_MAX_DEVICES;
+    const int spec = d->C == 20 ? 1 : 0;           // the reference's channel count has its own instantiation
     std::unique_lock<std::mutex> occ_lock(occ_mu);
-    size_t& occ_smem = occ_smem_dev[dev];
-    int& occ_val = occ_val_dev[dev];
+    size_t& occ_smem = occ_smem_dev[dev][spec];
+    int& occ_val = occ_val_dev[dev][spec];
     if (occ_val == 0 || occ_smem != smem) {
         int o = 0;
+        if (spec) {
+            NCA_CUDA_OK(cudaFuncSetAttribute(enc_fwd_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            o = t2_occupancy_by_regs(enc_fwd_tc_kernel<20>, ET2_NTHREADS);
+        } else {
         NCA_CUDA_OK(cudaFuncSetAttribute(enc_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         o = t2_occupancy_by_regs(enc_fwd_tc_kernel<0>, ET2_NTHREADS);
+        }
         const int by_smem = (int)((227 * 1024) / (smem + 1024));
         if (o > by_smem) o = by_smem;
         occ_val = o < 1 ? 1 : o;
@@ -437,8 +455,12 @@ int enc_tc_forward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void*
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
-    NCA_CUDA_OK(t2_launch(enc_fwd_tc_kernel<0>, grid, ET2_NTHREADS, smem, s, pdl != 0, *(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l,
-                          *(const CUtensorMap*)m->g, a));
+    if (spec)
+        NCA_CUDA_OK(t2_launch(enc_fwd_tc_kernel<20>, grid, ET2_NTHREADS, smem, s, pdl != 0, *(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l,
+                              *(const CUtensorMap*)m->g, a));
+    else
+        NCA_CUDA_OK(t2_launch(enc_fwd_tc_kernel<0>, grid, ET2_NTHREADS, smem, s, pdl != 0, *(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l,
+                              *(const CUtensorMap*)m->g, a));
     NCA_LAUNCH_OK();
     return NCA_OK;
 }
@@ -539,13 +561,14 @@ __device__ __forceinline__ void eb_conv_t(const float* __restrict__ P0, const fl
     }
 }
 
-template <int DUMMY>
+template <int CT>
 __global__ void __launch_bounds__(EB_NTHREADS, 1) enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                      const __grid_constant__ CUtensorMap tm_l,
                                                                      const __grid_constant__ CUtensorMap tm_g,
                                                                      const __grid_constant__ CUtensorMap tm_gn, const EncTcBwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const EncTcGeom& g = a.g;
+    EncTcGeom g = a.g;
+    etc_specialize<CT>(g);
     const EncTcBwdSmem L = etb_smem(g);
     uint64_t* barM = reinterpret_cast<uint64_t*>(smem);
     uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);
@@ -1102,9 +1125,15 @@ int enc_tc_backward_step(const NcaEncDesc* d, const NcaEncWeights* w, const void
     const size_t smem = etb_smem(a.g).total;
     int grid = t2_num_sms();
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
-    NCA_CUDA_OK(cudaFuncSetAttribute(enc_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    enc_bwd_tc_kernel<0><<<grid, EB_NTHREADS, smem, s>>>(*(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l, *(const CUtensorMap*)m->g,
-                                                         *(const CUtensorMap*)gm->x, a);
+    if (d->C == 20) {
+        NCA_CUDA_OK(cudaFuncSetAttribute(enc_bwd_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        enc_bwd_tc_kernel<20><<<grid, EB_NTHREADS, smem, s>>>(*(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l, *(const CUtensorMap*)m->g,
+                                                              *(const CUtensorMap*)gm->x, a);
+    } else {
+        NCA_CUDA_OK(cudaFuncSetAttribute(enc_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        enc_bwd_tc_kernel<0><<<grid, EB_NTHREADS, smem, s>>>(*(const CUtensorMap*)m->x, *(const CUtensorMap*)m->l, *(const CUtensorMap*)m->g,
+                                                             *(const CUtensorMap*)gm->x, a);
+    }
     NCA_LAUNCH_OK();
     return NCA_OK;
 }

@@ -342,6 +342,54 @@ class _EncRollout(torch.autograd.Function):
         return (gx0, ggoal, *[g.view(s) for g, s in zip(gws, ctx.w_shapes)], None, None, None, None)
 
 
+class _ImageEncoderFn(torch.autograd.Function):
+    """ImageEncoder.forward fused (EncoderConditioning/encoder.py:37-57) -> the zero-padded goal tensor [B,C,H,W] the rollout reads;
+    backward = the weight gradients from the BPTT's d(goal) in one kernel (the image is data: no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, goal_channels):
+        lib = load_library()
+        xc, w1c, b1c, w2c = _c(x), _c(w1), _c(b1), _c(w2)
+        B, ch, H, W = xc.shape
+        E = w2c.shape[0]
+        keep = any(ctx.needs_input_grad[1:4])
+        feats = torch.empty(B, ch + 3, H, W, device=x.device, dtype=torch.float32) if keep else None
+        hidden = torch.empty(B, E, H, W, device=x.device, dtype=torch.float32) if keep else None
+        goal = torch.empty(B, goal_channels, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            check(lib.nca_encoder_forward(B, ch, H, W, E, _ptr(xc), _ptr(w1c), _ptr(b1c), _ptr(w2c), _ptr(feats), _ptr(hidden), _ptr(goal),
+                                          goal_channels, _stream()))
+        ctx.save_for_backward(feats, hidden, w2c)
+        ctx.shapes = (w1.shape, b1.shape, w2.shape, ch, E, goal_channels)
+        return goal
+
+    @staticmethod
+    def backward(ctx, g_goal):
+        lib = load_library()
+        feats, hidden, w2c = ctx.saved_tensors
+        s1, sb, s2, ch, E, gc = ctx.shapes
+        g = _c(g_goal)
+        B, _, H, W = g.shape
+        sizes = [E * (ch + 3) * 9, E, E * E * 9]
+        gw1, gb1, gw2 = torch.empty(sum(sizes), device=g.device, dtype=torch.float32).split(sizes)
+        with torch.cuda.device(g.device):
+            check(lib.nca_encoder_backward(B, ch, H, W, E, _ptr(feats), _ptr(hidden), _ptr(w2c), _ptr(g), gc, _ptr(gw1), _ptr(gb1), _ptr(gw2),
+                                           _stream()))
+        return None, gw1.view(s1), gb1.view(sb), gw2.view(s2), None
+
+
+def image_encoder_supported(channels, embedding_dim):
+    return channels == 3 and embedding_dim == 16
+
+
+def image_encoder(x, w1, b1, w2, goal_channels):
+    """ImageEncoder (encoder.py:5-64) on the CUDA path: x [B,3,H,W] -> zero-padded goal encoding [B,goal_channels,H,W]."""
+    _need_cuda(x, w1, b1, w2)
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NcaError("the fused ImageEncoder does not differentiate its input image (it is data in the reference's trainer)")
+    return _ImageEncoderFn.apply(x, w1, b1, w2, int(goal_channels))
+
+
 def enc_rollout(cfg, x0, goal, wp, wa, ba, wb, bb, wc, T, masks=None, seed=None):
     """T ConditionedNCA steps (the loop of ConditionedNCA.grow, nca.py:207-208) on an already encoded, zero-padded
     goal [B,C,H,W].  masks: optional supplied fire masks [T,B,1,H,W] (1 = fire, i.e. u < rate)."""

@@ -2,8 +2,8 @@
 
 The T-step loop of ``grow`` / ``forward`` runs in libnca_b200.so (csrc/enc_f32.cu); the modules only hold the
 parameters in the reference's containers (same state_dict keys / shapes) and mirror its methods.  The
-ImageEncoder runs once per rollout and stays PyTorch; the rollout returns d(goal_encoding)
-to it through autograd."""
+ImageEncoder runs once per rollout: forward and weight-gradient pass are one fused kernel each (csrc/enc_encoder.cu) that
+write / read the zero-padded goal tensor of the rollout directly; other encoder shapes fall back to the reference's torch ops."""
 from typing import Optional, Tuple
 
 import numpy as np
@@ -40,11 +40,26 @@ class ImageEncoder(nn.Module):
             nn.Conv2d(embedding_dim, embedding_dim, kernel_size=3, padding=1, bias=False),
         )
 
-    def forward(self, x):
+    def fused_ok(self, x):
+        """the one-kernel CUDA path covers the reference's configuration (3 colour channels, 16-wide embedding, float32 on CUDA)"""
+        return (x.is_cuda and x.dtype == torch.float32 and not (x.requires_grad and torch.is_grad_enabled())
+                and Fn.image_encoder_supported(self.channels, self.embed[2].out_channels) and self.embed[0].out_channels == self.embed[2].out_channels)
+
+    def forward(self, x, goal_channels=None):
+        """goal_channels: when given, the embedding comes back already zero-padded to that many channels (leading zeros,
+        nca.py:199-203) - the tensor ConditionedNCA.grow feeds to the rollout."""
+        if self.fused_ok(x):
+            E = self.embed[2].out_channels
+            out = Fn.image_encoder(x, self.embed[0].weight, self.embed[0].bias, self.embed[2].weight, E if goal_channels is None else goal_channels)
+            return out
+        # other shapes / CPU tensors: the reference's own sequence of torch ops (not on the NCA hot path)
         gray = x.mean(dim=1, keepdim=True)
         feats = [self.sobel_x(gray), self.sobel_y(gray), self.laplacian(gray)]
         feats += [self.gaussian_blur(x[:, i:i + 1]) for i in range(self.channels)]
-        return self.embed(torch.cat(feats, dim=1))
+        out = self.embed(torch.cat(feats, dim=1))
+        if goal_channels is not None and goal_channels > out.size(1):
+            out = F.pad(out, (0, 0, 0, 0, goal_channels - out.size(1), 0))
+        return out
 
 
 class UpdateNet(nn.Module):
@@ -131,7 +146,10 @@ class ConditionedNCA(nn.Module):
         return x, goal_encoding
 
     def grow(self, x: torch.Tensor, num_steps: int, goal: torch.Tensor, *, masks=None, seed=None) -> torch.Tensor:
-        goal_encoding = self._pad_goal(self.encoder(goal))
+        if isinstance(self.encoder, ImageEncoder):      # embedding written straight into the zero-padded goal tensor
+            goal_encoding = self.encoder(goal, goal_channels=self.num_channels)
+        else:
+            goal_encoding = self._pad_goal(self.encoder(goal))
         return Fn.enc_rollout(self._cfg(), x, goal_encoding, *self._w(), num_steps, masks=masks, seed=seed)
 
     def save(self, path: str):
