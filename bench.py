@@ -361,7 +361,7 @@ def main():
 
     # ---- dominant kernel: the BPTT step kernel, timed through the C ABI call that launches it T times ----
     cfg = model._cfg(_lib.NCA_COND_CPE, 2)
-    hist, coarse, ops = Fn._dynca_forward_raw(cfg, x0, *[p.detach() for p in (model.w1.weight, model.w1.bias, model.w2.weight, model.w2.bias)],
+    hist, coarse, (ops, _t1) = Fn._dynca_forward_raw(cfg, x0, *[p.detach() for p in (model.w1.weight, model.w1.bias, model.w2.weight, model.w2.bias)],
                                               None, None, 77, T, 0.5, True, want_ops=True)
     import ctypes as Ct
     d = cfg.desc(B, H, W, 0.5, False)

@@ -260,3 +260,37 @@ def test_tc2_operand_history_matches_recompute(case, monkeypatch):
     for a, b in zip(grads[0][1:], grads[1][1:]):
         assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-4
         assert rel_err(a, b) < 5e-3
+
+
+def test_operand_history_cap_splits_the_rollout(monkeypatch):
+    """A rollout whose operand history exceeds NCA_OP_HIST_MAX_GB keeps the history for the last steps that fit and recomputes
+    the perception for the earlier ones (two C calls per pass, functional._op_hist_plan): same states, same gradients - including
+    rgb taps on both sides of the split point and exactly at it."""
+    import ctypes as Ct
+    import warnings
+    B, C, fc, H, W, T = 2, 16, 128, 32, 48, 7
+    g = torch.Generator().manual_seed(8)
+    cfg = Fn.DyncaConfig(C, fc, "replicate", [0, 1], _lib.NCA_COND_CPE, 2, precision="bf16")
+    lib = nca_b200.load_library()
+    per_step = lib.nca_dynca_op_hist_bytes(Ct.byref(cfg.desc(B, H, W, 0.5, True)), 1)
+    params = [torch.randn(fc, 4 * C + 2, generator=g) * 0.1, torch.randn(fc, generator=g) * 0.1,
+              torch.randn(C, fc, generator=g) * 0.05, torch.randn(C, generator=g) * 0.02]
+    x0 = torch.rand(B, C, H, W, generator=g) - 0.5
+    masks = (torch.rand(T, B, 1, H, W, generator=g) + 0.5).floor().to(DEV)
+    cf = torch.randn(B, C, H, W, generator=g).to(DEV)
+    ct = [torch.randn(B, 3, H, W, generator=g).to(DEV) for _ in range(3)]
+    out = []
+    for keep in (T, 3):            # whole history; history for the last 3 steps only (split at step 4)
+        monkeypatch.setenv("NCA_OP_HIST_MAX_GB", repr((keep * per_step + per_step // 2) / 2 ** 30))
+        monkeypatch.setattr(Fn, "_OP_HIST_WARNED", False)
+        pg = [p.clone().to(DEV).requires_grad_(True) for p in [x0] + params]
+        with warnings.catch_warnings(record=True) as wlist:
+            warnings.simplefilter("always")
+            fg, taps = Fn.dynca_rollout(cfg, *pg, T, 0.5, masks=masks, return_taps=True)
+        assert (len(wlist) == 1) == (keep < T)                        # the cap is never silent
+        loss = (fg * cf).sum() + (taps[1] * ct[0]).sum() + (taps[3] * ct[1]).sum() + (taps[5] * ct[2]).sum()     # states 2, 4 (= split), 6
+        loss.backward()
+        out.append([fg.detach().cpu()] + [p.grad.cpu() for p in pg])
+    assert torch.equal(out[0][0], out[1][0])
+    for a, b, n in zip(out[0][1:], out[1][1:], ("x0", "w1", "b1", "w2", "b2")):
+        assert float((a - b).norm() / b.norm()) < 2e-3, n              # run-to-run noise of the BPTT (see above)

@@ -55,7 +55,7 @@ def run(name, prec, T):
         res = Fn._dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, None, 7, T, 0.5, True, want_ops=True)
         ms = timed(lambda: Fn._dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, None, 7, T, 0.5, True, want_ops=True))
         out["fwd_hist_us"] = ms / T * 1e3
-        hist, coarse, ops = res
+        hist, coarse, (ops, _t1) = res
         d = cfg.desc(B, H, W, 0.5, False)
         nbytes = lib.nca_dynca_workspace_bytes(Ct.byref(d), 1)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)

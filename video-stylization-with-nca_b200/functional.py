@@ -5,6 +5,7 @@ for device memory, streams and autograd bookkeeping.
 """
 import collections.abc
 import os
+import warnings
 import ctypes as C
 
 import torch
@@ -111,10 +112,29 @@ def philox_mask(B, H, W, rate, seed, T, t0=0, enc=False, device="cuda"):
 
 
 # Operand history (nca_b200.h: op_hist): the forward records the bf16 perception operands of every step so that the BPTT
-# loads them instead of recomputing the perception.  160-224 B per cell and step; used while it stays below this many bytes
-# (NCA_OP_HIST_MAX_GB, default 48; 0 disables), results are bit-identical either way.
+# loads them instead of recomputing the perception.  128-224 B per cell and step (DESIGN.md section 2 lists every configuration);
+# kept within NCA_OP_HIST_MAX_GB (default 48; 0 disables).  A rollout whose history would exceed the cap keeps it for the LAST
+# steps that fit and recomputes the perception for the earlier ones (the rollout is split into two C calls at that step); a
+# one-time warning says so.  Results are bit-identical either way.
 def _op_hist_limit():
     return int(float(os.environ.get("NCA_OP_HIST_MAX_GB", "48")) * (1 << 30))
+
+
+_OP_HIST_WARNED = False
+
+
+def _op_hist_plan(lib, d, T):
+    """(steps without history, bytes of the history for the remaining steps)"""
+    global _OP_HIST_WARNED
+    per_step = lib.nca_dynca_op_hist_bytes(C.byref(d), 1)
+    if per_step == 0 or T <= 0:
+        return T, 0
+    k = min(T, _op_hist_limit() // per_step)
+    if k < T and not _OP_HIST_WARNED and _op_hist_limit() > 0:       # (a cap of 0 is an explicit opt-out, not a surprise)
+        _OP_HIST_WARNED = True
+        warnings.warn(f"NCA operand history: {T} steps need {T * per_step / 2**30:.1f} GiB, the cap (NCA_OP_HIST_MAX_GB) allows "
+                      f"{k}: the first {T - k} steps of the BPTT recompute the perception (slower, same results)", stacklevel=3)
+    return T - k, k * per_step
 
 
 def _dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, masks, seed, T, rate, keep_history, want_ops=False):
@@ -127,19 +147,28 @@ def _dynca_forward_raw(cfg, x0, w1, b1, w2, b2, cond, masks, seed, T, rate, keep
     coarse = None
     if keep_history and cfg.ns == 2:     # coarse (2x2-mean) state history, reused by the BPTT
         coarse = torch.empty(n_slots, B, Cc, H // 2, W // 2, device=x0.device, dtype=torch.float32)
-    ops = None
+    ops, t1 = None, 0
     with torch.cuda.device(x0.device):
         if keep_history and want_ops and T > 0:
-            ob = lib.nca_dynca_op_hist_bytes(C.byref(d), T)
-            if 0 < ob <= _op_hist_limit():
+            t1, ob = _op_hist_plan(lib, d, T)
+            if ob > 0:
                 ops = torch.empty(ob, device=x0.device, dtype=torch.uint8)
+            else:
+                t1 = 0
         nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 0)
         ws = torch.empty(max(nbytes, 16), device=x0.device, dtype=torch.uint8)
         wst = _weights_struct(w1, b1, w2, b2)
-        check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(seed), 0, T,
-                                    int(keep_history), _ptr(states), _ptr(coarse), _ptr(ops), _ptr(ws), nbytes, _stream()))
+        if t1 > 0:      # steps [0, t1) without the operand history, steps [t1, T) with it: two calls on the same buffers
+            check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(seed), 0, t1,
+                                        1, _ptr(states), _ptr(coarse), None, _ptr(ws), nbytes, _stream()))
+            check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks[t1:] if masks is not None else None), C.c_uint64(seed),
+                                        t1, T - t1, 1, _ptr(states[t1:]), _ptr(coarse[t1:] if coarse is not None else None), _ptr(ops),
+                                        _ptr(ws), nbytes, _stream()))
+        else:
+            check(lib.nca_dynca_forward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(seed), 0, T,
+                                        int(keep_history), _ptr(states), _ptr(coarse), _ptr(ops), _ptr(ws), nbytes, _stream()))
     if keep_history and want_ops:
-        return states, coarse, ops
+        return states, coarse, (ops, t1)
     if keep_history:
         return states, coarse
     return states
@@ -159,9 +188,9 @@ class _DyncaRollout(torch.autograd.Function):
     def forward(ctx, x0, w1, b1, w2, b2, cond, masks, cfg, T, rate, seed, handle):
         x0c, w1c, b1c, w2c, b2c = _c(x0), _c(w1), _c(b1), _c(w2), _c(b2)
         cond, masks = _c(cond), _c(masks)
-        hist, coarse, ops = _dynca_forward_raw(cfg, x0c, w1c, b1c, w2c, b2c, cond, masks, seed, T, rate, True, want_ops=True)
+        hist, coarse, (ops, ops_t1) = _dynca_forward_raw(cfg, x0c, w1c, b1c, w2c, b2c, cond, masks, seed, T, rate, True, want_ops=True)
         ctx.coarse = coarse
-        ctx.ops = ops
+        ctx.ops, ctx.ops_t1 = ops, ops_t1
         ctx.cfg, ctx.T, ctx.rate, ctx.seed, ctx.handle = cfg, T, rate, seed, handle
         ctx.w_shapes = (w1.shape, b1.shape, w2.shape, b2.shape)
         ctx.save_for_backward(w1c, b1c, w2c, b2c, cond, masks)
@@ -182,23 +211,39 @@ class _DyncaRollout(torch.autograd.Function):
         d = cfg.desc(B, H, W, ctx.rate, masks is not None)
         g_final = _c(g_final)
         taps = sorted(ctx.handle.tap_grads.items())
-        n_taps = len(taps)
         tap_c = ctx.handle.c_out
-        tap_ptrs = (C.c_void_p * max(n_taps, 1))(*[t.data_ptr() for _, t in taps])
-        tap_steps = (C.c_int32 * max(n_taps, 1))(*[s for s, _ in taps])
         gx0 = torch.empty(B, Cc, H, W, device=hist.device, dtype=torch.float32)
         # the four weight gradients are written back to back into ONE buffer (in parameter order): the data-parallel
         # all-reduce then runs on it as it is (parallel.flat_view), without a flatten / concatenate launch
         sizes = [t.numel() for t in (w1, b1, w2, b2)]
-        gw1, gb1, gw2, gb2 = torch.empty(sum(sizes), device=hist.device, dtype=torch.float32).split(sizes)
+        flat = torch.empty(sum(sizes), device=hist.device, dtype=torch.float32)
+        gw1, gb1, gw2, gb2 = flat.split(sizes)
+        t1 = ctx.ops_t1 if ctx.ops is not None else 0
         with torch.cuda.device(hist.device):
             nbytes = lib.nca_dynca_workspace_bytes(C.byref(d), 1)
             ws = torch.empty(nbytes, device=hist.device, dtype=torch.uint8)
             wst = _weights_struct(w1, b1, w2, b2)
-            gst = _weights_struct(gw1, gb1, gw2, gb2)
-            check(lib.nca_dynca_backward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks), C.c_uint64(ctx.seed), 0, T,
-                                         _ptr(hist), _ptr(ctx.coarse), _ptr(ctx.ops), _ptr(g_final), tap_ptrs, tap_steps, n_taps, max(tap_c, 1), 2.0,
-                                         _ptr(gx0), C.byref(gst), _ptr(ws), nbytes, _stream()))
+
+            def call(ta, tb, ops, g_in, g_out, gws):
+                """BPTT through steps [ta, tb): taps at states[ta+1 .. tb] belong to it"""
+                mine = [(s - ta, t) for s, t in taps if ta < s <= tb]
+                n = len(mine)
+                tap_ptrs = (C.c_void_p * max(n, 1))(*[t.data_ptr() for _, t in mine])
+                tap_steps = (C.c_int32 * max(n, 1))(*[s for s, _ in mine])
+                gst = _weights_struct(*gws)
+                check(lib.nca_dynca_backward(C.byref(d), C.byref(wst), _ptr(cond), _ptr(masks[ta:] if masks is not None else None),
+                                             C.c_uint64(ctx.seed), ta, tb - ta, _ptr(hist[ta:]),
+                                             _ptr(ctx.coarse[ta:] if ctx.coarse is not None else None), _ptr(ops), _ptr(g_in), tap_ptrs, tap_steps,
+                                             n, max(tap_c, 1), 2.0, _ptr(g_out), C.byref(gst), _ptr(ws), nbytes, _stream()))
+
+            if t1 > 0:      # [t1, T) with the operand history, then [0, t1) recomputing the perception (see _op_hist_plan)
+                g_mid = torch.empty_like(gx0)
+                part = torch.empty_like(flat)
+                call(t1, T, ctx.ops, g_final, g_mid, part.split(sizes))
+                call(0, t1, None, g_mid, gx0, (gw1, gb1, gw2, gb2))
+                flat += part
+            else:
+                call(0, T, ctx.ops, g_final, gx0, (gw1, gb1, gw2, gb2))
         ctx.handle.tap_grads = {}
         ctx.ops = None
         s1, sb1, s2, sb2 = ctx.w_shapes
