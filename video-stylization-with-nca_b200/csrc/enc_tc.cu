@@ -216,7 +216,15 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
                 for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) mx = fmaxf(mx, lp[dy * T2_XS + dx]);
-                sPre[tid] = (g.liv < 0 || mx > g.thr) ? 1.0f : 0.0f;
+                const float pre = (g.liv < 0 || mx > g.thr) ? 1.0f : 0.0f;
+                sPre[tid] = pre;
+                // ---- xin = x + goal * pre over the goal stage (nca.py:177): this thread's ring position, every channel ----
+                const int o0 = rr * T2_XS + T2_XO + q;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) {
+                    const int o = o0 + c * T2_XR * T2_XS;
+                    sG[o] = fmaf(sG[o], pre, sX[o]);
+                }
             }
             // residual state of this thread's cell: channels 16*half .. 16*half+15
             float xres[16];
@@ -224,13 +232,6 @@ __global__ void __launch_bounds__(ET2_NTHREADS) enc_fwd_tc_kernel(const __grid_c
             for (int i = 0; i < 16; ++i) {
                 const int c = 16 * half + i;
                 xres[i] = c < C ? sX[(c * T2_XR + py + 1) * T2_XS + T2_XO + px + 1] : 0.0f;
-            }
-            bar_sync_n(1, 256);
-            // ---- xin = x + goal * pre over the goal stage (nca.py:177) ----
-            for (int i = tid; i < C * T2_XR * 18; i += 256) {
-                const int q = i % 18, rr = (i / 18) % T2_XR, c = i / (18 * T2_XR);
-                const int o = (c * T2_XR + rr) * T2_XS + T2_XO + q;
-                sG[o] = fmaf(sG[o], sPre[rr * 18 + q], sX[o]);
             }
             bar_sync_n(1, 256);
             // ---- learned depthwise 3x3 -> A1: item = (channel pair, 4-row block); lane = (column, channel of the pair) ----
@@ -769,15 +770,23 @@ __global__ void __launch_bounds__(EB_NTHREADS, 1) enc_bwd_tc_kernel(const __grid
             mbar_wait(barT, phT);
             phT ^= 1u;
             // ---- pre-update alive mask at the ring positions; this thread's g and x (channels 8q .. 8q+7) ----
-            if (tid < T2_XR * 18) {
-                const int rr = tid / 18, q = tid % 18;
+            if (tid < 2 * T2_XR * 18) {      // two threads per ring position: even / odd channels of xin = x + goal * pre (nca.py:177)
+                const int grp = tid >= T2_XR * 18 ? 1 : 0, p = tid - grp * T2_XR * 18;
+                const int rr = p / 18, q = p % 18;
                 float mx = 0.0f;
                 const float* lp = sL + rr * T2_XS + T2_XO + q - 1;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) mx = fmaxf(mx, lp[dy * T2_XS + dx]);
-                sPre[tid] = (g.liv < 0 || mx > g.thr) ? 1.0f : 0.0f;
+                const float pre = (g.liv < 0 || mx > g.thr) ? 1.0f : 0.0f;
+                if (grp == 0) sPre[p] = pre;
+                const int o0 = rr * T2_XS + T2_XO + q;
+#pragma unroll 2
+                for (int c = grp; c < C; c += 2) {
+                    const int o = o0 + c * T2_XR * T2_XS;
+                    sXin[(c * T2_XR + rr) * 18 + q] = fmaf(sG[o], pre, sX[o]);
+                }
             }
             float xres[8], gn[8];
 #pragma unroll
@@ -785,12 +794,6 @@ __global__ void __launch_bounds__(EB_NTHREADS, 1) enc_bwd_tc_kernel(const __grid
                 const int c = 8 * qtr + i;
                 xres[i] = c < C ? sX[(c * T2_XR + py + 1) * T2_XS + T2_XO + px + 1] : 0.0f;
                 gn[i] = c < C ? sGn[(c * T2_TH + py) * T2_TW + px] : 0.0f;
-            }
-            bar_sync_n(1, EB_NCOMP);
-            for (int i = tid; i < C * T2_XR * 18; i += EB_NCOMP) {
-                const int q = i % 18, rr = (i / 18) % T2_XR, c = i / (18 * T2_XR);
-                const int o = (c * T2_XR + rr) * T2_XS + T2_XO + q;
-                sXin[i] = fmaf(sG[o], sPre[rr * 18 + q], sX[o]);
             }
             bar_sync_n(1, EB_NCOMP);
             // ---- learned depthwise 3x3 -> A1 ----
