@@ -289,7 +289,9 @@ class Workload:
     def fwd_only(self, x_in, seed):
         with torch.no_grad():
             if self.c["kind"] == "enc":
-                return self.model.grow(x_in, self.T, self.goal, seed=seed)
+                for r in range(self.c["rollouts"]):
+                    out = self.model.grow(x_in, self.T, self.goal, seed=seed * 4 + r)
+                return out
             return self.model.forward_nsteps(x_in, self.T, seed=seed, **self.extra)[0]
 
 

@@ -469,6 +469,29 @@ def enc_step(x, goal, wp, wa, ba, wb, bb, wc, fire, living_dim=3, thr=0.1, fast=
     return torch.clamp(x, -10.0, 10.0)
 
 
+def enc_step_bf16ops(x, goal, wp, wa, ba, wb, bb, wc, fire, living_dim=3, thr=0.1):
+    """enc_step with "the update MLP runs in BF16" stated from the math (see dynca_step_bf16ops): the operands of the three 1x1-conv
+    GEMMs (perception vector, Wa, h1, Wb, h2, Wc) rounded to bfloat16, fp32 accumulation, everything else fp32; autograd with
+    straight-through rounding.  Knows nothing about the kernels."""
+    q = _RoundBf16STE.apply
+    pre = enc_alive(x, living_dim, thr)
+    xin = x + goal * pre
+    p = enc_perception_fast(xin, wp)
+    h1 = torch.relu(torch.einsum("jk,bkhw->bjhw", q(wa), q(p)) + ba[None, :, None, None])
+    h2 = torch.relu(torch.einsum("jk,bkhw->bjhw", q(wb), q(h1)) + bb[None, :, None, None])
+    out = torch.einsum("cj,bjhw->bchw", q(wc), q(h2))
+    x = x + fire * out
+    post = enc_alive(x, living_dim, thr)
+    x = x * (pre & post).to(x.dtype)
+    return torch.clamp(x, -10.0, 10.0)
+
+
+def enc_rollout_bf16ops(x, goal, wp, wa, ba, wb, bb, wc, fires, living_dim=3, thr=0.1):
+    for t in range(fires.shape[0]):
+        x = enc_step_bf16ops(x, goal, wp, wa, ba, wb, bb, wc, fires[t], living_dim, thr)
+    return x
+
+
 def enc_rollout(x, goal, wp, wa, ba, wb, bb, wc, fires, living_dim=3, thr=0.1, keep=False):
     hist = [x]
     for t in range(fires.shape[0]):
