@@ -326,15 +326,19 @@ def _emu_preact(xr, w1q, b1q, scales, mode, cond, variant):
     if cond is not None:
         zq = torch.cat([zq, _hilo(cond)], dim=1)
     if variant == 2 and len(scales) == 2:
-        # tcgen05 v2: fine and coarse perception are rounded separately, the coarse pre-activation is rounded to bf16
-        # before the (exact, constant-matrix) bilinear upsample; W1 / n_scales is exact
+        # tcgen05 v2 (dynca_tc2.cu): fine and coarse perception are rounded separately, their sum Z = z_fine + up(z_coarse) is
+        # accumulated in fp32 (constant-matrix upsample on the tensor cores) and rounded once more: Z is the ONE perception
+        # operand of the step (forward GEMM, BPTT recompute and weight gradient); W1 / n_scales is exact
         xd = xr.detach()
         zf = bf16r(perceive(xd, 0, mode))
         zc = bf16r(perceive_coarse(xd, mode))
+        zsum = bf16r(zf + up2(zc))
         w1h = w1q[:, :4 * C] * 0.5
-        a = torch.einsum("jk,bkhw->bjhw", w1h, zf) + up2(bf16r(torch.einsum("jk,bkhw->bjhw", w1h, zc)))
+        a = torch.einsum("jk,bkhw->bjhw", w1h, zsum)
+        zq = zsum
         if cond is not None:
             a = a + torch.einsum("jk,bkhw->bjhw", w1q[:, 4 * C:], _hilo(cond))
+            zq = torch.cat([zsum, _hilo(cond)], dim=1)
         a = a + b1q[None, :, None, None]
     else:
         a = torch.einsum("jk,bkhw->bjhw", w1q, zq) + b1q[None, :, None, None]
@@ -381,20 +385,20 @@ def dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, scales, mode, cond, g
         ga = bf16r(gh * (a > 0).to(gh.dtype))
         gb1 += ga.sum(dim=(0, 2, 3))
         if two:
-            # dynca_tc2_bwd.cu: the coarse scale goes through GaU = U^T g_a (fp32 accumulate, rounded to bf16); the weight
-            # gradient pairs g_a with the rounded fine perception and GaU with the rounded coarse perception
+            # dynca_tc3_bwd.cu: the weight gradient pairs g_a with the recorded operand Z; g_z = g_a . W1h is fp32, its fine part goes
+            # through the transposed stencils as it is, its coarse part through U^T applied to bf16(g_z)
             xd = xr.detach().clone().requires_grad_(True)
             with torch.enable_grad():
                 zf = perceive(xd, 0, mode)
                 zc = perceive_coarse(xd, mode)
-            zfq, zcq = bf16r(zf.detach()), bf16r(zc.detach())
-            gaU = _up2T_tiled_bf16(ga)
+                zc_leaf = zc.detach().clone().requires_grad_(True)
+                zu = up2(zc_leaf)
             w1h = w1q[:, :4 * C] * 0.5
-            gw1[:, :4 * C] += 0.5 * (torch.einsum("bjhw,bkhw->jk", ga, zfq) + torch.einsum("bjhw,bkhw->jk", gaU, zcq))
+            gw1[:, :4 * C] += 0.5 * torch.einsum("bjhw,bkhw->jk", ga, zq[:, :4 * C])
             if cond is not None:
-                gw1[:, 4 * C:] += torch.einsum("bjhw,bkhw->jk", ga, _hilo(cond))
+                gw1[:, 4 * C:] += torch.einsum("bjhw,bkhw->jk", ga, zq[:, 4 * C:])
             gzf = torch.einsum("bjhw,jk->bkhw", ga, w1h)
-            gzc = torch.einsum("bjhw,jk->bkhw", gaU, w1h)
+            (gzc,) = torch.autograd.grad(zu, zc_leaf, bf16r(gzf))
             (gx,) = torch.autograd.grad([zf, zc], xd, [gzf, gzc])
         else:
             gw1 += torch.einsum("bjhw,bkhw->jk", ga, zq)

@@ -10,8 +10,10 @@
 //          -> A1 [128 x K1] bf16, K-major UMMA layout (K order k' = 8*(c/2) + 4*(c%2) + filter, then the cond chunk)
 //   coarse perception -> Zc [64 x 64] bf16 (60 coarse cells of the 6x10 footprint, replicate-extended at the image
 //          border so that the x2 bilinear upsample, dynca.py:93-94, becomes a constant matrix U)
-//   MMA  : Dc = Zc . W1h^T   (W1h = W1 / n_scales)            -> TMEM -> bf16 -> DcB  (B operand, MN-major)
-//          D1 = A1 . W1h^T + U . DcB                           = W1h (z_fine + up(z_coarse)) + cond / bias terms
+//   MMA  : Dz = U . Zc + A1 . I  (fp32, tensor memory)          -> bf16 -> Z = z_fine + up(z_coarse), in place over A1: the ONE
+//          perception operand of the step (perceive_multiscale's sum, dynca.py:99-111; the 1 / n_scales is in W1h = W1 / n_scales),
+//          which is also what the operand history records for the BPTT (dynca_tc3_bwd.cu)
+//          D1 = Z . W1h^T                                      = W1h (z_fine + up(z_coarse)) + cond / bias terms
 //   E1   : h = relu(D1) -> bf16 A2 ;  MMA: D2 = A2 . W2^T ;  E2: x' = x + (D2 + b2) * fire, coalesced NCHW store, and
 //          the 2x2 means of x' (the coarse state of the next step) by warp shuffles.
 #include <mutex>
@@ -29,14 +31,16 @@ struct T2FwdArgs {
     const __nv_bfloat16* B1; const __nv_bfloat16* B2; const float* b2p; const __nv_bfloat16* U;
     FireMask fm;
     T2Tiles tl;
-    uint8_t* op_out;   // operand history of this step (A1 | Zc of every tile, for the BPTT) or NULL
+    uint8_t* op_out;   // operand history of this step (Z of every tile, for the BPTT) or NULL
+    int ops_only;      // record the operand and stop (no MLP, no state written): the BPTT's recompute path
+    const __nv_bfloat16* Iz;   // identity operand [64][64] (two scales)
     int dbg;
     int pdl;           // launch with the programmatic-serialization attribute (not the first step of a call)
     long long* tdbg;   // optional phase timestamps of CTA 0 (debug)
 };
 
 struct T2Smem {
-    uint32_t b1, b2w, u, x, xc, cond, uni, a1, zc, dcb, total;
+    uint32_t b1, b2w, u, iz, x, xc, cond, uni, a1, zc, total;
 };
 __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16Geom& bg) {
     T2Smem s;
@@ -44,6 +48,7 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
     s.b1 = o; o += bg.b1_bytes;
     s.b2w = o; o += bg.b2_bytes;
     s.u = o; o += g.ns == 2 ? 16384u : 0u;
+    s.iz = o; o += g.ns == 2 ? 8192u : 0u;
     o = (o + 127u) & ~127u;
     s.x = o; o += (uint32_t)g.C * T2_XR * T2_XS * 4u;
     o = (o + 127u) & ~127u;
@@ -54,8 +59,7 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
     s.uni = o;
     s.a1 = o;
     s.zc = s.a1 + bg.a1_bytes;
-    s.dcb = s.zc + (g.ns == 2 ? 8192u : 0u);
-    o += bg.a1_bytes + (g.ns == 2 ? 8192u + (uint32_t)(g.fc / 8) * 1024u : 0u);       // the hidden layer (A2) lives in tensor memory
+    o += bg.a1_bytes + (g.ns == 2 ? 8192u + 1024u : 0u);       // the hidden layer (A2) lives in tensor memory; + slack for the M = 128 reads of Zc
     s.total = o;
     return s;
 }
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
     uint64_t* barM = reinterpret_cast<uint64_t*>(smem);         // MMA batch complete (tcgen05.commit)
     uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 8);     // TMA complete
     uint64_t* barA = reinterpret_cast<uint64_t*>(smem + 16);    // 256 arrivals: A1 / Zc written, stage consumed
-    uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 24);    // 256 arrivals: DcB written
+    uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 24);    // 256 arrivals: Z written (two scales)
     uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 32);    // 256 arrivals: A2 written
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 40);
     uint64_t* barZ = reinterpret_cast<uint64_t*>(smem + 48);    // 256 arrivals: Zc written (two scales: the coarse MMA starts under the fine perception)
@@ -84,12 +88,12 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
     uint8_t* sB1 = smem + L.b1;
     uint8_t* sB2w = smem + L.b2w;
     uint8_t* sU = smem + L.u;
+    uint8_t* sIz = smem + L.iz;
     float* sX = reinterpret_cast<float*>(smem + L.x);
     float* sXc = reinterpret_cast<float*>(smem + L.xc);
     float* sCond = reinterpret_cast<float*>(smem + L.cond);
     uint8_t* sA1 = smem + L.a1;
     uint8_t* sZc = smem + L.zc;
-    uint8_t* sDcB = smem + L.dcb;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
     const size_t plane = (size_t)H * W;
@@ -104,9 +108,12 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
         reinterpret_cast<uint4*>(sB1)[i] = __ldg(reinterpret_cast<const uint4*>(a.B1) + i);
     for (uint32_t i = tid; i < bg.b2_bytes / 16; i += T2_NTHREADS)
         reinterpret_cast<uint4*>(sB2w)[i] = __ldg(reinterpret_cast<const uint4*>(a.B2) + i);
-    if (NS == 2)
+    if (NS == 2) {
         for (uint32_t i = tid; i < 16384u / 16; i += T2_NTHREADS)
             reinterpret_cast<uint4*>(sU)[i] = __ldg(reinterpret_cast<const uint4*>(a.U) + i);
+        for (uint32_t i = tid; i < 8192u / 16; i += T2_NTHREADS)
+            reinterpret_cast<uint4*>(sIz)[i] = __ldg(reinterpret_cast<const uint4*>(a.Iz) + i);
+    }
     if (tid < 16) sB2[tid] = a.b2p[tid];
     if (tid == 0) {
         mbar_init(barM, 1);
@@ -124,23 +131,25 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     griddep_wait();          // the previous step's state (and coarse state) is complete and visible from here on
-    // columns, two scales: Dc 0..127, D1 128..255; D2 (0..15) and the bf16 hidden layer A2 (64..127, 8 columns per K step)
-    // reuse Dc's columns, dead once DcB is written.  One scale (128 columns, so that three CTAs fit an SM): A2 is written
+    // columns, two scales: Dz 0..63, D1 128..255; D2 (0..15) reuses Dz's columns (dead once Z is written), the bf16 hidden layer
+    // A2 sits at 64..127 (8 columns per K step).  One scale (128 columns, so that three CTAs fit an SM): A2 is written
     // IN PLACE over D1 - a thread owns 64 columns of its lane, reads 32 of them and then stores the 16 packed columns over
     // the part it has already read: K step ks sits at column 64*(ks/4) + 8*(ks%4); D2 goes to columns 32..47 (read by then).
     const uint32_t TM_D1 = NS == 2 ? 128u : 0u, TM_DC = 0u, TM_D2 = NS == 2 ? 0u : 32u;
     if (warp == 8) {
         // =========================== MMA / TMA warp ===========================
         const uint32_t idesc1 = umma_idesc_bf16(128, fc), idesc2 = umma_idesc_bf16(128, 16);
-        const uint32_t idescU = umma_idesc_bf16(128, fc) | (1u << 16);      // B operand MN-major
+        const int N6 = 16 * ((bg.npairs + 1) / 2);                          // perception columns, padded to the MMA granularity
+        const uint32_t idescZ = umma_idesc_bf16(128, N6), idescUz = idescZ | (1u << 16);      // Dz; B operand (Zc) MN-major
         const uint32_t lbo_b1 = (uint32_t)(fc / 8) * 128u;
         // every operand lives at a fixed shared-memory address: descriptors are kernel constants, K steps are adds
         const uint64_t dA1 = umma_desc(smem_u32(sA1), 2048u, 128u), dB1 = umma_desc(smem_u32(sB1), lbo_b1, 128u);
         const uint64_t dZc = umma_desc(smem_u32(sZc), 1024u, 128u), dU = umma_desc(smem_u32(sU), 2048u, 128u);
-        const uint64_t dDcB = umma_desc(smem_u32(sDcB), 128u, 1024u);
+        const uint64_t dZcB = umma_desc(smem_u32(sZc), 128u, 1024u);      // Zc as [K = coarse cell][N = k'], MN-major B
+        const uint64_t dIz = umma_desc(smem_u32(sIz), 1024u, 128u);
         const uint64_t dB2 = umma_desc(smem_u32(sB2w), 256u, 128u);
         const uint64_t sB1k = (uint64_t)((2u * lbo_b1) >> 4);
-        const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, k2steps = fc / 16;
+        const int k1steps = bg.K1 / 16, kzsteps = N6 / 16, k2steps = fc / 16;
         const uint32_t op_bytes = dynca_tc2_op_tile_bytes(g);
         const CUtensorMap* const ptm_x = &tm_x;
         const CUtensorMap* const ptm_xc = &tm_xc;
@@ -167,17 +176,14 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++miter) {
             T2_MSTAMP(0);
             if (NS == 2) {
-                // Dc = Zc . W1h^T over the perception columns as soon as the coarse operand is there (the compute warps go on with
-                // the fine perception).  Zc holds 64 rows per K chunk (LBO 1024): rows 64..127 of the M = 128 instruction alias the
-                // next chunk (finite values) and produce rows of Dc nobody reads
+                // Dz = U . Zc as soon as the coarse operand is there (the compute warps go on with the fine perception) ...
                 mbar_wait(barZ, phZ);
                 phZ ^= 1u;
                 tc_fence_after();
                 if (leader) {
-#pragma unroll 4
-                    for (int ks = 0; ks < kcsteps; ++ks)
-                        umma_ss(tmem_base + TM_DC, dZc + (uint64_t)(ks * (2048 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
-                    umma_commit(barM);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_ss(tmem_base + TM_DC, dU + (uint64_t)(ks * (4096 >> 4)), dZcB + (uint64_t)(ks * (256 >> 4)), idescUz, ks > 0);
                 }
             }
             mbar_wait(barA, phA);
@@ -185,29 +191,39 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
             tc_fence_after();
             T2_MSTAMP(1);
             if (leader) {
-#pragma unroll 5
-                for (int ks = 0; ks < k1steps; ++ks)
-                    umma_ss(tmem_base + TM_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
-                if (NS == 1) umma_commit(barM);
+                if (NS == 2) {
+                    // ... + A1 . I: the fine perception joins the accumulator exactly (bf16 x 1 in fp32)
+#pragma unroll 4
+                    for (int ks = 0; ks < kzsteps; ++ks)
+                        umma_ss(tmem_base + TM_DC, dA1 + (uint64_t)(ks * (4096 >> 4)), dIz + (uint64_t)(ks * (2048 >> 4)), idescZ, true);
+                    umma_commit(barM);
+                }
                 if (tile + (int)gridDim.x < n_tiles) T2_ISSUE_TMA(tile + gridDim.x);     // the stage is free
-                // operand history: the perception operands of this tile (A1 and, behind it, Zc) go to global memory as one
-                // bulk copy, so that the BPTT loads them instead of recomputing the perception (behind the MMAs and the
-                // prefetch, which the compute warps are waiting for)
-                if (a.op_out) bulk_store(a.op_out + (size_t)tile * op_bytes, sA1, op_bytes);
             }
             T2_MSTAMP(2);
             if (NS == 2) {
-                mbar_wait(barB, phB);
+                mbar_wait(barB, phB);                           // Z written over A1
                 phB ^= 1u;
                 tc_fence_after();
                 T2_MSTAMP(3);
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)         // D1 += U . DcB
-                        umma_ss(tmem_base + TM_D1, dU + (uint64_t)(ks * (4096 >> 4)), dDcB + (uint64_t)(ks * (256 >> 4)), idescU, true);
+            }
+            if (leader) {
+                if (!a.ops_only) {
+#pragma unroll 5
+                    for (int ks = 0; ks < k1steps; ++ks)
+                        umma_ss(tmem_base + TM_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
                     umma_commit(barM);
                 }
+                // operand history: the perception operand of this tile goes to global memory as one bulk copy, so that the BPTT
+                // loads it instead of recomputing the perception
+                if (a.op_out) bulk_store(a.op_out + (size_t)tile * op_bytes, sA1, op_bytes);
+                if (a.ops_only) {
+                    bulk_store_wait_read();
+                    mbar_arrive(barM);                          // the operand buffer is free (no MMA reads it in this mode)
+                    continue;
+                }
             }
+            if (a.ops_only) continue;
             T2_MSTAMP(4);
             mbar_wait(barC, phC);
             phC ^= 1u;
@@ -317,24 +333,25 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
                 phM ^= 1u;
                 tc_fence_after();
                 T2_STAMP(5);
-                // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major ----
-                if ((warp & 3) < 2) {
-                    const int q = r;                          // 0..63
-#pragma unroll 1
-                    for (int blk = 0; blk < 2; ++blk) {
-                        const int j0 = 64 * half + 32 * blk;
-                        if (j0 < fc) {
-                            uint32_t v[32];
-                            tmem_ld32(tmem_lane + TM_DC + (uint32_t)j0, v);
-                            tmem_ld_wait();
+                // ---- Dz = z_fine + up(z_coarse) (fp32) -> bf16 -> Z, in place over the perception chunks of A1 (the MMA that read
+                //      them is complete); thread -> its row, columns 32 half .. 32 half + 31 ----
+                {
+                    const int N6 = 16 * ((bg.npairs + 1) / 2);
+                    const int j0 = 32 * half;
+                    if (j0 < N6) {
+                        uint32_t v[32];
+                        if (N6 - j0 >= 32) tmem_ld32(tmem_lane + TM_DC + (uint32_t)j0, v);
+                        else tmem_ld16(tmem_lane + TM_DC + (uint32_t)j0, v);
+                        tmem_ld_wait();
 #pragma unroll
-                            for (int qq = 0; qq < 4; ++qq) {
+                        for (int qq = 0; qq < 4; ++qq) {
+                            if (j0 + 8 * qq < N6) {
                                 uint4 o;
                                 o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
                                 o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
                                 o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
                                 o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                                *reinterpret_cast<uint4*>(sDcB + (uint32_t)(j0 / 8 + qq) * 1024u + (uint32_t)q * 16u) = o;
+                                *reinterpret_cast<uint4*>(sA1 + (uint32_t)(j0 / 8 + qq) * 2048u + row_off) = o;
                             }
                         }
                     }
@@ -342,7 +359,12 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
                 T2_STAMP(6);
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(barB);                             // ---- B: DcB complete ----
+                mbar_arrive(barB);                             // ---- B: Z complete ----
+            }
+            if (a.ops_only) {                                  // the operand is recorded by the MMA warp; wait until the buffer is free again
+                mbar_wait(barM, phM);
+                phM ^= 1u;
+                continue;
             }
             T2_STAMP(8);
             mbar_wait(barM, phM);
@@ -419,8 +441,8 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
 __global__ void dynca_tc2_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __restrict__ w1, const float* __restrict__ b1,
                                       const float* __restrict__ w2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ B1,
                                       __nv_bfloat16* __restrict__ B2, float* __restrict__ b2p, __nv_bfloat16* __restrict__ U) {
-    const int n1 = bg.K1 * g.fc, n2 = g.fc * 16, n3 = g.ns == 2 ? 128 * 64 : 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + 16 + n3; i += gridDim.x * blockDim.x) {
+    const int n1 = bg.K1 * g.fc, n2 = g.fc * 16, n3 = g.ns == 2 ? 128 * 64 : 0, n4 = g.ns == 2 ? 64 * 64 : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + 16 + n3 + n4; i += gridDim.x * blockDim.x) {
         if (i < n1) {
             const int kp = i / g.fc, j = i % g.fc;
             const int kc = kp >> 3, s = kp & 7;
@@ -442,6 +464,10 @@ __global__ void dynca_tc2_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __r
         } else if (i < n1 + n2 + 16) {
             const int c = i - n1 - n2;
             b2p[c] = c < g.C ? b2[c] : 0.0f;
+        } else if (i >= n1 + n2 + 16 + n3) {
+            // identity [N = 64][K = 64], K-major, behind U: A1 . I adds the fine perception to the accumulator of U . Zc
+            const int e = i - n1 - n2 - 16 - n3, n = e / 64, k = e % 64;
+            U[128 * 64 + (size_t)(k >> 3) * 512 + (size_t)n * 8 + (k & 7)] = __float2bfloat16_rn(n == k ? 1.0f : 0.0f);
         } else {
             const int e = i - n1 - n2 - 16, rr = e / 64, q = e % 64;
             const int py = rr >> 4, px = rr & 15, qy = q / T2_QW, qx = q % T2_QW;
@@ -459,7 +485,7 @@ __global__ void dynca_tc2_prep_kernel(DyncaGeom g, Bf16Geom bg, const float* __r
 }
 
 // ---- host side --------------------------------------------------------------------------------------------
-// operand history: per step, per tile, A1 [K1/8 chunks x 128 rows x 16 B] followed (two scales) by Zc [8 x 64 x 16 B]
+// operand history: per step, per tile, the perception operand Z [K1/8 chunks x 128 rows x 16 B]
 size_t dynca_tc2_op_hist_bytes(const DyncaGeom& g, int T) {
     const T2Tiles tl = t2_make_tiles(g.B, g.H, g.W);
     return (size_t)T * tl.n_tiles * dynca_tc2_op_tile_bytes(g);
@@ -477,7 +503,7 @@ bool dynca_tc2_supported(const DyncaGeom& g) {
 size_t dynca_tc2_weight_bytes(const DyncaGeom& g) {
     Bf16Geom bg;
     if (dynca_bf16_geom(g, &bg)) return 0;
-    return nca_align_up((size_t)bg.b1_bytes + bg.b2_bytes + 64 + (g.ns == 2 ? 16384 : 0), 256);
+    return nca_align_up((size_t)bg.b1_bytes + bg.b2_bytes + 64 + (g.ns == 2 ? 16384 + 8192 : 0), 256);
 }
 
 int dynca_tc2_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s) {
@@ -510,10 +536,11 @@ int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, cons
 
 int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Maps* m, int slot_in, const float* x_in, float* x_out,
                            int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s, int pdl,
-                           uint8_t* op_out) {
+                           uint8_t* op_out, int ops_only) {
     T2FwdArgs a;
     a.pdl = pdl;
     a.op_out = op_out;
+    a.ops_only = ops_only;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
     a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.x_out = x_out; a.xc_out = xc_out;
@@ -522,6 +549,7 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     a.B2 = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes);
     a.b2p = (const float*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes);
     a.U = (const __nv_bfloat16*)((const uint8_t*)ws + a.bg.b1_bytes + a.bg.b2_bytes + 64);
+    a.Iz = a.U + 128 * 64;
     a.fm = fm;
     { const char* e = getenv("NCA_T2_DBG"); a.dbg = e ? atoi(e) : 0; }
     static long long* tdbg = nullptr;

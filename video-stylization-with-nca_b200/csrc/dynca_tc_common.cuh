@@ -178,10 +178,10 @@ struct Bf16Geom {
     int tmem_cols;   // power of two >= N1 + 16
     uint32_t a1_bytes, b1_bytes, a2_bytes, b2_bytes;
 };
-// bytes of one tile's perception operands in the operand history (A1, then Zc with two scales)
+// bytes of one tile's perception operand in the operand history
 __host__ __device__ static inline uint32_t dynca_tc2_op_tile_bytes(const DyncaGeom& g) {
     const int npairs = (g.C + 1) / 2, K1 = ((npairs + 1) * 8 + 15) / 16 * 16;
-    return (uint32_t)(K1 / 8) * 2048u + (g.ns == 2 ? 8192u : 0u);
+    return (uint32_t)(K1 / 8) * 2048u;
 }
 static inline int dynca_bf16_geom(const DyncaGeom& g, Bf16Geom* b) {
     if (g.fc % 16 != 0 || g.fc < 16 || g.fc > 240) { nca_set_error("bf16 path needs fc %% 16 == 0 and 16 <= fc <= 240 (got %d)", g.fc); return NCA_ERR_UNSUPPORTED; }

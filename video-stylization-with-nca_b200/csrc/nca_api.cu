@@ -104,6 +104,8 @@ size_t nca_dynca_workspace_bytes(const NcaDyncaDesc* d, int32_t backward) {
         const size_t b2 = x3 ? 0 : (backward ? dynca_tc2_bwd_weight_bytes(g) : dynca_tc2_weight_bytes(g));
         // coarse slots: forward 2 (ping-pong states); backward 3 (coarse state of the step + 2 coarse-gradient buffers)
         bytes += (b > b2 ? b : b2) + (backward ? 3 : 2) * dynca_bf16_coarse_floats(g) * sizeof(float);
+        // one step of perception operands for the tcgen05 BPTT when the caller kept no operand history (recompute path)
+        if (backward && !x3 && dynca_tc2_bwd_supported(g)) bytes = nca_align_up(bytes, 256) + dynca_tc2_op_hist_bytes(g, 1);
     }
     return bytes;
 }
@@ -282,6 +284,7 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
         NCA_CUDA_OK(cudaMemsetAsync(gx0, 0, nb, s));
         if (g.ns == 2) NCA_CUDA_OK(cudaMemsetAsync(G[0], 0, 2 * nc * sizeof(float), s));
         const bool chist = coarse_hist != nullptr && g.ns == 2;
+        uint8_t* op_scratch = (uint8_t*)workspace + nca_align_up((size_t)((uint8_t*)(wsXc + 3 * nc) - (uint8_t*)workspace), 256);
         DyncaTc2Maps xm, gm_final, gm[2];
         NCA_CHECK_ARG(NCA_ALIGNED16(cond) && NCA_ALIGNED16(g_final), "cond / g_final must be 16-byte aligned");
         rc = dynca_tc2_make_maps(g, states, T + 1, chist ? coarse_hist : wsXc, chist ? T + 1 : 1, ncx, cond, &xm);
@@ -297,16 +300,21 @@ int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const fl
             float* gout = t == 0 ? gx0 : F[p_out];
             const float* tap = nullptr;
             if (ti >= 0 && tap_steps[ti] == t + 1) tap = g_taps[ti--];
-            const float* xc_t = nullptr;
-            if (g.ns == 2) {
-                if (chist) xc_t = coarse_hist + (size_t)t * ncx;
-                else { rc = dynca_bf16_coarsen(g, states + (size_t)t * n, wsXc, s); if (rc) return rc; xc_t = wsXc; }
+            const uint8_t* op_t = op_hist ? (const uint8_t*)op_hist + (size_t)t * dynca_tc2_op_hist_bytes(g, 1) : nullptr;
+            if (op_t == nullptr) {
+                // no operand history for this step: the forward kernel records the operand of states[t] into the workspace and stops
+                const float* xc_t = nullptr;
+                if (g.ns == 2) {
+                    if (chist) xc_t = coarse_hist + (size_t)t * ncx;
+                    else { rc = dynca_bf16_coarsen(g, states + (size_t)t * n, wsXc, s); if (rc) return rc; xc_t = wsXc; }
+                }
+                rc = dynca_tc2_forward_step(g, wsB, &xm, t, states + (size_t)t * n, nullptr, chist ? t : 0, xc_t, nullptr, cond, fm, s, 0, op_scratch, 1);
+                if (rc) return rc;
+                op_t = op_scratch;
             }
-            rc = dynca_tc2_backward_step(g, wsB, wsG, &xm, t, states + (size_t)t * n, chist ? t : 0, xc_t,
-                                         from_final ? &gm_final : &gm[p_in], from_final ? const_cast<float*>(g_final) : F[p_in], G[p_in],
-                                         from_final ? 0 : 1, 1, tap, tap_c, tap_scale, gout, G[p_out], cond, fm, s,
-                                         t < T - 1 && (chist || g.ns != 2),       // no coarsen launch in between
-                                         op_hist ? (const uint8_t*)op_hist + (size_t)t * dynca_tc2_op_hist_bytes(g, 1) : nullptr);
+            rc = dynca_tc2_backward_step(g, wsB, wsG, from_final ? &gm_final : &gm[p_in], from_final ? const_cast<float*>(g_final) : F[p_in], G[p_in],
+                                         from_final ? 0 : 1, 1, tap, tap_c, tap_scale, gout, G[p_out], fm, s,
+                                         t < T - 1 && op_hist != nullptr, op_t);
             if (rc) return rc;
             p_in = p_out;
         }

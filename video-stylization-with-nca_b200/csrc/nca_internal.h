@@ -38,22 +38,22 @@ size_t dynca_tc2_weight_bytes(const DyncaGeom& g);
 int dynca_tc2_prep_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s);
 int dynca_tc2_make_maps(const DyncaGeom& g, const float* states, int slots, const float* coarse, int cslots, size_t cslot_floats,
                         const float* cond, DyncaTc2Maps* m);
+// ops_only: record the perception operand of the step in op_out and do nothing else (the BPTT's recompute path)
 int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Maps* m, int slot_in, const float* x_in, float* x_out,
                            int cslot_in, const float* xc_in, float* xc_out, const float* cond, const FireMask& fm, cudaStream_t s, int pdl,
-                           uint8_t* op_out);
+                           uint8_t* op_out, int ops_only = 0);
 size_t dynca_tc2_op_hist_bytes(const DyncaGeom& g, int T);
 int dynca_bf16_coarsen(const DyncaGeom& g, const float* x, float* xc, cudaStream_t s);
 
-// dynca_tc2_bwd.cu (tcgen05 BPTT, 8x16 tiles + TMA)
+// dynca_tc3_bwd.cu (tcgen05 BPTT, 8x16 tiles, transposed perception gradient + register stencils; needs the recorded operand)
 bool dynca_tc2_bwd_supported(const DyncaGeom& g);
 size_t dynca_tc2_bwd_weight_bytes(const DyncaGeom& g);
 int dynca_tc2_prep_bwd_weights(const DyncaGeom& g, const NcaDyncaWeights* w, void* ws, cudaStream_t s);
 int dynca_tc2_make_gmaps(const DyncaGeom& g, const float* gfine, const float* gcoarse, DyncaTc2Maps* m);
 int dynca_tc2_add_coarse(const DyncaGeom& g, const float* gc, float* gx, cudaStream_t s);
-int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const DyncaTc2Maps* xm, int slot_in, const float* x_in,
-                            int cslot_in, const float* xc_in, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
-                            int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out,
-                            const float* cond, const FireMask& fm, cudaStream_t s, int pdl, const uint8_t* op_in);
+int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
+                            int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out, const FireMask& fm,
+                            cudaStream_t s, int pdl, const uint8_t* op_in);
 
 // enc_tc.cu (ConditionedNCA forward on tcgen05)
 struct EncTcMaps { alignas(64) unsigned char x[128]; alignas(64) unsigned char l[128]; alignas(64) unsigned char g[128]; };
