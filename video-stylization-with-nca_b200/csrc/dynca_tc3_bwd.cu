@@ -28,7 +28,7 @@
 
 #define T3_NTHREADS 544
 #define T3_NE 256          // threads of the E warps
-#define T3_HDR 2048u
+#define T3_HDR 4096u
 #define T3_D1 0u
 #define T3_R0 128u
 #define T3_D4 384u
@@ -85,6 +85,14 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {        
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t v[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+// wait for the tensor-memory loads; the registers of the last load are operands, so that no use of them can be scheduled above
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
                  : "memory");
 }
 // image index that padded coordinate r of an axis of n cells folds back to under the TRANSPOSED padding (-1 = dropped)
@@ -228,7 +236,8 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
     uint64_t* barM4 = reinterpret_cast<uint64_t*>(smem + 96);      // [2] MMA -> S group: D7^T
     uint64_t* barE = reinterpret_cast<uint64_t*>(smem + 112);      // [2] S group -> MMA: D7^T consumed (128)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
-    float* sFire2 = reinterpret_cast<float*>(smem + 256);          // 2 x 128 floats
+    uint64_t* barF = reinterpret_cast<uint64_t*>(smem + 192);      // [4] MMA warp -> E: fire table of a tile written
+    float* sFire4 = reinterpret_cast<float*>(smem + 256);          // 4 x 128 floats (ring over tiles)
     uint8_t* sB1 = smem + L.b1;
     uint8_t* sB2d = smem + L.b2d;
     uint8_t* sU = smem + L.u;
@@ -269,6 +278,7 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
         mbar_init(barD, 128); mbar_init(barD + 1, 128);
         mbar_init(barM4, 1); mbar_init(barM4 + 1, 1);
         mbar_init(barE, 128); mbar_init(barE + 1, 128);
+        mbar_init(barF, 1); mbar_init(barF + 1, 1); mbar_init(barF + 2, 1); mbar_init(barF + 3, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(tmem_slot, 512u);
@@ -325,6 +335,18 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
                 umma_commit(barM4 + (it & 1));
             }
         };
+        // fire decisions of a tile (Philox, one quad per lane) in the idle time of this warp, three tiles ahead of their use
+        auto fire_table = [&](int it) {
+            if (a.fm.supplied || it >= n_my) return;
+            int tb_, ty_, tx_;
+            t2_tile_decode(a.tl, (int)blockIdx.x + it * (int)gridDim.x, tb_, ty_, tx_);
+            t2_fire_tile(a.fm, tb_, ty_, tx_, H, W, lane, sFire4 + (it & 3) * 128);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barF + (it & 3));
+        };
+        fire_table(0);
+        fire_table(1);
+        fire_table(2);
         recompute(0);
         for (int it = 0; it < n_my; ++it) {
             const uint64_t par = (uint64_t)(it & 1);
@@ -357,6 +379,7 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
                 }
                 recompute(it + 1);
             }
+            fire_table(it + 3);
             if (leader) T3_STAMP(it, 19);
         }
         if (NS == 2) coarse(n_my - 1);
@@ -382,11 +405,6 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
             mbar_expect_tx(bo, op_bytes);
             bulk_load(sZ2 + (uint32_t)(it & 1) * bg.a1_bytes, src, op_bytes, bo);
         };
-        auto fire_table = [&](int it) {     // one warp: fire decisions of local tile it -> sFire2[it & 1]
-            int tb_, ty_, tx_;
-            t2_tile_decode(a.tl, (int)blockIdx.x + it * (int)gridDim.x, tb_, ty_, tx_);
-            t2_fire_tile(a.fm, tb_, ty_, tx_, H, W, lane, sFire2 + (it & 1) * 128);
-        };
         // ---- P1 of local tile it: gn = g + 0.25 gc (+ tap), Gy = fire * gn -> bf16, residual red.add, zeroing of the consumed tile ----
         auto p1 = [&](int it) {
             int b, y0, x0;
@@ -395,8 +413,8 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
             const bool inimg = gy < H && gx < W;
             const int par = it & 1;
             mbar_wait(barT, (uint32_t)(it & 1));
-            if (it >= 1) mbar_wait(barG + ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));      // fire table of this tile published
-            const float fire = a.fm.supplied ? (inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f) : sFire2[par * 128 + r];
+            if (!a.fm.supplied) mbar_wait(barF + (it & 3), (uint32_t)((it >> 2) & 1));      // fire table of this tile published
+            const float fire = a.fm.supplied ? (inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f) : sFire4[(it & 3) * 128 + r];
             float gn[8];
             const float* gp = sGn + (8 * eh * T2_TH + py) * T2_TW + px;
             const float* gcp = sGcn + (8 * eh * 4 + (py >> 1)) * 8 + (px >> 1);
@@ -448,7 +466,6 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
                     *reinterpret_cast<float4*>(a.gc_in + ((size_t)b * C + c) * (plane >> 2) + (size_t)((y0 >> 1) + rr) * (W >> 1) + (x0 >> 1) + x4) =
                         make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (!a.fm.supplied && it + 1 < n_my && warp == ((it + 1) & 7)) fire_table(it + 1);
             fence_proxy_async();          // operand images -> MMA; stage reads before the next TMA write
             mbar_arrive(barG + par);
             if (tid == 0 && it + 1 < n_my) {      // the stage is free once every E thread has read it
@@ -457,13 +474,11 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
             }
         };
 
-        if (!a.fm.supplied && warp == 0) fire_table(0);
         if (tid == 0) {
             issue_g(0);
             issue_z(0);
             if (n_my > 1) issue_z(1);
         }
-        bar_sync_n(1, T3_NE);
         p1(0);
         for (int it = 0; it < n_my; ++it) {
             const uint32_t R = T3_R0 + 128u * (uint32_t)(it & 1);
@@ -556,6 +571,7 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
         const int m = (q & 1) * 32 + lane;                       // k' = 4c + f
         const int f = m & 3, c = m >> 2;
         const T3Coef K = t3_coef(f);
+        const float2 v0 = make_float2(K.v0, K.v0), v1 = make_float2(K.v1, K.v1), v2 = make_float2(K.v2, K.v2);
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         T3Emit e;
         e.H = H; e.W = W; e.pad = g.pad;
@@ -575,52 +591,67 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
             if (q == 0 && lane == 0) T3_STAMP(it, 9);
             // ---- fine transposed stencil of tile rows 4P .. 4P+3 -> output rows 4P-1 .. 4P+4.  One copy of the code (the kernel
             //      must stay inside the instruction cache): iteration k streams input row k (none for k = 4, 5) through the two
-            //      pending output rows PA (row k) / PB (row k + 1) and emits output row k - 1 ----
+            //      pending output rows PA (row k) / PB (row k + 1) and emits output row k - 1; the tensor-memory load of row k + 1 is
+            //      in flight during the reduction of row k - 1.  Pairs of ring positions (2j, 2j+1) are packed fp32 pairs. ----
             {
-                float PA[18], PB[18];
+                float2 PA[9], PB[9];
+                float of[18];
 #pragma unroll
-                for (int p = 0; p < 18; ++p) { PA[p] = 0.0f; PB[p] = 0.0f; }
+                for (int j = 0; j < 9; ++j) { PA[j] = make_float2(0.f, 0.f); PB[j] = make_float2(0.f, 0.f); }
+#pragma unroll
+                for (int p = 0; p < 18; ++p) of[p] = 0.0f;
 #pragma unroll 1
-                for (int k = 0; k < 6; ++k) {
-                    float T[18], Gc[16];
-#pragma unroll
-                    for (int p = 0; p < 18; ++p) T[p] = 0.0f;
-#pragma unroll
-                    for (int p = 0; p < 16; ++p) Gc[p] = 0.0f;
+                for (int k = 0; k < 7; ++k) {
+                    uint32_t gv[16];
+                    if (k < 4) tmem_ld16(R + 16u * (uint32_t)(4 * P + k), gv);      // in flight during the reduction below
+                    if (k >= 1) t3_emit_fine(e, 4 * P + k - 2, of);                   // output row produced by the previous iteration
+                    float2 o[9];
                     if (k < 4) {
-                        uint32_t gv[16];
-                        tmem_ld16(R + 16u * (uint32_t)(4 * P + k), gv);
-                        tmem_ld_wait();
+                        tmem_ld_wait16(gv);
+                        float G[20];                             // G[i + 2] = cell i: two zero cells either side
+                        G[0] = G[1] = G[18] = G[19] = 0.0f;
 #pragma unroll
-                        for (int p = 0; p < 18; ++p) {
-                            float t = 0.0f;
-                            if (p < 16) t = K.h0 * __uint_as_float(gv[p]);
-                            if (p >= 1 && p < 17) t = fmaf(K.h1, __uint_as_float(gv[p - 1]), t);
-                            if (p >= 2) t = fmaf(K.h2, __uint_as_float(gv[p - 2]), t);
-                            T[p] = t;
+                        for (int i = 0; i < 16; ++i) G[i + 2] = __uint_as_float(gv[i]);
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            // T(p) = h0 G(p) + h1 G(p-1) + h2 G(p-2), p = 2j, 2j+1
+                            float2 t;
+                            t.x = fmaf(K.h2, G[2 * j], fmaf(K.h1, G[2 * j + 1], K.h0 * G[2 * j + 2]));
+                            t.y = fmaf(K.h2, G[2 * j + 1], fmaf(K.h1, G[2 * j + 2], K.h0 * G[2 * j + 3]));
+                            o[j] = f2fma(v0, t, PA[j]);
+                            PA[j] = f2fma(v1, t, PB[j]);
+                            PB[j] = make_float2(K.v2 * t.x, K.v2 * t.y);
                         }
+                        // centre term of the Laplacian: position p = cell + 1
 #pragma unroll
-                        for (int p = 0; p < 16; ++p) Gc[p] = K.ctr * __uint_as_float(gv[p]);
+                        for (int j = 0; j < 9; ++j) {
+                            PA[j].x = fmaf(K.ctr, G[2 * j + 1], PA[j].x);
+                            PA[j].y = fmaf(K.ctr, G[2 * j + 2], PA[j].y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) { o[j] = PA[j]; PA[j] = PB[j]; PB[j] = make_float2(0.f, 0.f); }
                     }
-                    float o[18];
 #pragma unroll
-                    for (int p = 0; p < 18; ++p) { o[p] = fmaf(K.v0, T[p], PA[p]); PA[p] = fmaf(K.v1, T[p], PB[p]); PB[p] = K.v2 * T[p]; }
-#pragma unroll
-                    for (int p = 0; p < 16; ++p) PA[p + 1] += Gc[p];
-                    t3_emit_fine(e, 4 * P + k - 1, o);
+                    for (int j = 0; j < 9; ++j) { of[2 * j] = o[j].x; of[2 * j + 1] = o[j].y; }
                 }
             }
             if (q == 0 && lane == 0) T3_STAMP(it, 10);
             if (NS == 2) {
-                // ---- bf16(D6^T) of all 128 cells, packed in place into the first 64 columns: the A operand of D7^T ----
+                // ---- bf16(D6^T) of all 128 cells, packed in place into the first 64 columns: the A operand of D7^T
+                //      (row y goes to columns 8y .. 8y+7, always behind the columns still to be read) ----
 #pragma unroll 1
-                for (int y = 0; y < 8; ++y) {
-                    uint32_t gv[16], pk[8];
-                    tmem_ld16(R + 16u * (uint32_t)y, gv);
+                for (int y = 0; y < 8; y += 2) {
+                    uint32_t ga[16], gb[16], pk[8];
+                    tmem_ld16(R + 16u * (uint32_t)y, ga);
+                    tmem_ld16(R + 16u * (uint32_t)y + 16u, gb);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(gv[2 * i]), __uint_as_float(gv[2 * i + 1]));
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(ga[2 * i]), __uint_as_float(ga[2 * i + 1]));
                     tmem_st8(R + 8u * (uint32_t)y, pk);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(gb[2 * i]), __uint_as_float(gb[2 * i + 1]));
+                    tmem_st8(R + 8u * (uint32_t)y + 8u, pk);
                 }
                 tmem_st_wait();
             }
@@ -652,7 +683,7 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
                 }
                 const bool cfast = cy0 >= 1 && cx0 >= 1 && cy0 + T2_QH + 1 <= Hc && cx0 + T2_QW + 1 <= Wc;
                 if (!cfast) {
-                    // transpose of the replicate extension: footprint cells outside the image fold into the clamped cell
+                    // transpose of the replicate extension: footprint cells outside the image fold into the clamped cell.
                     // rows: footprint row fr sits at coarse row cy0 + fr; rows below the image fold upwards (chain), row 0 of a top
                     // tile folds into row 1.  Only the rows this pair holds are touched: the single case that would cross the pairs
                     // (a ragged tile with 4 valid rows: row 3 -> row 2) is handled by relocating row 3 below, its rows 4 / 5 are zero.
@@ -680,28 +711,39 @@ __global__ void __launch_bounds__(T3_NTHREADS, 1) dynca_bwd_tc3_kernel(const __g
                 float* gcb = a.gc_out + ((size_t)b * C + (e.act ? c : 0)) * (plane >> 2);
                 const int rb = (P == 1 && cy0 + 3 >= Hc) ? Hc - 1 : cy0 + 3 * P;      // coarse image row of the pair's first footprint row
                 const int oy0 = rb - 1;                          // coarse image row of the first output row
-                float PA[12], PB[12];
+                float2 PA[6], PB[6];
 #pragma unroll
-                for (int p = 0; p < 12; ++p) { PA[p] = 0.0f; PB[p] = 0.0f; }
+                for (int j = 0; j < 6; ++j) { PA[j] = make_float2(0.f, 0.f); PB[j] = make_float2(0.f, 0.f); }
 #pragma unroll 1
                 for (int k = 0; k < 5; ++k) {
-                    float Gk[10], T[12];
+                    float2 o[6];
+                    if (k < 3) {
+                        float Gk[14];                            // Gk[p + 2]: two zero cells either side
+                        Gk[0] = Gk[1] = Gk[12] = Gk[13] = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 10; ++i) Gk[i] = k == 0 ? G[0][i] : (k == 1 ? G[1][i] : (k == 2 ? G[2][i] : 0.0f));
+                        for (int i = 0; i < 10; ++i) Gk[i + 2] = k == 0 ? G[0][i] : (k == 1 ? G[1][i] : G[2][i]);
 #pragma unroll
-                    for (int p = 0; p < 12; ++p) {
-                        float t = 0.0f;
-                        if (p < 10) t = K.h0 * Gk[p];
-                        if (p >= 1 && p < 11) t = fmaf(K.h1, Gk[p - 1], t);
-                        if (p >= 2) t = fmaf(K.h2, Gk[p - 2], t);
-                        T[p] = t;
+                        for (int j = 0; j < 6; ++j) {
+                            float2 t;
+                            t.x = fmaf(K.h2, Gk[2 * j], fmaf(K.h1, Gk[2 * j + 1], K.h0 * Gk[2 * j + 2]));
+                            t.y = fmaf(K.h2, Gk[2 * j + 1], fmaf(K.h1, Gk[2 * j + 2], K.h0 * Gk[2 * j + 3]));
+                            o[j] = f2fma(v0, t, PA[j]);
+                            PA[j] = f2fma(v1, t, PB[j]);
+                            PB[j] = make_float2(K.v2 * t.x, K.v2 * t.y);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            PA[j].x = fmaf(K.ctr, Gk[2 * j + 1], PA[j].x);
+                            PA[j].y = fmaf(K.ctr, Gk[2 * j + 2], PA[j].y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) { o[j] = PA[j]; PA[j] = PB[j]; PB[j] = make_float2(0.f, 0.f); }
                     }
-                    float o[12];
+                    float of[12];
 #pragma unroll
-                    for (int p = 0; p < 12; ++p) { o[p] = fmaf(K.v0, T[p], PA[p]); PA[p] = fmaf(K.v1, T[p], PB[p]); PB[p] = K.v2 * T[p]; }
-#pragma unroll
-                    for (int p = 0; p < 10; ++p) PA[p + 1] = fmaf(K.ctr, Gk[p], PA[p + 1]);
-                    t3_emit_coarse(ec, gcb, oy0 + k, cx0 - 1, Hc, Wc, o);
+                    for (int j = 0; j < 6; ++j) { of[2 * j] = o[j].x; of[2 * j + 1] = o[j].y; }
+                    t3_emit_coarse(ec, gcb, oy0 + k, cx0 - 1, Hc, Wc, of);
                 }
                 tc_fence_before();
                 mbar_arrive(barE + grp);
