@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnca_b200.so")
-SOURCES = ["nca_api.cu", "dynca_f32.cu", "dynca_bf16.cu", "dynca_tc2.cu", "dynca_tc3_bwd.cu", "enc_f32.cu", "enc_tc.cu", "enc_encoder.cu", "nca_callers.cu"]
+SOURCES = ["nca_api.cu", "dynca_f32.cu", "dynca_bf16.cu", "dynca_tc2.cu", "dynca_tc2_bwd.cu", "enc_f32.cu", "enc_tc.cu", "enc_encoder.cu", "nca_callers.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1,18 +1,19 @@
 // DyNCA BPTT step on the 5th-gen tensor cores, second generation (8x16 tiles, TMA staging; companion of dynca_tc2.cu).
 // Replaces autograd's replay of ExtraChannels/models/dynca.py:113-123 for one step:
-//   given x_t (recomputed perception / hidden layer) and g = dL/dx_{t+1}  ->  dL/dx_t and the weight gradients.
+//   given the perception operand Z_t the forward recorded (operand history; dynca_tc2.cu: Z = z_fine + up(z_coarse), one bf16
+//   operand for both scales) and g = dL/dx_{t+1}  ->  dL/dx_t and the weight gradients.
 //
 // One CTA per SM = 16 compute warps (512 threads, one 8x16 tile at a time) + 1 MMA / TMA warp.  Row r = py*16 + px of
 // every M = 128 operand is TMEM lane r; thread (r, q = tid >> 7) owns cell r and channels 4q .. 4q+3 (= 16 columns of
 // the K-permuted perception order k' = 8*(c/2) + 4*(c%2) + filter) or hidden units 32q .. 32q+31.
 //
-//   TMA   : x_t tile + ring, coarse x_t tile, g_{t+1} tile, coarse part of g_{t+1} (see below)
-//   P1    : fine perception -> A1, coarse perception -> Zc (as the forward kernel); g_y = fire * g -> bf16 Gy
-//   MMA   : Dc = Zc.W1h^T | D1 = A1.W1h^T (+ U.DcB after the Dc round trip) | D3 = Gy.W2           (recompute, dgrad 2)
+//   TMA   : g_{t+1} tile, coarse part of g_{t+1} (see below); bulk copy of Z (operand history)
+//   P1    : g_y = fire * g -> bf16 Gy
+//   MMA   : D1 = Z.W1h^T | D3 = Gy.W2                                                                  (recompute, dgrad 2)
 //   E1    : h = relu(D1) -> H ; g_a = D3 * [D1 > 0] -> Ga                                             (bf16 operands)
-//   MMA   : D4 += H^T.Gy (gW2) | D5 += Ga^T.A1 (gW1, fine part) | D6 = Ga.W1h (g_z fine) | GaU = U^T.Ga
-//   E2    : D6 -> zero-padded fp32 planes ; GaU -> bf16
-//   MMA   : D5 += GaU^T.Zc (gW1, coarse part) | D7 = GaU.W1h (g_z on the coarse footprint)
+//   MMA   : D4 += H^T.Gy (gW2) | D5 += Ga^T.Z (gW1) | D6 = Ga.W1h (g_z)
+//   E2    : D6 -> zero-padded fp32 planes, and -> bf16 D6b (MN-major operand)
+//   MMA   : D7 = U^T.D6b (g_z on the coarse footprint: transpose of the x2 bilinear upsample)
 //   P5/P6 : transposed perception: fine planes -> red.add into dL/dx_t ; coarse planes -> red.add into a COARSE gradient
 //           buffer gc [B,C,H/2,W/2].  The 2x2-mean transpose (0.25 * gc broadcast to the 4 fine cells) is applied when
 //           the next BPTT step reads its g tile (and once at the end for dL/dx_0), so the coarse scale costs one
@@ -20,15 +21,15 @@
 //   P7    : the tile of g_{t+1} (and of its coarse part) this CTA consumed is zeroed in place: those buffers are the
 //           outputs of the next launch (ping-pong), so no per-step memset is needed.
 // Weight gradients stay in TMEM (D4, D5) over all tiles of the CTA and are flushed once with red.add.
+// Without an operand history the caller first lets the forward kernel record Z of the step (ops_only, nca_api.cu).
 #include "dynca_tc2.cuh"
 
 #define TB_NCOMP 512
 #define TB_NTHREADS 544
 #define TB_HDR 2048u
 // TMEM columns
-#define TB_DC 0u      // Dc, later GaU
-#define TB_D1 128u    // D1, later D6 (128..) and D7 (192..)
-#define TB_D3 256u
+#define TB_D1 128u
+#define TB_D3 256u    // D3, later D6 (256..) and D7 (320..)
 #define TB_D4 384u
 #define TB_D5 400u
 // fp32 plane geometry (zero padded): fine cell (py,px) at [py+1][px+5] of [10][24] (ring position (oy,ox) reads rows
@@ -45,9 +46,6 @@
 struct T2BwdArgs {
     DyncaGeom g;
     Bf16Geom bg;
-    const float* cond;
-    const float* x_in; const float* xc_in;            // states[t], its coarse state (border patches)
-    int slot_in, cslot_in;
     float* g_in; float* gc_in;                        // dL/dx_{t+1} and its coarse part (read through TMA; zeroed if zero_in)
     int zero_in, zero_cin;
     const float* g_tap; int tap_c; float tap_scale;   // optional rgb tap at states[t+1]
@@ -57,20 +55,18 @@ struct T2BwdArgs {
     FireMask fm;
     T2Tiles tl;
     int pdl;           // launch with the programmatic-serialization attribute (not the first step of a call)
-    const uint8_t* op_in;   // operand history of this step (A1 | Zc per tile, written by the forward) or NULL = recompute the perception
+    const uint8_t* op_in;   // operand history of this step (Z per tile, written by the forward)
     long long* tdbg;
 };
 
 struct TBSmem {
-    uint32_t b1, b2d, u, x, xc, gn, gcn, cond, zc, gau, a1, gy, h, ga, px, ctr, cpx, cctr, total;
+    uint32_t b1, b2d, u, cpl, gn, gcn, d6b, z, gy, h, ga, px, ctr, cpx, cctr, total;
 };
-// A1 / Zc / Gy are double buffered over tiles (the next tile's operands are produced while the gradient MMAs of the
-// current tile run); DcB shares its storage with GaU (DcB is dead once D1 is complete, GaU is written after that); the
-// fp32 planes overlay H | Ga (dead once the gradient MMAs are complete), the coarse planes reuse the fine planes.
-// With an operand history (oph) nothing is staged in x / xc: with two scales that space (grown to 30 KB) holds the coarse planes
-// instead, which then have a life of their own - their zero pads are written once per launch, and the D7 scatter runs on two
-// otherwise idle warps during the fine transposed stencil instead of in three barrier-separated phases after it.
-__host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16Geom& bg, bool oph) {
+// Z / Gy are double buffered over tiles (the next tile's operands arrive while the gradient MMAs of the current tile run); the
+// fine fp32 planes overlay H | Ga (dead once the gradient MMAs are complete).  With two scales the coarse planes have storage of
+// their own - their zero pads are written once per launch, and the D7 scatter runs on two otherwise idle warps during the fine
+// transposed stencil.
+__host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16Geom& bg) {
     TBSmem s;
     const uint32_t C = (uint32_t)g.C;
     uint32_t o = TB_HDR;
@@ -78,20 +74,14 @@ __host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16G
     s.b2d = o; o += (uint32_t)(g.fc / 8) * 256u;
     s.u = o; o += g.ns == 2 ? 16384u : 0u;
     o = (o + 127u) & ~127u;
-    const uint32_t own_cp = (oph && g.ns == 2) ? 3u * C * TB_CPP * 4u + C * T2_QH * T2_QW * 4u : 0u;      // coarse planes + centre terms
-    s.x = o; o += own_cp ? 0u : C * T2_XR * T2_XS * 4u;
-    o = (o + 127u) & ~127u;
-    s.xc = o; o += own_cp ? own_cp : (g.ns == 2 ? C * T2_CR * T2_CS * 4u : 0u);
+    s.cpl = o; o += g.ns == 2 ? 3u * C * TB_CPP * 4u + C * T2_QH * T2_QW * 4u : 0u;      // coarse planes + centre terms
     o = (o + 127u) & ~127u;
     s.gn = o; o += C * T2_TH * T2_TW * 4u;
     o = (o + 127u) & ~127u;
     s.gcn = o; o += g.ns == 2 ? C * 4u * 8u * 4u : 0u;
     o = (o + 127u) & ~127u;
-    s.cond = o; o += g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u;
-    o = (o + 127u) & ~127u;
-    s.zc = o; o += g.ns == 2 ? 2u * 8192u : 0u;          // 2 buffers; M = 128 reads of a 64-row chunk alias what follows
-    s.gau = o; o += g.ns == 2 ? 16u * 1024u : 0u;        // GaU | DcB, 16 chunks whatever fc is
-    s.a1 = o; o += 2u * bg.a1_bytes;
+    s.d6b = o; o += g.ns == 2 ? 16u * 1024u : 0u;        // bf16(D6), [k' / 8][128 cells][8]: 8 chunks used, M = 128 views read further
+    s.z = o; o += 2u * bg.a1_bytes;
     s.gy = o; o += 2u * 4096u;
     o = (o + 127u) & ~127u;
     s.h = o; o += 16u * 2048u;
@@ -99,16 +89,8 @@ __host__ __device__ static inline TBSmem tb_smem(const DyncaGeom& g, const Bf16G
     uint32_t p = s.h;
     s.px = p; p += 3u * C * TB_PP * 4u;
     s.ctr = p; p += C * T2_TH * T2_TW * 4u;
-    const uint32_t pf = p;
-    p = s.h;
-    if (own_cp) {
-        s.cpx = s.xc; s.cctr = s.xc + 3u * C * TB_CPP * 4u;
-    } else {
-        s.cpx = p; p += g.ns == 2 ? 3u * C * TB_CPP * 4u : 0u;
-        s.cctr = p; p += g.ns == 2 ? C * T2_QH * T2_QW * 4u : 0u;
-    }
-    const uint32_t pm = pf > p ? pf : p;
-    s.total = (o > pm ? o : pm) + 1024u;                 // + slack for the aliasing reads of the last buffer
+    s.cpx = s.cpl; s.cctr = s.cpl + 3u * C * TB_CPP * 4u;
+    s.total = (o > p ? o : p) + 1024u;                   // + slack for the aliasing reads of the last buffer
     return s;
 }
 
@@ -171,70 +153,51 @@ __device__ __forceinline__ int tb_fold(int r, int n, int mode) {
     return r < 0 ? 1 : n - 2;                                         // reflect
 }
 
-// OPH = with an operand history (compile-time: the recompute paths - perception, border patches, overlaid coarse planes - are
-// then not in the kernel at all; the kernel is far larger than the instruction cache and jumps over dead regions cost fetches)
-template <int NS, bool OPH, int CT, int FT>
-__global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
-                                                                        const __grid_constant__ CUtensorMap tm_xc,
-                                                                        const __grid_constant__ CUtensorMap tm_g,
-                                                                        const __grid_constant__ CUtensorMap tm_gc,
-                                                                        const __grid_constant__ CUtensorMap tm_c, const T2BwdArgs a) {
+template <int NS, int CT, int FT>
+__global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_g,
+                                                                        const __grid_constant__ CUtensorMap tm_gc, const T2BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     DyncaGeom g = a.g;
     Bf16Geom bg = a.bg;
     t2_specialize<CT, FT>(g, bg);
-    const TBSmem L = tb_smem(g, bg, OPH);
+    const TBSmem L = tb_smem(g, bg);
 #ifdef NCA_T2_TIMING
     if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) a.tdbg[128] = clock64();
 #endif
     // MMA-completion barriers (tcgen05.commit), one per batch of a tile, so that the MMA warp may run ahead into the next
     // tile's recompute batch without a barrier ever being two phases ahead of its waiters
-    uint64_t* barM1 = reinterpret_cast<uint64_t*>(smem);          // Dc
     uint64_t* barM2 = reinterpret_cast<uint64_t*>(smem + 8);      // D1, D3
-    uint64_t* barM3 = reinterpret_cast<uint64_t*>(smem + 16);     // D4, D5 (fine), D6, GaU
-    uint64_t* barM4 = reinterpret_cast<uint64_t*>(smem + 24);     // D5 (coarse), D7
+    uint64_t* barM3 = reinterpret_cast<uint64_t*>(smem + 16);     // D4, D5, D6
+    uint64_t* barM4 = reinterpret_cast<uint64_t*>(smem + 24);     // D7
     uint64_t* barT = reinterpret_cast<uint64_t*>(smem + 32);      // TMA
     // compute -> MMA warp hand-offs (512 arrivals each)
-    uint64_t* barA = reinterpret_cast<uint64_t*>(smem + 40);      // A1 / Zc written
     uint64_t* barG = reinterpret_cast<uint64_t*>(smem + 48);      // Gy written, stage consumed
-    uint64_t* barB = reinterpret_cast<uint64_t*>(smem + 56);      // DcB written
     uint64_t* barC = reinterpret_cast<uint64_t*>(smem + 64);      // H, Ga written; D1 / D3 consumed
-    uint64_t* barD = reinterpret_cast<uint64_t*>(smem + 72);      // GaU (bf16) written
+    uint64_t* barD = reinterpret_cast<uint64_t*>(smem + 72);      // D6b (bf16) written
     uint64_t* barE = reinterpret_cast<uint64_t*>(smem + 80);      // D6 / D7 read back (their TMEM columns are D3's)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 88);
-    uint64_t* barO = reinterpret_cast<uint64_t*>(smem + 96);      // [2]: operand-history tiles (A1 | Zc) of buffer 0 / 1 loaded
+    uint64_t* barO = reinterpret_cast<uint64_t*>(smem + 96);      // [2]: operand-history tile (Z) of buffer 0 / 1 loaded
     float* sFire2 = reinterpret_cast<float*>(smem + 128);               // 2 x 128 floats
-    uint32_t* sCpe2 = reinterpret_cast<uint32_t*>(smem + 128 + 1024);   // 2 x 24
     uint8_t* sB1 = smem + L.b1;
     uint8_t* sB2d = smem + L.b2d;
     uint8_t* sU = smem + L.u;
-    float* sX = reinterpret_cast<float*>(smem + L.x);
-    float* sXc = reinterpret_cast<float*>(smem + L.xc);
     float* sGn = reinterpret_cast<float*>(smem + L.gn);
     float* sGcn = reinterpret_cast<float*>(smem + L.gcn);
-    float* sCond = reinterpret_cast<float*>(smem + L.cond);
-    uint8_t* sZc2 = smem + L.zc;          // 2 x 8192
-    uint8_t* sGaU = smem + L.gau;         // GaU, and DcB before it
-    uint8_t* sDcB = sGaU;
-    uint8_t* sA12 = smem + L.a1;          // 2 x a1_bytes
+    uint8_t* sD6b = smem + L.d6b;
+    uint8_t* sZ2 = smem + L.z;            // 2 x a1_bytes
     uint8_t* sGy2 = smem + L.gy;          // 2 x 4096
     uint8_t* sH = smem + L.h;
     uint8_t* sGa = smem + L.ga;
-    float* sPX = reinterpret_cast<float*>(smem + L.px);       // [3][C][12][20]: X, Y, L planes
+    float* sPX = reinterpret_cast<float*>(smem + L.px);       // [3][C][10][24]: X, Y, L planes
     float* sCtr = reinterpret_cast<float*>(smem + L.ctr);     // [C][8][16]: g + g_z(id) - 16 g_z(lap)
-    float* sCPX = reinterpret_cast<float*>(smem + L.cpx);     // [3][C][10][14]   (reuses the fine planes after P5)
+    float* sCPX = reinterpret_cast<float*>(smem + L.cpx);     // [3][C][10][14]
     float* sCCtr = reinterpret_cast<float*>(smem + L.cctr);   // [C][6][10]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = g.C, H = g.H, W = g.W, fc = g.fc;
     const size_t plane = (size_t)H * W;
     const int n_tiles = a.tl.n_tiles;
     const int N6 = 16 * ((bg.npairs + 1) / 2);                 // perception columns of g_z, padded to the MMA granularity
-    // with an operand history the perception operands arrive by bulk copy and only the gradient tiles are staged
-    constexpr bool ophist = OPH;
-    const uint32_t stage_bytes = ophist ? (uint32_t)C * (T2_TH * T2_TW + (NS == 2 ? 32 : 0)) * 4u
-                                        : (uint32_t)C * (T2_XR * T2_XS + T2_TH * T2_TW) * 4u +
-                                              (NS == 2 ? (uint32_t)C * (T2_CR * T2_CS + 32) * 4u : 0u) +
-                                              (g.cond_kind == NCA_COND_TENSOR ? (uint32_t)g.cc * T2_TH * T2_TW * 4u : 0u);
+    const uint32_t stage_bytes = (uint32_t)C * (T2_TH * T2_TW + (NS == 2 ? 32 : 0)) * 4u;
     const uint32_t op_bytes = dynca_tc2_op_tile_bytes(g);
 
     griddep_launch();
@@ -246,15 +209,12 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     if (NS == 2)
         for (uint32_t i = tid; i < 16384u / 16; i += TB_NTHREADS)
             reinterpret_cast<uint4*>(sU)[i] = __ldg(reinterpret_cast<const uint4*>(a.U) + i);
-    // everything an MMA may read before the tile loop writes it must be finite: clear the dynamic area once
-    for (uint32_t i = L.zc / 16 + tid; i < L.total / 16; i += TB_NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    if (NS == 2 && OPH)      // persistent coarse planes: the zero pads are written here, once
-        for (uint32_t i = L.cpx / 16 + tid; i < (L.cctr + (uint32_t)g.C * T2_QH * T2_QW * 4u) / 16; i += TB_NTHREADS)
-            reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    // everything an MMA may read before the tile loop writes it must be finite: clear the dynamic area once (this also writes the
+    // zero pads of the persistent coarse planes)
+    for (uint32_t i = L.cpl / 16 + tid; i < L.total / 16; i += TB_NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        mbar_init(barM1, 1); mbar_init(barM2, 1); mbar_init(barM3, 1); mbar_init(barM4, 1); mbar_init(barT, 1);
-        mbar_init(barA, TB_NCOMP); mbar_init(barG, TB_NCOMP); mbar_init(barB, TB_NCOMP);
-        mbar_init(barC, TB_NCOMP); mbar_init(barD, TB_NCOMP); mbar_init(barE, TB_NCOMP);
+        mbar_init(barM2, 1); mbar_init(barM3, 1); mbar_init(barM4, 1); mbar_init(barT, 1);
+        mbar_init(barG, TB_NCOMP); mbar_init(barC, TB_NCOMP); mbar_init(barD, TB_NCOMP); mbar_init(barE, TB_NCOMP);
         mbar_init(barO, 1); mbar_init(barO + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -269,37 +229,29 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
     if (warp == 16) {
         // =========================== MMA / TMA warp ===========================
         // deliberately from the ARGUMENTS, not from the specialised geometry: with every descriptor of this warp a compile-time
-        // constant, nvcc 12.9 generates a <2, true, 16, 128> instantiation whose recompute / weight-gradient products are wrong
-        // (caught by tests/test_dynca_bf16_gpu.py; either this value or the K-step count read at run time avoids it, the
-        // single-scale and the (12, 96) / (13, 96) instantiations are not affected).  The cost is nil: one warp's scalar arithmetic.
+        // constant, nvcc 12.9 generated a two-scale (16, 128) instantiation whose recompute / weight-gradient products were wrong
+        // (caught by tests/test_dynca_bf16_gpu.py).  The cost is nil: one warp's scalar arithmetic.
         const uint32_t lbo_b1 = (uint32_t)(a.g.fc / 8) * 128u;
-        const uint32_t id_fc = umma_idesc_bf16(128, fc), id_fc_bmn = id_fc | (1u << 16), id_fc_mn = umma_idesc_bf16_mn(128, fc);
-        const uint32_t id_w2 = umma_idesc_bf16_mn(128, 16), id_w1 = umma_idesc_bf16_mn(128, bg.K1), id_w1c = umma_idesc_bf16_mn(128, N6);
+        const uint32_t id_fc = umma_idesc_bf16(128, fc);
+        const uint32_t id_w2 = umma_idesc_bf16_mn(128, 16), id_w1 = umma_idesc_bf16_mn(128, bg.K1), id_c = umma_idesc_bf16_mn(128, N6);
         const uint32_t id_gz = umma_idesc_bf16(128, N6) | (1u << 16);
         const uint64_t dB1 = umma_desc(smem_u32(sB1), lbo_b1, 128u);
-        const uint64_t dU = umma_desc(smem_u32(sU), 2048u, 128u);
-        const uint64_t dDcB = umma_desc(smem_u32(sDcB), 128u, 1024u);
         const uint64_t dB2d = umma_desc(smem_u32(sB2d), lbo_b1, 128u);
-        // MN-major views (cells / coarse cells / hidden units become K): LBO = 128 (K groups), SBO = group stride of MN
+        // MN-major views (cells / hidden units become K): LBO = 128 (K groups), SBO = group stride of MN
         const uint64_t dHt = umma_desc(smem_u32(sH), 128u, 2048u), dGat = umma_desc(smem_u32(sGa), 128u, 2048u);
-        const uint64_t dUt = umma_desc(smem_u32(sU), 128u, 2048u);
+        const uint64_t dUt = umma_desc(smem_u32(sU), 128u, 2048u);                    // U^T: [M = coarse cell][K = cell]
+        const uint64_t dD6bt = umma_desc(smem_u32(sD6b), 128u, 2048u);                // bf16(D6) as [N = k'][K = cell]
         const uint64_t dGa = umma_desc(smem_u32(sGa), 2048u, 128u);
         const uint64_t dB1t = umma_desc(smem_u32(sB1), 128u, lbo_b1);                 // B1 as [N = k'][K = hidden]
-        const uint64_t dGaUt = umma_desc(smem_u32(sGaU), 128u, 1024u);
-        const uint64_t dGaU = umma_desc(smem_u32(sGaU), 1024u, 128u);
         // double-buffered operands: descriptor of buffer 1 = descriptor of buffer 0 + (bytes >> 4)
-        const uint64_t dA1_0 = umma_desc(smem_u32(sA12), 2048u, 128u), dA1t_0 = umma_desc(smem_u32(sA12), 128u, 2048u);
-        const uint64_t dZc_0 = umma_desc(smem_u32(sZc2), 1024u, 128u), dZct_0 = umma_desc(smem_u32(sZc2), 128u, 1024u);
+        const uint64_t dZ_0 = umma_desc(smem_u32(sZ2), 2048u, 128u), dZt_0 = umma_desc(smem_u32(sZ2), 128u, 2048u);
         const uint64_t dGy_0 = umma_desc(smem_u32(sGy2), 2048u, 128u), dGyt_0 = umma_desc(smem_u32(sGy2), 128u, 2048u);
-        const uint64_t oA1 = (uint64_t)(bg.a1_bytes >> 4), oZc = (uint64_t)(8192u >> 4), oGy = (uint64_t)(4096u >> 4);
+        const uint64_t oZ = (uint64_t)(bg.a1_bytes >> 4), oGy = (uint64_t)(4096u >> 4);
         const uint64_t sB1k = (uint64_t)((2u * lbo_b1) >> 4);
-        const int k1steps = bg.K1 / 16, kcsteps = (bg.npairs + 1) / 2, kfsteps = fc / 16;
-        const CUtensorMap* const ptm_x = &tm_x;
-        const CUtensorMap* const ptm_xc = &tm_xc;
+        const int k1steps = bg.K1 / 16, kfsteps = fc / 16;
         const CUtensorMap* const ptm_g = &tm_g;
         const CUtensorMap* const ptm_gc = &tm_gc;
-        const CUtensorMap* const ptm_c = &tm_c;
-        uint32_t phA = 0, phB = 0, phC = 0, phD = 0, phG = 0, phE = 0;
+        uint32_t phC = 0, phD = 0, phG = 0, phE = 0;
         const bool leader = elect_one();
         bool first = true;
 #define TB_ISSUE_TMA(tile_)                                                                                              \
@@ -308,57 +260,40 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         int tb_, ty_, tx_;                                                                                               \
         t2_tile_decode(a.tl, tt_, tb_, ty_, tx_);                                                                        \
         mbar_expect_tx(barT, stage_bytes);                                                                               \
-        if (!ophist) tma_load_5d(sX, ptm_x, barT, tx_ - 4, ty_ - 1, 0, tb_, a.slot_in);                                  \
         tma_load_5d(sGn, ptm_g, barT, tx_, ty_, 0, tb_, 0);                                                              \
-        if (!ophist && g.cond_kind == NCA_COND_TENSOR) tma_load_5d(sCond, ptm_c, barT, tx_, ty_, 0, tb_, 0);             \
-        if (NS == 2) {                                                                                                   \
-            if (!ophist) tma_load_5d(sXc, ptm_xc, barT, (tx_ >> 1) - 4, (ty_ >> 1) - 2, 0, tb_, a.cslot_in);             \
-            tma_load_5d(sGcn, ptm_gc, barT, tx_ >> 1, ty_ >> 1, 0, tb_, 0);                                              \
-        }                                                                                                                \
+        if (NS == 2) tma_load_5d(sGcn, ptm_gc, barT, tx_ >> 1, ty_ >> 1, 0, tb_, 0);                                     \
     } while (0)
-        // operand-history tile of sequence index par_ (buffer par_ & 1): A1 then Zc, one mbarrier per buffer
+        // operand-history tile of sequence index par_ (buffer par_ & 1), one mbarrier per buffer
 #define TB_ISSUE_OP(tile_, par_)                                                                                         \
     do {                                                                                                                 \
         const uint8_t* src_ = a.op_in + (size_t)(tile_) * op_bytes;                                                      \
         uint64_t* bo_ = barO + ((par_) & 1);                                                                             \
         mbar_expect_tx(bo_, op_bytes);                                                                                   \
-        bulk_load(sA12 + (uint32_t)((par_) & 1) * bg.a1_bytes, src_, bg.a1_bytes, bo_);                                  \
-        if (NS == 2) bulk_load(sZc2 + (uint32_t)((par_) & 1) * 8192u, src_ + bg.a1_bytes, 8192u, bo_);                   \
+        bulk_load(sZ2 + (uint32_t)((par_) & 1) * bg.a1_bytes, src_, op_bytes, bo_);                                      \
     } while (0)
         if (leader && (int)blockIdx.x < n_tiles) {
             TB_ISSUE_TMA(blockIdx.x);
-            if (ophist) {
-                TB_ISSUE_OP(blockIdx.x, 0);
-                if ((int)(blockIdx.x + gridDim.x) < n_tiles) TB_ISSUE_OP(blockIdx.x + gridDim.x, 1);
-            }
+            TB_ISSUE_OP(blockIdx.x, 0);
+            if ((int)(blockIdx.x + gridDim.x) < n_tiles) TB_ISSUE_OP(blockIdx.x + gridDim.x, 1);
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint64_t par = (uint64_t)(it & 1);
-            if (ophist && it >= 1) {
-                // the operand buffer of the previous tile is free once its last reader (the second gradient batch, or the
-                // first with one scale) is complete: load the tile after this one into it
-                mbar_wait(NS == 2 ? barM4 : barM3, (uint32_t)((it - 1) & 1));
+            if (it >= 1) {
+                // the operand buffer of the previous tile is free once its last reader (the gradient batch) is complete: load the
+                // tile after this one into it
+                mbar_wait(barM3, (uint32_t)((it - 1) & 1));
                 if (leader && tile + (int)gridDim.x < n_tiles) TB_ISSUE_OP(tile + gridDim.x, it + 1);
             }
-            const uint64_t dA1 = dA1_0 + par * oA1, dA1t = dA1t_0 + par * oA1;
-            const uint64_t dZc = dZc_0 + par * oZc, dZct = dZct_0 + par * oZc;
+            const uint64_t dZ = dZ_0 + par * oZ, dZt = dZt_0 + par * oZ;
             const uint64_t dGy = dGy_0 + par * oGy, dGyt = dGyt_0 + par * oGy;
-            // ---- recompute batch: the compute warps produced these operands while the previous tile's gradient MMAs ran ----
-            mbar_wait(barA, phA);
-            phA ^= 1u;
-            if (ophist) mbar_wait(barO + (it & 1), (uint32_t)((it >> 1) & 1));
+            // ---- recompute batch ----
+            mbar_wait(barO + (it & 1), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             if (leader) {
-                if (NS == 2) {
-#pragma unroll 4
-                    for (int ks = 0; ks < kcsteps; ++ks)
-                        umma_ss(tmem_base + TB_DC, dZc + (uint64_t)(ks * (2048 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
-                    umma_commit(barM1);
-                }
 #pragma unroll 5
                 for (int ks = 0; ks < k1steps; ++ks)
-                    umma_ss(tmem_base + TB_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
+                    umma_ss(tmem_base + TB_D1, dZ + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, id_fc, ks > 0);
             }
             mbar_wait(barG, phG);                              // Gy written, stage consumed
             phG ^= 1u;
@@ -370,18 +305,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             tc_fence_after();
             if (leader) {
                 umma_ss(tmem_base + TB_D3, dGy, dB2d, id_fc, false);
-                if (NS == 1) umma_commit(barM2);
-            }
-            if (NS == 2) {
-                mbar_wait(barB, phB);
-                phB ^= 1u;
-                tc_fence_after();
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(tmem_base + TB_D1, dU + (uint64_t)(ks * (4096 >> 4)), dDcB + (uint64_t)(ks * (256 >> 4)), id_fc_bmn, true);
-                    umma_commit(barM2);
-                }
+                umma_commit(barM2);
             }
             mbar_wait(barC, phC);                              // H, Ga written; D1 / D3 consumed
             phC ^= 1u;
@@ -389,37 +313,27 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             if (leader) {
                 // g_z first (the compute warps wait for it), weight gradients behind it in the same batch
 #pragma unroll 8
-                for (int ks = 0; ks < kfsteps; ++ks)           // D6 = Ga . W1h  (g_z of the fine scale)
+                for (int ks = 0; ks < kfsteps; ++ks)           // D6 = Ga . W1h  (g_z)
                     umma_ss(tmem_base + TB_D3, dGa + (uint64_t)(ks * (4096 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
-                if (NS == 2) {
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {           // GaU = U^T . Ga
-                        const uint64_t o = (uint64_t)(ks * (256 >> 4));
-                        umma_ss(tmem_base + TB_DC, dUt + o, dGat + o, id_fc_mn, ks > 0);
-                    }
-                }
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {               // 16 cells per instruction
                     const uint64_t o = (uint64_t)(ks * (256 >> 4));
                     umma_ss(tmem_base + TB_D4, dHt + o, dGyt + o, id_w2, !(first && ks == 0));
-                    umma_ss(tmem_base + TB_D5, dGat + o, dA1t + o, id_w1, !(first && ks == 0));
+                    umma_ss(tmem_base + TB_D5, dGat + o, dZt + o, id_w1, !(first && ks == 0));
                 }
                 umma_commit(barM3);
             }
             first = false;
             if (NS == 2) {
-                mbar_wait(barD, phD);                          // GaU (bf16) written
+                mbar_wait(barD, phD);                          // D6b (bf16) written
                 phD ^= 1u;
                 tc_fence_after();
                 if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {           // D5[:, perception columns] += GaU^T . Zc
+                    for (int ks = 0; ks < 8; ++ks) {           // D7 = U^T . D6b  (g_z on the coarse footprint), 16 cells per instruction
                         const uint64_t o = (uint64_t)(ks * (256 >> 4));
-                        umma_ss(tmem_base + TB_D5, dGaUt + o, dZct + o, id_w1c, true);
+                        umma_ss(tmem_base + TB_D3 + 64u, dUt + o, dD6bt + o, id_c, ks > 0);
                     }
-#pragma unroll 8
-                    for (int ks = 0; ks < kfsteps; ++ks)       // D7 = GaU . W1h  (g_z on the coarse footprint)
-                        umma_ss(tmem_base + TB_D3 + 64u, dGaU + (uint64_t)(ks * (2048 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
                     umma_commit(barM4);
                 }
             }
@@ -430,7 +344,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t row_off = (uint32_t)r * 16u;
         const int py = r >> 4, px = r & 15;
-        uint32_t phM1 = 0, phM2 = 0, phM3 = 0, phM4 = 0, phT = 0;
+        uint32_t phM2 = 0, phM3 = 0, phM4 = 0, phT = 0;
         float b2acc[4] = {0.f, 0.f, 0.f, 0.f};
         // zero pads of the fine planes: rows 0 and 9 (columns 4..23 as float4) and columns 4 / 21 of rows 1..8 (a scalar
         // pair): 3*C planes x 18 items over 512 threads = at most 2 items per thread, offsets (in floats) fixed for the launch
@@ -446,69 +360,23 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             zoff[q] = o;
         }
-        // CPE rows / columns (warp 15) and fire decisions (warp 14) of a tile, double buffered over tiles
+        // fire decisions (warp 14) of a tile, double buffered over tiles
         auto tables = [&](int tile_, int buf_) {
-            if (warp < 14) return;
+            if (warp != 14 || a.fm.supplied) return;
             int tb_, ty_, tx_;
             t2_tile_decode(a.tl, tile_, tb_, ty_, tx_);
-            if (g.cond_kind == NCA_COND_CPE && warp == 15 && lane < T2_TH + T2_TW) {
-                const float raw_ = lane < T2_TH ? dynca_cpe(ty_ + lane, H, g.cpe_oh) : dynca_cpe(tx_ + lane - T2_TH, W, g.cpe_ow);
-                const __nv_bfloat16 hi_ = __float2bfloat16_rn(raw_), lo_ = __float2bfloat16_rn(raw_ - __bfloat162float(hi_));
-                sCpe2[buf_ * 24 + lane] = (uint32_t)__bfloat16_as_ushort(hi_) | ((uint32_t)__bfloat16_as_ushort(lo_) << 16);
-            }
-            if (!a.fm.supplied && warp == 14) t2_fire_tile(a.fm, tb_, ty_, tx_, H, W, lane, sFire2 + buf_ * 128);
+            t2_fire_tile(a.fm, tb_, ty_, tx_, H, W, lane, sFire2 + buf_ * 128);
         };
-        // ---- P1 of a tile: perception operands A1 / Zc (-> barrier A), g = dL/dx_{t+1} and Gy (-> barrier G).
-        //      Runs for tile i+1 while the gradient MMAs of tile i are in flight.  itn = iteration index of that tile. ----
-        // p1a: stage wait, border patch, fine perception -> A1, cond chunk.   p1b: coarse perception -> Zc (-> A), Gy (-> G).
-        auto p1a = [&](int b, int y0, int x0, int itn) {
-            const int gy = y0 + py, gx = x0 + px;
-            const bool inimg = gy < H && gx < W;
-            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
-                                (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
-            if (ophist) return;                              // A1 / Zc arrive from the operand history (the MMA warp waits for them)
-            uint8_t* sA1 = sA12 + (uint32_t)(itn & 1) * bg.a1_bytes;
-            const uint32_t* sCpe = sCpe2 + (itn & 1) * 24;
-            mbar_wait(barT, phT);
-            phT ^= 1u;
-            if (border && g.pad != NCA_PAD_CONSTANT) {
-                t2_patch_border<NS, TB_NCOMP>(g, a.x_in, a.xc_in, b, y0, x0, sX, sXc);
-                bar_sync_n(1, TB_NCOMP);
-            }
-            t2_fine_to_a1<16>(sX, sA1, C, bg.npairs, warp, lane);
-            if (qtr == 0) {
-                uint4 cv;
-                if (g.cond_kind == NCA_COND_CPE) {
-                    const uint32_t ry = sCpe[py], cx = sCpe[T2_TH + px];
-                    cv = make_uint4((ry & 0xffffu) | (cx << 16), 0x3F803F80u, (ry >> 16) | (cx & 0xffff0000u), 0u);
-                    if (!inimg) cv = make_uint4(0, 0, 0, 0);      // rows of A1 are summed over cells by the weight-gradient MMA
-                } else {
-                    cv = g.cond_kind == NCA_COND_TENSOR ? t2_cond_chunk_smem(g, sCond, r, inimg) : dynca_cond_chunk(g, a.cond, b, gy, gx, inimg);
-                }
-                *reinterpret_cast<uint4*>(sA1 + (uint32_t)bg.npairs * 2048u + row_off) = cv;
-            } else if (qtr == 1) {
-                for (int ch = bg.npairs + 1; ch < bg.K1 / 8; ++ch)
-                    *reinterpret_cast<uint4*>(sA1 + (uint32_t)ch * 2048u + row_off) = make_uint4(0, 0, 0, 0);
-            }
-        };
+        // ---- P1 of a tile: g = dL/dx_{t+1} and Gy (-> barrier G).  Runs for tile i+1 while the gradient MMAs of tile i are in
+        //      flight.  itn = iteration index of that tile. ----
         auto p1b = [&](int tile_, int b, int y0, int x0, int itn, float (&gn)[4]) {
             const int gy = y0 + py, gx = x0 + px;
             const bool inimg = gy < H && gx < W;
-            const bool border = y0 == 0 || x0 == 0 || y0 + T2_TH >= H || x0 + T2_TW >= W ||
-                                (NS == 2 && (y0 + T2_TH + 4 > H || x0 + T2_TW + 4 > W));
             const int par = itn & 1;
-            uint8_t* sZc = sZc2 + (uint32_t)par * 8192u;
             uint8_t* sGy = sGy2 + (uint32_t)par * 4096u;
             const float* sFire = sFire2 + par * 128;
-            if (ophist) {                                     // the gradient stage is this phase's only input
-                mbar_wait(barT, phT);
-                phT ^= 1u;
-            } else if (NS == 2) {
-                t2_coarse_to_zc<16>(g, sXc, sZc, bg.npairs, y0, x0, border, tid, warp, lane);
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(barA);
+            mbar_wait(barT, phT);                             // the gradient stage is this phase's only input
+            phT ^= 1u;
             // g of this thread's 4 channels (+ coarse part, + tap); g_y = fire * g -> Gy
             {
                 const float fire = a.fm.supplied ? (inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f) : sFire[r];
@@ -553,32 +421,6 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barG);
-        };
-
-        // ---- Dc (rows 0..63) -> bf16 -> DcB [N = fc][K = coarse cell], MN-major, for the tile whose operands were produced last:
-        //      runs one tile ahead (before the coarse transposed stencil of the current tile), so that U . DcB and with it D1 are
-        //      complete when the next tile starts ----
-        auto dc_roundtrip = [&]() {
-            mbar_wait(barM1, phM1);
-            phM1 ^= 1u;
-            tc_fence_after();
-            if ((warp & 3) < 2 && 32 * qtr < fc) {
-                uint32_t v[32];
-                tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)qtr, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    uint4 o;
-                    o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                    o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                    o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                    o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                    *reinterpret_cast<uint4*>(sDcB + (uint32_t)(4 * qtr + qq) * 1024u + row_off) = o;
-                }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(barB);
         };
 
         // ---- P6: transposed coarse perception of one tile (coordinates b_, y0_, x0_) -> red.add into the coarse gradient buffer.
@@ -626,9 +468,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         int nb = 0, ny0 = 0, nx0 = 0;      // coordinates of the tile whose operands are produced ahead
         if ((int)blockIdx.x < n_tiles) {
             t2_tile_decode(a.tl, blockIdx.x, nb, ny0, nx0);
-            p1a(nb, ny0, nx0, 0);
             p1b(blockIdx.x, nb, ny0, nx0, 0, gn);
-            if (NS == 2) dc_roundtrip();
         }
 #ifdef NCA_T2_TIMING
 #define TB_STAMP(k_) do { if (a.tdbg && blockIdx.x == 0 && tid == 0 && iter < 8) a.tdbg[iter * 16 + (k_)] = clock64(); } while (0)
@@ -646,10 +486,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             TB_STAMP(0);
             TB_STAMP(2);
             const int next = tile + (int)gridDim.x;
-            if (next < n_tiles) {                              // software pipeline, part 1: in the shadow of D1 / D3
-                t2_tile_decode(a.tl, next, nb, ny0, nx0);
-                p1a(nb, ny0, nx0, iter + 1);
-            }
+            if (next < n_tiles) t2_tile_decode(a.tl, next, nb, ny0, nx0);
             mbar_wait(barM2, phM2);
             phM2 ^= 1u;
             tc_fence_after();
@@ -688,30 +525,10 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             if (next < n_tiles) p1b(next, nb, ny0, nx0, iter + 1, gn_next);
             TB_STAMP(5);
             if (NS == 2 && pend_b >= 0) { p6(pend_b, pend_y0, pend_x0); pend_b = -1; }      // previous tile's coarse stencil, under the MMAs
-            mbar_wait(barM3, phM3);                            // D6, GaU, D4, D5 (fine) complete; H | Ga are free
+            mbar_wait(barM3, phM3);                            // D6, D4, D5 complete; H | Ga are free
             phM3 ^= 1u;
             tc_fence_after();
             TB_STAMP(6);
-            if (NS == 2) {
-                // ---- GaU (rows 0..63) -> bf16 -> [(j/8)*1024 + q*16]: K-major A of D7, MN-major A of the gW1 coarse part ----
-                if ((warp & 3) < 2 && 32 * qtr < fc) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)qtr, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                        o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                        o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                        o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                        *reinterpret_cast<uint4*>(sGaU + (uint32_t)(4 * qtr + qq) * 1024u + row_off) = o;
-                    }
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                mbar_arrive(barD);
-            }
             // ---- E2: D6 -> fp32 planes (overlay H | Ga) ----
             {
 #pragma unroll
@@ -731,6 +548,16 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     uint32_t v[16];
                     tmem_ld16(tmem_lane + TB_D3 + 16u * (uint32_t)qtr, v);
                     tmem_ld_wait();
+                    if (NS == 2) {
+                        // bf16(D6) -> D6b [(k' / 8) * 2048 + cell * 16]: the MN-major B operand of D7 = U^T . D6b
+                        uint4 o0, o1;
+                        o0.x = pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])); o0.y = pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                        o0.z = pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])); o0.w = pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7]));
+                        o1.x = pack_bf16(__uint_as_float(v[8]), __uint_as_float(v[9])); o1.y = pack_bf16(__uint_as_float(v[10]), __uint_as_float(v[11]));
+                        o1.z = pack_bf16(__uint_as_float(v[12]), __uint_as_float(v[13])); o1.w = pack_bf16(__uint_as_float(v[14]), __uint_as_float(v[15]));
+                        *reinterpret_cast<uint4*>(sD6b + (uint32_t)(2 * qtr) * 2048u + row_off) = o0;
+                        *reinterpret_cast<uint4*>(sD6b + (uint32_t)(2 * qtr + 1) * 2048u + row_off) = o1;
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = 4 * qtr + i;
@@ -744,9 +571,14 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         }
                     }
                 }
-                // D6 read: D3's columns are free again as far as this thread is concerned (with own coarse planes D7 is read by
-                // warps 12 / 13 alone, during the fine transposed stencil)
-                if (NS == 1 || (ophist && warp != 12 && warp != 13)) { tc_fence_before(); mbar_arrive(barE); }
+                if (NS == 2) {
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(barD);
+                }
+                // D6 read: D3's columns are free again as far as this thread is concerned (D7 is read by warps 12 / 13 alone,
+                // during the fine transposed stencil)
+                if (NS == 1 || (warp != 12 && warp != 13)) { tc_fence_before(); mbar_arrive(barE); }
             }
             TB_STAMP(7);
             bar_sync_n(1, TB_NCOMP);
@@ -758,10 +590,10 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             //      one vector reduction per row. ----
             {
                 const bool ragged = y0 + T2_TH > H || x0 + T2_TW > W;
-                if (NS == 2 && ophist && (warp == 12 || warp == 13)) {
+                if (NS == 2 && (warp == 12 || warp == 13)) {
                     // ---- D7 (coarse footprint rows 0..59, all N6 columns) -> the persistent coarse planes, by the two warps of
                     //      lane quarters 0 / 1 that have nothing to do in this phase ----
-                    mbar_wait(barM4, phM4);                    // D5 coarse part, D7 complete
+                    mbar_wait(barM4, phM4);                    // D7 complete
                     phM4 ^= 1u;
                     tc_fence_after();
                     const int qy = r / T2_QW, qx = r % T2_QW;
@@ -785,35 +617,6 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                     }
                     tc_fence_before();
                     mbar_arrive(barE);                         // D7 read: D3's columns are free again
-                    if (next < n_tiles) {
-                        // ---- and the NEXT tile's Dc (rows 0..63, all hidden columns) -> bf16 -> DcB: its U . DcB then runs under
-                        //      the rest of this phase, and D1 is complete when the next tile starts ----
-                        mbar_wait(barM1, phM1);
-                        phM1 ^= 1u;
-                        tc_fence_after();
-#pragma unroll 1
-                        for (int q4 = 0; 32 * q4 < fc; ++q4) {
-                            uint32_t v[32];
-                            tmem_ld32(tmem_lane + TB_DC + 32u * (uint32_t)q4, v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int qq = 0; qq < 4; ++qq) {
-                                uint4 o;
-                                o.x = pack_bf16(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1]));
-                                o.y = pack_bf16(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3]));
-                                o.z = pack_bf16(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5]));
-                                o.w = pack_bf16(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7]));
-                                *reinterpret_cast<uint4*>(sDcB + (uint32_t)(4 * q4 + qq) * 1024u + row_off) = o;
-                            }
-                        }
-                        fence_proxy_async();
-                        tc_fence_before();
-                        mbar_arrive(barB);
-                    }
-                } else if (NS == 2 && ophist && next < n_tiles) {
-                    phM1 ^= 1u;                                // this thread skips the Dc wait of the next tile
-                    tc_fence_before();
-                    mbar_arrive(barB);                         // (nothing to contribute to DcB)
                 }
                 if (warp < 12) {
                     const int j = lane & 3;
@@ -914,39 +717,13 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             }
             TB_STAMP(9);
             if (NS == 2) {
-                if (!(ophist && (warp == 12 || warp == 13))) {
-                    mbar_wait(barM4, phM4);                    // D5 coarse part, D7 complete (GaU in shared memory is free)
+                if (warp != 12 && warp != 13) {
+                    mbar_wait(barM4, phM4);                    // D7 complete (D6b in shared memory is free)
                     phM4 ^= 1u;
                     tc_fence_after();
                 }
-                bar_sync_n(1, TB_NCOMP);                       // every P5 read of the fine planes is done; own coarse planes: written
+                bar_sync_n(1, TB_NCOMP);                       // every P5 read of the fine planes is done; coarse planes: written
                 TB_STAMP(10);
-                if (!ophist) {
-                    // ---- D7 -> coarse planes (zero padded [10][14], footprint cell (qy,qx) at [qy+2][qx+2]), over the fine planes ----
-                    for (int i = tid; i < 3 * C * TB_CPP / 2; i += TB_NCOMP) reinterpret_cast<float2*>(sCPX)[i] = make_float2(0.f, 0.f);
-                    bar_sync_n(1, TB_NCOMP);
-                    if ((warp & 3) < 2 && 16 * qtr < N6) {      // warp-uniform: the TMEM load is .sync.aligned
-                        uint32_t v[16];
-                        const int qy = r / T2_QW, qx = r % T2_QW;
-                        tmem_ld16(tmem_lane + TB_D3 + 64u + 16u * (uint32_t)qtr, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int c = 4 * qtr + i;
-                            if (c < C && r < T2_QH * T2_QW) {
-                                const int o = (c * TB_CPR + qy + 2) * TB_CPS + qx + 2;
-                                const float lp = __uint_as_float(v[4 * i + 3]);
-                                sCPX[o] = __uint_as_float(v[4 * i + 1]);
-                                sCPX[C * TB_CPP + o] = __uint_as_float(v[4 * i + 2]);
-                                sCPX[2 * C * TB_CPP + o] = lp;
-                                sCCtr[(c * T2_QH + qy) * T2_QW + qx] = fmaf(-16.0f, lp, __uint_as_float(v[4 * i + 0]));
-                            }
-                        }
-                    }
-                    tc_fence_before();
-                    mbar_arrive(barE);                             // D7 read: D3's columns are free again
-                    bar_sync_n(1, TB_NCOMP);
-                }
                 const int Hc = H >> 1, Wc = W >> 1;
                 const int cy0 = (y0 >> 1) - 1, cx0 = (x0 >> 1) - 1;          // coarse coordinates of footprint cell (0,0)
                 if (border) {
@@ -983,10 +760,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         bar_sync_n(1, TB_NCOMP);
                     }
                 }
-                if (!ophist && next < n_tiles) dc_roundtrip();      // next tile's DcB: its U . DcB runs under the coarse stencil below
                 TB_STAMP(11);
-                if (ophist) { pend_b = b; pend_y0 = y0; pend_x0 = x0; }      // deferred into the next tile's MMA wait
-                else p6(b, y0, x0);
+                pend_b = b; pend_y0 = y0; pend_x0 = x0;        // the coarse transposed stencil is deferred into the next tile's MMA wait
             }
             TB_STAMP(12);
             bar_sync_n(1, TB_NCOMP);     // the planes overlay H | Ga, which the next tile's E1 writes
@@ -1071,10 +846,10 @@ bool dynca_tc2_bwd_supported(const DyncaGeom& g) {
     Bf16Geom bg;
     if (!dynca_tc2_supported(g)) return false;
     if (dynca_bf16_geom(g, &bg)) return false;
-    return tb_smem(g, bg, false).total <= 227u * 1024u && tb_smem(g, bg, true).total <= 227u * 1024u;
+    return tb_smem(g, bg).total <= 227u * 1024u;
 }
 
-// operand images: [forward block of dynca_tc2_prep_weights (B1 | B2 | b2 | U)] then B2d
+// operand images: [forward block of dynca_tc2_prep_weights (B1 | B2 | b2 | U | I)] then B2d
 size_t dynca_tc2_bwd_weight_bytes(const DyncaGeom& g) {
     const size_t f = dynca_tc2_weight_bytes(g);
     return f ? f + nca_align_up((size_t)(g.fc / 8) * 256, 256) : 0;
@@ -1104,16 +879,16 @@ int dynca_tc2_add_coarse(const DyncaGeom& g, const float* gc, float* gx, cudaStr
     return NCA_OK;
 }
 
-int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const DyncaTc2Maps* xm, int slot_in, const float* x_in,
-                            int cslot_in, const float* xc_in, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
-                            int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out,
-                            const float* cond, const FireMask& fm, cudaStream_t s, int pdl, const uint8_t* op_in) {
+int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, const DyncaTc2Maps* gm, float* g_in, float* gc_in, int zero_in,
+                            int zero_cin, const float* g_tap, int tap_c, float tap_scale, float* g_out, float* gc_out, const FireMask& fm,
+                            cudaStream_t s, int pdl, const uint8_t* op_in) {
     T2BwdArgs a;
     a.pdl = pdl;
     a.op_in = op_in;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
-    a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.slot_in = slot_in; a.cslot_in = cslot_in;
+    if (op_in == nullptr) { nca_set_error("the tcgen05 BPTT step needs the recorded perception operand of the step"); return NCA_ERR_ARG; }
+    a.g = g;
     a.g_in = g_in; a.gc_in = gc_in; a.zero_in = zero_in; a.zero_cin = zero_cin;
     a.g_tap = g_tap; a.tap_c = tap_c; a.tap_scale = tap_scale; a.g_out = g_out; a.gc_out = gc_out;
     a.B1 = (const __nv_bfloat16*)ws;
@@ -1126,25 +901,20 @@ int dynca_tc2_backward_step(const DyncaGeom& g, const void* ws, float* wsG, cons
     const bool timing = getenv("NCA_T2_TDBG") != nullptr;
     if (timing && !tdbg) cudaMalloc(&tdbg, 160 * sizeof(long long));
     a.tdbg = timing ? tdbg : nullptr;
-    const size_t smem = tb_smem(g, a.bg, op_in != nullptr).total;
+    const size_t smem = tb_smem(g, a.bg).total;
     int grid = t2_num_sms();
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
-    const CUtensorMap* tx = (const CUtensorMap*)xm->x;
-    const CUtensorMap* txc = (const CUtensorMap*)xm->xc;
     const CUtensorMap* tg = (const CUtensorMap*)gm->x;
     const CUtensorMap* tgc = (const CUtensorMap*)gm->xc;
-    const CUtensorMap* tcn = (const CUtensorMap*)xm->cond;
-#define TB_LAUNCH(NS_, OPH_, CT_, FT_)                                                                                        \
+#define TB_LAUNCH(NS_, CT_, FT_)                                                                                              \
     do {                                                                                                                      \
-        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<NS_, OPH_, CT_, FT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<NS_, OPH_, CT_, FT_>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tg, *tgc, *tcn, a)); \
+        NCA_CUDA_OK(cudaFuncSetAttribute(dynca_bwd_tc2_kernel<NS_, CT_, FT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        NCA_CUDA_OK(t2_launch(dynca_bwd_tc2_kernel<NS_, CT_, FT_>, grid, TB_NTHREADS, smem, s, a.pdl != 0, *tg, *tgc, a));      \
     } while (0)
-    // specialised instantiations: the operand-history kernels of the reference's (C, fc) pairs; everything else is generic
-#define TB_LAUNCH_OPH(CT_, FT_) do { if (g.ns == 2) TB_LAUNCH(2, true, CT_, FT_); else TB_LAUNCH(1, true, CT_, FT_); } while (0)
+    // specialised instantiations for the reference's (C, fc) pairs; everything else is generic
+#define TB_LAUNCH_CF(CT_, FT_) do { if (g.ns == 2) TB_LAUNCH(2, CT_, FT_); else TB_LAUNCH(1, CT_, FT_); } while (0)
     const bool T2_NOSPEC = t2_nospec("NCA_T2_NOSPEC_BWD");
-    if (op_in) T2_DISPATCH_CF(g.C, g.fc, TB_LAUNCH_OPH);
-    else if (g.ns == 2) TB_LAUNCH(2, false, 0, 0);
-    else TB_LAUNCH(1, false, 0, 0);
+    T2_DISPATCH_CF(g.C, g.fc, TB_LAUNCH_CF);
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps
         long long h[160];
