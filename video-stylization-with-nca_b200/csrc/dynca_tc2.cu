@@ -32,7 +32,6 @@ struct T2FwdArgs {
     FireMask fm;
     T2Tiles tl;
     uint8_t* op_out;   // operand history of this step (Z of every tile, for the BPTT) or NULL
-    int ops_only;      // record the operand and stop (no MLP, no state written): the BPTT's recompute path
     const __nv_bfloat16* Iz;   // identity operand [64][64] (two scales)
     int dbg;
     int pdl;           // launch with the programmatic-serialization attribute (not the first step of a call)
@@ -66,7 +65,8 @@ __host__ __device__ static inline T2Smem t2_smem(const DyncaGeom& g, const Bf16G
 
 #define T2_NTHREADS 288     // 8 compute warps + 1 MMA / TMA warp
 
-template <int NS, int CT, int FT>
+// OPS: record the perception operand and stop (no MLP, no state written): the BPTT's recompute path, generic geometry only
+template <int NS, int CT, int FT, bool OPS>
 __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                      const __grid_constant__ CUtensorMap tm_xc,
                                                                      const __grid_constant__ CUtensorMap tm_c, const T2FwdArgs a) {
@@ -190,6 +190,15 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
             phA ^= 1u;
             tc_fence_after();
             T2_MSTAMP(1);
+            auto gemm1 = [&]() {      // D1 = (A1 | Z) . W1h^T, then the operand-history copy of the operand (one bulk copy per tile)
+                if (!OPS) {
+#pragma unroll 5
+                    for (int ks = 0; ks < k1steps; ++ks)
+                        umma_ss(tmem_base + TM_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
+                    umma_commit(barM);
+                }
+                if (a.op_out) bulk_store(a.op_out + (size_t)tile * op_bytes, sA1, op_bytes);
+            };
             if (leader) {
                 if (NS == 2) {
                     // ... + A1 . I: the fine perception joins the accumulator exactly (bf16 x 1 in fp32)
@@ -197,6 +206,8 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
                     for (int ks = 0; ks < kzsteps; ++ks)
                         umma_ss(tmem_base + TM_DC, dA1 + (uint64_t)(ks * (4096 >> 4)), dIz + (uint64_t)(ks * (2048 >> 4)), idescZ, true);
                     umma_commit(barM);
+                } else {
+                    gemm1();
                 }
                 if (tile + (int)gridDim.x < n_tiles) T2_ISSUE_TMA(tile + gridDim.x);     // the stage is free
             }
@@ -206,24 +217,13 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
                 phB ^= 1u;
                 tc_fence_after();
                 T2_MSTAMP(3);
+                if (leader) gemm1();
             }
-            if (leader) {
-                if (!a.ops_only) {
-#pragma unroll 5
-                    for (int ks = 0; ks < k1steps; ++ks)
-                        umma_ss(tmem_base + TM_D1, dA1 + (uint64_t)(ks * (4096 >> 4)), dB1 + (uint64_t)ks * sB1k, idesc1, ks > 0);
-                    umma_commit(barM);
-                }
-                // operand history: the perception operand of this tile goes to global memory as one bulk copy, so that the BPTT
-                // loads it instead of recomputing the perception
-                if (a.op_out) bulk_store(a.op_out + (size_t)tile * op_bytes, sA1, op_bytes);
-                if (a.ops_only) {
-                    bulk_store_wait_read();
-                    mbar_arrive(barM);                          // the operand buffer is free (no MMA reads it in this mode)
-                    continue;
-                }
+            if (leader && OPS) {
+                bulk_store_wait_read();
+                mbar_arrive(barM);                              // the operand buffer is free (no MMA reads it in this mode)
             }
-            if (a.ops_only) continue;
+            if (OPS) continue;
             T2_MSTAMP(4);
             mbar_wait(barC, phC);
             phC ^= 1u;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(T2_NTHREADS, NS == 2 ? 2 : 4) dynca_fwd_tc2_ke
                 tc_fence_before();
                 mbar_arrive(barB);                             // ---- B: Z complete ----
             }
-            if (a.ops_only) {                                  // the operand is recorded by the MMA warp; wait until the buffer is free again
+            if (OPS) {                                  // the operand is recorded by the MMA warp; wait until the buffer is free again
                 mbar_wait(barM, phM);
                 phM ^= 1u;
                 continue;
@@ -540,7 +540,6 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     T2FwdArgs a;
     a.pdl = pdl;
     a.op_out = op_out;
-    a.ops_only = ops_only;
     int rc = dynca_bf16_geom(g, &a.bg);
     if (rc) return rc;
     a.g = g; a.cond = cond; a.x_in = x_in; a.xc_in = xc_in; a.x_out = x_out; a.xc_out = xc_out;
@@ -567,28 +566,30 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     const CUtensorMap* tcn = (const CUtensorMap*)m->cond;
     // (function attributes are per device and the launchers run on several threads: the cache is per device, under a mutex)
     static std::mutex occ_mu;
-    static size_t occ_smem_dev[NCA_MAX_DEVICES][8];
-    static int occ_val_dev[NCA_MAX_DEVICES][8];
+    static size_t occ_smem_dev[NCA_MAX_DEVICES][10];
+    static int occ_val_dev[NCA_MAX_DEVICES][10];
     const bool T2_NOSPEC = t2_nospec("NCA_T2_NOSPEC_FWD");
     const int spec = T2_NOSPEC ? 0 : ((g.C == 16 && g.fc == 128) ? 1 : ((g.C == 12 && g.fc == 96) ? 2 : ((g.C == 13 && g.fc == 96) ? 3 : 0)));
-    const int oi = (g.ns == 2 ? 4 : 0) + spec;
+    const int oi = ops_only ? 8 + (g.ns == 2 ? 1 : 0) : (g.ns == 2 ? 4 : 0) + spec;
     const int dev = nca_device_ordinal() % NCA_MAX_DEVICES;
     std::unique_lock<std::mutex> occ_lock(occ_mu);
     size_t* const occ_smem = occ_smem_dev[dev];
     int* const occ_val = occ_val_dev[dev];
     if (occ_val[oi] == 0 || occ_smem[oi] != smem) {
         int o = 0;
-#define T2F_ATTR(CT_, FT_)                                                                                                          \
+#define T2F_ATTR(CT_, FT_, OPS_)                                                                                                    \
     do {                                                                                                                            \
         if (g.ns == 2) {                                                                                                            \
-            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2, CT_, FT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<2, CT_, FT_>, T2_NTHREADS);                                               \
+            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<2, CT_, FT_, OPS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<2, CT_, FT_, OPS_>, T2_NTHREADS);                                         \
         } else {                                                                                                                    \
-            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1, CT_, FT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<1, CT_, FT_>, T2_NTHREADS);                                               \
+            NCA_CUDA_OK(cudaFuncSetAttribute(dynca_fwd_tc2_kernel<1, CT_, FT_, OPS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            o = t2_occupancy_by_regs(dynca_fwd_tc2_kernel<1, CT_, FT_, OPS_>, T2_NTHREADS);                                         \
         }                                                                                                                           \
     } while (0)
-        T2_DISPATCH_CF(g.C, g.fc, T2F_ATTR);
+#define T2F_ATTR_STEP(CT_, FT_) T2F_ATTR(CT_, FT_, false)
+        if (ops_only) T2F_ATTR(0, 0, true);
+        else T2_DISPATCH_CF(g.C, g.fc, T2F_ATTR_STEP);
         const int by_smem = (int)((227 * 1024) / (smem + 1024));
         if (o > by_smem) o = by_smem;
         occ_val[oi] = o < 1 ? 1 : o;
@@ -601,12 +602,14 @@ int dynca_tc2_forward_step(const DyncaGeom& g, const void* ws, const DyncaTc2Map
     if (occ < 1) occ = 1;
     int grid = t2_num_sms() * occ;
     if (grid > a.tl.n_tiles) grid = a.tl.n_tiles;
-#define T2F_LAUNCH(CT_, FT_)                                                                                                        \
+#define T2F_LAUNCH(CT_, FT_, OPS_)                                                                                                  \
     do {                                                                                                                            \
-        if (g.ns == 2) NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<2, CT_, FT_>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a)); \
-        else NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<1, CT_, FT_>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a)); \
+        if (g.ns == 2) NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<2, CT_, FT_, OPS_>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a)); \
+        else NCA_CUDA_OK(t2_launch(dynca_fwd_tc2_kernel<1, CT_, FT_, OPS_>, grid, T2_NTHREADS, smem, s, a.pdl != 0, *tx, *txc, *tcn, a)); \
     } while (0)
-    T2_DISPATCH_CF(g.C, g.fc, T2F_LAUNCH);
+#define T2F_LAUNCH_STEP(CT_, FT_) T2F_LAUNCH(CT_, FT_, false)
+    if (ops_only) T2F_LAUNCH(0, 0, true);
+    else T2_DISPATCH_CF(g.C, g.fc, T2F_LAUNCH_STEP);
     NCA_LAUNCH_OK();
     if (timing) {      // debug only: synchronous dump of CTA 0's phase timestamps (cycles since the tile's first stamp)
         long long h[256];
