@@ -391,7 +391,7 @@ def main():
     else:
         roof = {"bound": "hbm", "achieved": ach_gb, "peak": hbm, "unit": "GB/s", "frac": fr["frac"]}
     variant = Fn.dynca_kernel_variant(cfg, B, H, W, backward=True)
-    kname = {0: "dynca_bwd_f32_kernel<2>", 1: "dynca_bwd_bf16_kernel<2, false>", 2: "dynca_bwd_tc2_kernel<2, true>",
+    kname = {0: "dynca_bwd_f32_kernel<2>", 1: "dynca_bwd_bf16_kernel<2, false>", 2: "dynca_bwd_tc2_kernel<2>",
              3: "dynca_bwd_bf16_kernel<2, true>"}[variant]
     traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")

@@ -94,9 +94,10 @@ int nca_edge_extract(int B, int H, int W, const float* img, int tanh_transform, 
  *            [T+1,B,C,H/2,W/2]; the forward writes the 2x2-mean coarse state of every states[t] there so that
  *            nca_dynca_backward does not have to recompute it (pass the same buffer to it)
  *   op_hist: optional (may be NULL), only used when keep_history != 0 and nca_dynca_op_hist_bytes(d, T) != 0: that many
- *            bytes, 16-byte aligned.  The forward records the bf16 perception operands of every tile of every step there
- *            (one bulk copy per tile) so that nca_dynca_backward loads them instead of recomputing the perception: memory
- *            (160-224 B per cell and step) traded for time; results are bit-identical with and without it
+ *            bytes, 16-byte aligned.  The forward records the bf16 perception operand Z of every tile of every step there
+ *            (one bulk copy per tile; with two scales Z = z_fine + up(z_coarse) is ONE operand) so that nca_dynca_backward loads
+ *            it instead of recomputing the perception: memory (128-160 B per cell and step) traded for time; results are
+ *            bit-identical with and without it
  *   workspace: nca_dynca_workspace_bytes(d, 0) bytes                                              */
 int nca_dynca_forward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
                       uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, float* coarse_hist,
@@ -116,8 +117,9 @@ size_t nca_dynca_op_hist_bytes(const NcaDyncaDesc* d, int32_t T);
  *   gx0      : dL/d states[0]  [B,C,H,W] (written)
  *   gw       : weight gradients, reference layout (written)
  *   coarse_hist: NULL or the buffer nca_dynca_forward filled (n_scales == 2)
- *   op_hist  : NULL or the operand history nca_dynca_forward filled for the same d, T
- *   workspace: nca_dynca_workspace_bytes(d, 1) bytes
+ *   op_hist  : NULL or the operand history nca_dynca_forward filled for the same d, T.  NULL: every BPTT step is preceded by
+ *              a launch of the forward kernel that records the operand of states[t] into the workspace and stops
+ *   workspace: nca_dynca_workspace_bytes(d, 1) bytes (includes one step of operands for the NULL case)
  * State gradients are accumulated with red.add (fp32 summation order is not deterministic).          */
 int nca_dynca_backward(const NcaDyncaDesc* d, const NcaDyncaWeights* w, const float* cond, const float* masks,
                        uint64_t seed, int32_t t0, int32_t T, const float* states, const float* coarse_hist,

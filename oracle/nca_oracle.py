@@ -282,39 +282,6 @@ def perceive_coarse(x, mode):
     return torch.cat([xc, _stencil(xc, SOBEL_X, mode), _stencil(xc, SOBEL_Y, mode), _stencil(xc, LAPLACE, mode)], dim=1)
 
 
-def _up2T_tiled_bf16(ga, th=8, tw=16):
-    """Transpose of the x2 bilinear upsample applied tile by tile the way dynca_tc2_bwd.cu does it: every 8x16 tile
-    produces its own partial GaU on the (unclamped) 6x10 coarse footprint in fp32, rounds it to bf16, and only then
-    the rows / columns outside the image fold into the clamped border cells and the tiles add up."""
-    B, J, H, W = ga.shape
-    Hc, Wc = H // 2, W // 2
-
-    def umat(n):       # [n fine, n/2 + 2 extended coarse]: unclamped weights, extended index = coarse index + 1
-        m = torch.zeros(n, n // 2 + 2)
-        for y in range(n):
-            Q = y // 2
-            if y % 2 == 0:
-                m[y, Q] += 0.25
-                m[y, Q + 1] += 0.75
-            else:
-                m[y, Q + 1] += 0.75
-                m[y, Q + 2] += 0.25
-        return m
-
-    Uy, Ux = umat(H), umat(W)
-    out = torch.zeros(B, J, Hc, Wc)
-    for y0 in range(0, H, th):
-        for x0 in range(0, W, tw):
-            t = ga[:, :, y0:y0 + th, x0:x0 + tw]
-            ext = bf16r(torch.einsum("yq,bjyx,xp->bjqp", Uy[y0:y0 + th], t, Ux[x0:x0 + tw]))
-            ext[:, :, 1] += ext[:, :, 0]
-            ext[:, :, Hc] += ext[:, :, Hc + 1]
-            ext[:, :, :, 1] += ext[:, :, :, 0]
-            ext[:, :, :, Wc] += ext[:, :, :, Wc + 1]
-            out += ext[:, :, 1:Hc + 1, 1:Wc + 1]
-    return out
-
-
 def _emu_preact(xr, w1q, b1q, scales, mode, cond, variant):
     """pre-activation a of one step with the rounding points of kernel `variant` (1: dynca_bf16.cu, 2: dynca_tc2.cu).
     Returns (a, zp, zq): zp = fp32 perception that autograd can differentiate, zq = the rounded GEMM operand the

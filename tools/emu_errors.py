@@ -1,4 +1,4 @@
-"""debug: per-case kernel variants and emulator errors of the tcgen05 path (usage: dbg_emu.py [T] [case ...])"""
+"""Per-case kernel variants and errors of the tcgen05 path against the rounding-point emulator (usage: emu_errors.py [T] [case ...])"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
