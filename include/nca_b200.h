@@ -178,8 +178,8 @@ typedef struct NcaEncWeightGrads {
 int nca_enc_forward(const NcaEncDesc* d, const NcaEncWeights* w, const float* goal, const float* masks,
                     uint64_t seed, int32_t t0, int32_t T, int32_t keep_history, float* states, uint8_t* life_hist,
                     void* workspace, size_t workspace_bytes, void* stream);
-/* BPTT through nca_enc_forward's T steps. g_goal [B,C,H,W] = dL/d goal (consumed by the ImageEncoder,
- * EncoderConditioning/encoder.py, which stays in PyTorch); gx0, g_goal and gw are written. */
+/* BPTT through nca_enc_forward's T steps. g_goal [B,C,H,W] = dL/d goal (consumed by nca_encoder_backward below, the
+ * weight-gradient pass of the ImageEncoder, EncoderConditioning/encoder.py); gx0, g_goal and gw are written. */
 int nca_enc_backward(const NcaEncDesc* d, const NcaEncWeights* w, const float* goal, const float* masks,
                      uint64_t seed, int32_t t0, int32_t T, const float* states, const uint8_t* life_hist,
                      const float* g_final, float* gx0, float* g_goal, const NcaEncWeightGrads* gw,
