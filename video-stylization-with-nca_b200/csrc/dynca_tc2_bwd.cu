@@ -377,6 +377,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             const float* sFire = sFire2 + par * 128;
             mbar_wait(barT, phT);                             // the gradient stage is this phase's only input
             phT ^= 1u;
+#ifdef NCA_T2_TIMING
+            if (a.tdbg && blockIdx.x == 0 && tid == 0 && itn >= 1 && itn <= 8) a.tdbg[(itn - 1) * 16 + 14] = clock64();
+#endif
             // g of this thread's 4 channels (+ coarse part, + tap); g_y = fire * g -> Gy
             {
                 const float fire = a.fm.supplied ? (inimg ? a.fm.supplied[((size_t)b * H + gy) * W + gx] : 0.0f) : sFire[r];
@@ -418,6 +421,9 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (tile_ + (int)gridDim.x < n_tiles) tables(tile_ + gridDim.x, (itn + 1) & 1);
+#ifdef NCA_T2_TIMING
+            if (a.tdbg && blockIdx.x == 0 && tid == 0 && itn >= 1 && itn <= 8) a.tdbg[(itn - 1) * 16 + 15] = clock64();
+#endif
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barG);
