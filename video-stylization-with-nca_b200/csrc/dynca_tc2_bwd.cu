@@ -28,6 +28,7 @@
 #define TB_NTHREADS 544
 #define TB_HDR 2048u
 // TMEM columns
+#define TB_GA 0u      // bf16 Ga (packed pairs, 64 columns): the A operand of D6, read from tensor memory
 #define TB_D1 128u
 #define TB_D3 256u    // D3, later D6 (256..) and D7 (320..)
 #define TB_D4 384u
@@ -241,7 +242,6 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
         const uint64_t dHt = umma_desc(smem_u32(sH), 128u, 2048u), dGat = umma_desc(smem_u32(sGa), 128u, 2048u);
         const uint64_t dUt = umma_desc(smem_u32(sU), 128u, 2048u);                    // U^T: [M = coarse cell][K = cell]
         const uint64_t dD6bt = umma_desc(smem_u32(sD6b), 128u, 2048u);                // bf16(D6) as [N = k'][K = cell]
-        const uint64_t dGa = umma_desc(smem_u32(sGa), 2048u, 128u);
         const uint64_t dB1t = umma_desc(smem_u32(sB1), 128u, lbo_b1);                 // B1 as [N = k'][K = hidden]
         // double-buffered operands: descriptor of buffer 1 = descriptor of buffer 0 + (bytes >> 4)
         const uint64_t dZ_0 = umma_desc(smem_u32(sZ2), 2048u, 128u), dZt_0 = umma_desc(smem_u32(sZ2), 128u, 2048u);
@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
             if (leader) {
                 // g_z first (the compute warps wait for it), weight gradients behind it in the same batch
 #pragma unroll 8
-                for (int ks = 0; ks < kfsteps; ++ks)           // D6 = Ga . W1h  (g_z)
-                    umma_ss(tmem_base + TB_D3, dGa + (uint64_t)(ks * (4096 >> 4)), dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
+                for (int ks = 0; ks < kfsteps; ++ks)           // D6 = Ga . W1h  (g_z), Ga from tensor memory
+                    umma_ts(tmem_base + TB_D3, tmem_base + TB_GA + 8u * (uint32_t)ks, dB1t + (uint64_t)(ks * (256 >> 4)), id_gz, ks > 0);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {               // 16 cells per instruction
                     const uint64_t o = (uint64_t)(ks * (256 >> 4));
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                 // is consumed as it is produced instead of being parked in predicate bits
 #pragma unroll
                 for (int hp = 0; hp < 2; ++hp) {
-                    uint32_t av[16], gv[16];
+                    uint32_t av[16], gv[16], ga8[8];
                     tmem_ld16(tmem_lane + TB_D1 + 32u * (uint32_t)qtr + 16u * (uint32_t)hp, av);
                     tmem_ld16(tmem_lane + TB_D3 + 32u * (uint32_t)qtr + 16u * (uint32_t)hp, gv);
                     tmem_ld_wait();
@@ -520,9 +520,13 @@ __global__ void __launch_bounds__(TB_NTHREADS, 1) dynca_bwd_tc2_kernel(const __g
                         p.w = pack_bf16(__uint_as_float(gv[qq * 8 + 6]), __uint_as_float(gv[qq * 8 + 7])) & bf16x2_nz_mask(o.w);
                         *reinterpret_cast<uint4*>(sH + (uint32_t)(4 * qtr + 2 * hp + qq) * 2048u + row_off) = o;
                         *reinterpret_cast<uint4*>(sGa + (uint32_t)(4 * qtr + 2 * hp + qq) * 2048u + row_off) = p;
+                        ga8[4 * qq + 0] = p.x; ga8[4 * qq + 1] = p.y; ga8[4 * qq + 2] = p.z; ga8[4 * qq + 3] = p.w;
                     }
+                    // the same 16 hidden units as the A operand of D6 = Ga . W1h in tensor memory (no shared-memory fetch for it)
+                    tmem_st8(tmem_lane + TB_GA + 16u * (uint32_t)qtr + 8u * (uint32_t)hp, ga8);
                 }
             }
+            tmem_st_wait();
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(barC);
