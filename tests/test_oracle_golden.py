@@ -96,3 +96,34 @@ def test_image_encoder_oracle_matches_reference_golden():
     for p, k in zip(ps, ("w1", "b1", "w2")):
         assert rel_err(p.grad, t["g_" + k]) < 2e-5, k
     assert rel_err(O.gaussian_kernel5(), t["gauss"][0, 0]) < 1e-6
+
+
+def test_bf16_yardsticks_are_consistent_on_two_scales():
+    """The two bf16 yardsticks of the tcgen05 path on a two-scale case (the reference's perceive_multiscale sum, dynca.py:99-111):
+    the rounding-point emulator (z_fine, z_coarse, then their sum Z rounded; dynca_tc2.cu) must stay within bf16 noise of the
+    bf16-operand oracle stated from the math (Z rounded once), and both within the 1e-2 BF16 bar of the fp32 oracle."""
+    g = torch.Generator().manual_seed(5)
+    B, C, fc, H, W, T = 1, 8, 32, 16, 16, 2
+    w1 = torch.randn(fc, 4 * C, generator=g) * 0.1
+    b1 = torch.randn(fc, generator=g) * 0.05
+    w2 = torch.randn(C, fc, generator=g) * 0.05
+    b2 = torch.zeros(C)
+    x0 = torch.rand(B, C, H, W, generator=g) - 0.5
+    masks = (torch.rand(T, B, 1, H, W, generator=g) + 0.5).floor()
+    cf = torch.randn(B, C, H, W, generator=g)
+    fe, ge, _ = O.dynca_bf16emu_rollout_grads(x0, w1, b1, w2, b2, masks, (0, 1), "circular", None, cf, {}, 2, 2)
+    fq = O.dynca_rollout_bf16ops(x0, w1, b1, w2, b2, masks, (0, 1), "circular", None)
+    f32 = x0
+    for t in range(T):
+        f32 = O.dynca_step(f32, w1, b1, w2, b2, masks[t], (0, 1), "circular", None)
+    assert rel_err(fe, fq) < 5e-3
+    assert rel_err(fe, f32) < 1e-2 and rel_err(fq, f32) < 1e-2
+    # gradients of the emulator against fp32 autograd: bf16-level agreement (relu flips included)
+    xs = x0.clone().requires_grad_(True)
+    ps = [p.clone().requires_grad_(True) for p in (w1, b1, w2, b2)]
+    f = xs
+    for t in range(T):
+        f = O.dynca_step(f, ps[0], ps[1], ps[2], ps[3], masks[t], (0, 1), "circular", None)
+    gs = torch.autograd.grad((f * cf).sum(), [xs] + ps)
+    for a, n in zip(gs, ("x0", "w1", "b1", "w2", "b2")):
+        assert float((ge[n] - a).norm() / (a.norm() + 1e-30)) < 1e-1, n
